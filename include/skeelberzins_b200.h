@@ -1,0 +1,198 @@
+/*
+ * skeelberzins_b200.h -- C ABI of the B200-native batched Skeel-Berzins solve path.
+ *
+ * This is the drop-in boundary for the internal implicit-Euler / stationary Newton solvers of
+ * SkeelBerzins.jl (reference paths are cited per entry point as file:line relative to the
+ * reference tree).  The host (Julia via ccall, Python via ctypes, or C++) owns the time loop
+ * (reference src/pdepe.jl:90-108) and the Newton loop (src/utils.jl:311-336) and calls the
+ * entry points below once per Newton iteration.  All work runs in hand-written sm_100a CUDA
+ * kernels; there is NO CPU fallback: every compute entry point fails with SB_ERR_CUDA when no
+ * device is present.
+ *
+ * Conventions
+ *   - every function returns an int status: SB_OK (0) or a negative SB_ERR_* code; the text of the
+ *     last error of the calling thread is available from sb_last_error().  Nothing throws.
+ *   - host arrays in the REFERENCE layout: one instance after another, inside an instance node by
+ *     node with the npde components fastest (src/utils.jl:632, src/assembler.jl:21-22):
+ *         u_host[(k*Nx + i)*npde + j]      k = instance, i = mesh node, j = component
+ *   - one sb_ctx per GPU; a context is not thread-safe, distinct contexts are independent.
+ *   - calls are asynchronous on the context's stream unless they move data to/from the host.
+ */
+#ifndef SKEELBERZINS_B200_H
+#define SKEELBERZINS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID (-1)      /* bad argument (message says which)                              */
+#define SB_ERR_CUDA (-2)         /* CUDA runtime error / no device                                  */
+#define SB_ERR_UNSUPPORTED (-3)  /* valid request outside the kernels' compiled range               */
+#define SB_ERR_CONVERGENCE (-4)  /* reference: throw("convergence failed") src/utils.jl:336,377     */
+#define SB_ERR_PLUGIN (-5)       /* NVRTC compilation of a user functor failed                      */
+
+/* ---- coefficient-functor registry ------------------------------------------------------------
+ * Device-compiled restatements of the reference's example callbacks pdefun(x,t,u,dudx)->(c,f,s) and
+ * bdfun(xl,ul,xr,ur,t)->(pl,ql,pr,qr).  Each instance k of a batch carries its own parameter
+ * vector prm[0..nparams) (the "parameter sweep").  The values in brackets reproduce the example.
+ */
+enum sb_functor_id {
+    /* examples/Example101_LinearDiffusion.jl:21-38 ; test/test_solveTransient.jl:7-24
+     * c=1, f=D*ux, s=0 ; p=0,q=1 both ends.                      prm = {D [1]}                    */
+    SB_LIN_DIFF = 0,
+    /* examples/Example102_NonlinearDiffusion.jl:44-65
+     * c=1, f=a*u*ux, s=0 ; p=0,q=1 both ends.                    prm = {a [2]}                    */
+    SB_NONLIN_DIFF = 1,
+    /* examples/Example103_LinearDiffusionCylindrical.jl:35-58  (m=1, singular)
+     * c=1, f=D*ux, s=0 ; left (0,0) ; right p=ur-g*exp(-D*n^2*t), q=0.
+     *                                                            prm = {D [1], n, g [=J0(n)]}      */
+    SB_LIN_DIFF_CYL = 2,
+    /* examples/Example104_Poisson.jl:20-41 ; test/test_solveStationary.jl:6-23 (c0=0)
+     * c=c0, f=ux, s=s0 ; p=u-ub, q=0 both ends.                  prm = {c0 [1], s0 [1], ub [0.1]}  */
+    SB_POISSON = 3,
+    /* examples/Example105_StationaryNonlinearDiffusion.jl:30-51
+     * c=1, f=a*u*ux, s=s0 ; p=u-ub, q=0 both ends.               prm = {a [2], s0 [1], ub [0.1]}   */
+    SB_STAT_NONLIN = 4,
+    /* examples/Example106_SystemReactionDiffusion.jl:42-64   (npde = 2)
+     * c=(1,1), f=(d1,d2).*ux, y=u1-u2, s=(-k*y, k*y) ;
+     * left p=(u1-1,0) q=(0,1) ; right p=(0,u2) q=(1,0).          prm = {d1 [.5], d2 [.1], k [1]}   */
+    SB_REACT_DIFF = 5,
+    /* examples/Example107_LinearDiffusionSpherical.jl:34-55  (m=2, singular)
+     * c=1, f=D*ux, s=0 ; left (0,0) ; right p=ur-(1+6*D*t), q=0. prm = {D [1]}                     */
+    SB_LIN_DIFF_SPH = 6,
+    /* examples/Example201_PartialDerivativeApprox.jl:34-51
+     * c=1, f=D*ux, s=-(D*eta/L)*ux ; p=u, q=0 both ends.         prm = {D [.1], eta [10], L [1]}   */
+    SB_CONV_DIFF = 7,
+    /* examples/Example301_PDEOptimSciMLSensitivity.jl:31-48
+     * c=1, f=a1*ux, s=2*a0*u ; p=u, q=0 both ends.               prm = {a0, a1}                    */
+    SB_LIN_REACT = 8,
+    /* quasi-linear scalar family (covers all scalar examples and the manufactured tests):
+     *   c = c0 + c1*u ; f = (d0 + d1*u)*ux ; s = s0 + s1*u + s2*ux
+     *   left : p = al*ul - (gl0 + gl1*t + gl2*exp(-ll*t)), q = ql
+     *   right: p = ar*ur - (gr0 + gr1*t + gr2*exp(-lr*t)), q = qr
+     * prm = {c0,c1,d0,d1,s0,s1,s2, al,gl0,gl1,gl2,ll,ql, ar,gr0,gr1,gr2,lr,qr}   (19 values)       */
+    SB_GENERIC_SCALAR = 9,
+    SB_NUM_BUILTIN_FUNCTORS = 10,
+    /* ids >= SB_USER_FUNCTOR_BASE are handed out by sb_register_user_functor()                     */
+    SB_USER_FUNCTOR_BASE = 1000
+};
+
+#define SB_MAX_NPDE 2
+#define SB_GENERIC_SCALAR_NPARAMS 19
+
+typedef struct sb_ctx sb_ctx;
+typedef struct sb_problem sb_problem;
+
+/* which Newton-iteration pipeline sb_newton_iteration() runs */
+enum sb_design {
+    SB_DESIGN_SPLIT = 0, /* assemble kernel writes F and the block-tridiagonal J to HBM; solve kernel
+                            reads them (the two calls sb_residual_jacobian + sb_solve_update_norm)  */
+    SB_DESIGN_FUSED = 1  /* one kernel per iteration; J and F never leave the SM                    */
+};
+
+/* ---- library / context ---------------------------------------------------------------------- */
+const char* sb_version(void);
+const char* sb_last_error(void);
+int sb_device_count(int* count);
+/* stream == NULL: the context creates its own non-blocking stream; otherwise a cudaStream_t of the
+ * caller (e.g. the torch current stream, so that the caller's events bracket the kernels).       */
+int sb_ctx_create(int device, void* stream, sb_ctx** out);
+int sb_ctx_destroy(sb_ctx* ctx);
+int sb_ctx_synchronize(sb_ctx* ctx);
+
+/* functor metadata: npde and number of per-instance parameters of a registry entry              */
+int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name);
+
+/* Plugin slot: compile (NVRTC, sm_100a) a user functor given as CUDA C++ source that defines
+ *   struct <struct_name> { static constexpr int npde, nparams;
+ *       template<class S> static __device__ void pde(double x,double t,const S* u,const S* ux,
+ *                                                    const double* prm, S* c, S* f, S* s);
+ *       template<class S> static __device__ void bc (double xl,const S* ul,double xr,const S* ur,
+ *                                                    double t,const double* prm,
+ *                                                    S* pl,double* ql,S* pr,double* qr); };
+ * i.e. the reference's pdefun/bdfun (docs/src/solvers.md:9-47) generic in the scalar type so the
+ * dual numbers flow through.  Returns the new functor id in *functor_id.                          */
+int sb_register_user_functor(sb_ctx* ctx, const char* cuda_source, const char* struct_name,
+                             int npde, int nparams, int* functor_id);
+
+/* ---- problem (replaces problem_init, src/utils.jl:609-663, for a batch of B instances) -------
+ * m          coordinate symmetry 0/1/2 (asserts of src/pdepe.jl:55-57 apply)
+ * xmesh_host Nx mesh points shared by the batch
+ * params_host[B*nparams] per-instance functor parameters, instance-major
+ * Computes singular (src/utils.jl:616), xi/zeta (src/utils.jl:683-718) and the interpolation and
+ * flux/volume weights used by assemble! (src/utils.jl:18-48, src/assembler.jl:36,68-69,98).      */
+int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh_host,
+                      int functor_id, const double* params_host, int nparams, sb_problem** out);
+int sb_problem_destroy(sb_problem* pb);
+/* queries: npde, Nx, B, singular flag, xi/zeta (host copies, length Nx-1 each; may be NULL)      */
+int sb_problem_info(sb_problem* pb, int* npde, int* Nx, int64_t* B, int* singular);
+int sb_problem_quadrature(sb_problem* pb, double* xi_host, double* zeta_host);
+int sb_problem_set_design(sb_problem* pb, int design);
+
+/* state u (reference layout on the host side; the device keeps a chunk-transposed SoA layout)   */
+int sb_state_upload(sb_problem* pb, const double* u_host);
+int sb_state_download(sb_problem* pb, double* u_host);
+
+/* mass_matrix (src/assembler.jl:138-174): 0/1 flags per (instance, component, node class) from the
+ * CURRENT state at time t0 (call right after uploading the initial condition).  stationary != 0
+ * selects implicitEuler_stat! semantics (src/utils.jl:264-276): all flags 1.                     */
+int sb_mass_flags(sb_problem* pb, double t0, int stationary);
+/* download flags as doubles in reference layout [B][Nx][npde] (diag of the mass matrix)          */
+int sb_mass_download(sb_problem* pb, double* mass_host);
+
+/* assemble!(du,u,pb,t) (src/assembler.jl:19-125) on reference-layout HOST vectors of B instances;
+ * copies in, runs the residual-only kernel, copies out.  u_host==NULL: use the resident state.   */
+int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host);
+
+/* time step n -> n+1 (src/pdepe.jl:94, src/utils.jl:309): b = M.*u_n ; u <- b ; all instances
+ * active ; per-step iteration counters cleared.  inv_tau = 1/tau (0 for the stationary solve).   */
+int sb_begin_step(sb_problem* pb, double t_next, double inv_tau);
+
+/* implicitEuler! + forwarddiff_color_jacobian! + value! + rhs update
+ * (src/utils.jl:245-257, 312-314): F = -assemble(u,t) + inv_tau*M.*u - inv_tau*b and the
+ * block-tridiagonal dF/du, for active instances, into device scratch.                           */
+int sb_residual_jacobian(sb_problem* pb);
+/* solve + update + norm + stop test (src/utils.jl:317-333): h = J\F ; u -= h ; nm = ||h||_2 ;
+ * iters++ ; active &= !(nm < tol).                                                               */
+int sb_solve_update_norm(sb_problem* pb, double tol);
+/* one whole Newton iteration with the configured design (split = the two calls above)           */
+int sb_newton_iteration(sb_problem* pb, double tol);
+
+/* number of instances still iterating after the most recent iteration that has completed.
+ * blocking != 0 waits for everything enqueued so far; otherwise returns the newest value already
+ * delivered (never less than the true current value -> safe for "keep iterating" decisions).     */
+int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active);
+
+/* convenience: the Newton loop of src/utils.jl:311-336 driven from C with software pipelining
+ * (iterations are enqueued ahead of the poll; converged instances are frozen bit-exactly).
+ * Returns SB_ERR_CONVERGENCE if any instance is still active after maxit iterations.
+ * iters_done (may be NULL) = iterations launched.                                                */
+int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done);
+
+/* diagnostics (host arrays of length B unless stated)                                            */
+int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iterations this step  */
+int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */
+int sb_get_last_norm(sb_problem* pb, double* norm_host);          /* ||h||_2 of last iteration    */
+int sb_get_status(sb_problem* pb, int32_t* status_host);          /* 0 ok,1 active,2 non-finite   */
+/* ||h||_2 history of the current step: hist_host[B*maxit_cap], entry [k*cap + it]               */
+int sb_get_history(sb_problem* pb, double* hist_host, int cap);
+/* sum over instances of Newton iterations since upload (the work counter of the metric)         */
+int sb_total_active_iterations(sb_problem* pb, int64_t* total);
+
+/* device-side scratch access for parity tests of the assemble kernel: F and J of the last
+ * sb_residual_jacobian in reference layout: F[B][Nx][npde], Jl/Jd/Ju[B][Nx][npde][npde]
+ * (row component major): Jl = d F_i / d u_{i-1}, Jd = d F_i / d u_i, Ju = d F_i / d u_{i+1}.     */
+int sb_debug_download_system(sb_problem* pb, double* F, double* Jl, double* Jd, double* Ju);
+/* solve given block-tridiagonal systems (reference layout as above) with the product kernels;
+ * x[B][Nx][npde].  Used by the solver parity tests.                                              */
+int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const double* Ju,
+                   const double* F, double* x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKEELBERZINS_B200_H */

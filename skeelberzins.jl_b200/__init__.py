@@ -1,0 +1,12 @@
+"""skeelberzins.jl_b200 -- B200-native batched implicit-Euler / stationary-Newton path of SkeelBerzins.jl.
+
+Host-side mirror of the reference interface for this path (``pdepe``, ``Params``,
+``ProblemDefinition``/``SkeelBerzinsDiscretization``, ``assemble_``, ``newton``) over the C-ABI
+library ``libskeelberzins_b200.so`` (include/skeelberzins_b200.h).  All compute runs in
+hand-written sm_100a CUDA kernels; there is no CPU fallback -- importing the host logic works
+anywhere, but every solve raises if the CUDA library or a GPU is missing.
+"""
+from . import examples, timegrid  # noqa: F401
+from .timegrid import julia_range, time_grid  # noqa: F401
+
+__version__ = "0.1.0"
