@@ -132,6 +132,9 @@ int sb_problem_destroy(sb_problem* pb);
 int sb_problem_info(sb_problem* pb, int* npde, int* Nx, int64_t* B, int* singular);
 int sb_problem_quadrature(sb_problem* pb, double* xi_host, double* zeta_host);
 int sb_problem_set_design(sb_problem* pb, int design);
+/* thread decomposition chosen for the batch: R rows per thread, T threads per system (T == 32: one warp
+ * per system, shuffles only; T > 32: one CTA per system, shared-memory exchange)                      */
+int sb_problem_layout(sb_problem* pb, int* R, int* T, int* warp);
 
 /* state u (reference layout on the host side; the device keeps a chunk-transposed SoA layout)   */
 int sb_state_upload(sb_problem* pb, const double* u_host);
@@ -166,6 +169,9 @@ int sb_newton_iteration(sb_problem* pb, double tol);
  * blocking != 0 waits for everything enqueued so far; otherwise returns the newest value already
  * delivered (never less than the true current value -> safe for "keep iterating" decisions).     */
 int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active);
+/* wait for Newton iteration `it` (0-based since sb_begin_step) and return the number of instances
+ * that were still active after it; later iterations may already be enqueued behind it.           */
+int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active);
 
 /* convenience: the Newton loop of src/utils.jl:311-336 driven from C with software pipelining
  * (iterations are enqueued ahead of the poll; converged instances are frozen bit-exactly).
@@ -178,7 +184,9 @@ int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iter
 int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */
 int sb_get_last_norm(sb_problem* pb, double* norm_host);          /* ||h||_2 of last iteration    */
 int sb_get_status(sb_problem* pb, int32_t* status_host);          /* 0 ok,1 active,2 non-finite   */
-/* ||h||_2 history of the current step: hist_host[B*maxit_cap], entry [k*cap + it]               */
+/* ||h||_2 history of the current step (Params.hist, src/utils.jl:305-307,325-327): enable with a
+ * capacity (>= maxit), then after a step hist_host[k*cap + it] holds the norm of iteration it.     */
+int sb_enable_history(sb_problem* pb, int cap);
 int sb_get_history(sb_problem* pb, double* hist_host, int cap);
 /* sum over instances of Newton iterations since upload (the work counter of the metric)         */
 int sb_total_active_iterations(sb_problem* pb, int64_t* total);

@@ -1,0 +1,492 @@
+"""Host-side mirror of the reference interface for the internal implicit-Euler / Newton path.
+
+Same names, argument meaning and error behaviour as SkeelBerzins.jl (citations are reference
+file:line), batched over B independent PDE instances:
+
+    pdepe(m, pdefun, icfun, bdfun, xmesh, tspan; params=Params(), kwargs...)   src/pdepe.jl:42
+    pdepe(m, pdefun, icfun, bdfun, xmesh; ...)            (stationary)          src/pdepe.jl:156
+    Params                                                                      src/utils.jl:191
+    ProblemDefinition (alias SkeelBerzinsDiscretization)                        src/utils.jl:113
+    assemble_(du, u, pb, t)                (assemble!)                          src/assembler.jl:19
+    mass_matrix(pb)                                                             src/assembler.jl:138
+    newton(...), newton_stat(...)                                               src/utils.jl:303,344
+
+The host owns the time loop and the Newton loop exactly as the reference does; each Newton
+iteration is one (fused) or two (split) kernel launches through the C ABI.  ``pdefun`` / ``bdfun``
+are registry functors (``Functor``): Julia closures cannot run on the device, so the example
+callbacks are device-compiled (include/skeelberzins_b200.h, enum sb_functor_id) and carry a
+per-instance parameter matrix -- that is the parameter sweep.  ``icfun`` stays a host callable, as
+in the reference (src/utils.jl:629-632).
+"""
+import ctypes
+from dataclasses import dataclass, field, replace
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import SBError
+from .timegrid import time_grid
+
+
+class ConvergenceFailed(RuntimeError):
+    """reference: throw("convergence failed")  (src/utils.jl:336,377)"""
+
+
+@dataclass
+class Params:
+    """Keyword arguments of the solver, field for field (src/utils.jl:191-238)."""
+    solver: str = "euler"                      # :euler | :DiffEq
+    tstep: Union[float, Sequence[float]] = 1e-2
+    hist: bool = False
+    sparsity: str = "sparseArrays"             # :sparseArrays | :banded (storage plug; block-tridiagonal on device)
+    linsolve: object = "KLUFactorization"      # accepted for source compatibility; the GPU solver is fixed
+    maxit: int = 100
+    tol: float = 1e-10
+    data: bool = False
+    nb_design_var: int = 0
+
+
+@dataclass
+class Functor:
+    """Registry coefficient functor (pdefun + bdfun) with per-instance parameters [B, nparams]."""
+    id: int
+    params: np.ndarray
+
+    def __post_init__(self):
+        npde, nprm, name = functor_info(self.id)
+        p = np.ascontiguousarray(self.params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p.reshape(1, -1)
+        if p.shape[1] != nprm:
+            raise ValueError("functor %s takes %d parameters per instance, got %d" % (name, nprm, p.shape[1]))
+        self.params = p
+        self.npde, self.nparams, self.name = npde, nprm, name
+
+    @property
+    def batch(self):
+        return self.params.shape[0]
+
+
+def functor_info(fid):
+    lib = _lib.load()
+    npde, nprm, name = ctypes.c_int(), ctypes.c_int(), ctypes.c_char_p()
+    _lib.check(lib.sb_functor_info(int(fid), ctypes.byref(npde), ctypes.byref(nprm), ctypes.byref(name)))
+    return npde.value, nprm.value, name.value.decode()
+
+
+class Context:
+    """One per GPU (sb_ctx).  stream: a cudaStream_t handle (int) to run on, or None for an own stream."""
+
+    def __init__(self, device=0, stream=None):
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.sb_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h, self.device = h, int(device)
+
+    def synchronize(self):
+        _lib.check(_lib.load().sb_ctx_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.load().sb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DeviceProblem:
+    """Thin object wrapper of sb_problem: the per-iteration entry points of the C ABI."""
+
+    def __init__(self, ctx, m, xmesh, functor, design="fused"):
+        self.lib = _lib.load()
+        self.ctx = ctx
+        x = np.ascontiguousarray(xmesh, dtype=np.float64)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.sb_problem_create(ctx._h, int(m), x.size, ctypes.c_int64(functor.batch), _lib.ptr(x),
+                                              int(functor.id), _lib.ptr(functor.params), functor.nparams,
+                                              ctypes.byref(h)))
+        self._h = h
+        self.B, self.Nx, self.npde = functor.batch, x.size, functor.npde
+        self.set_design(design)
+
+    def close(self):
+        if self._h:
+            self.lib.sb_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_design(self, design):
+        d = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED}[design] if isinstance(design, str) else int(design)
+        _lib.check(self.lib.sb_problem_set_design(self._h, d))
+        self.design = "fused" if d == _lib.DESIGN_FUSED else "split"
+
+    def layout(self):
+        R, T, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.sb_problem_layout(self._h, ctypes.byref(R), ctypes.byref(T), ctypes.byref(w)))
+        return dict(R=R.value, T=T.value, warp=bool(w.value))
+
+    def info(self):
+        npde, Nx, B, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int()
+        _lib.check(self.lib.sb_problem_info(self._h, ctypes.byref(npde), ctypes.byref(Nx), ctypes.byref(B), ctypes.byref(s)))
+        return dict(npde=npde.value, Nx=Nx.value, B=B.value, singular=bool(s.value))
+
+    def quadrature(self):
+        xi, ze = np.empty(self.Nx - 1), np.empty(self.Nx - 1)
+        _lib.check(self.lib.sb_problem_quadrature(self._h, _lib.ptr(xi), _lib.ptr(ze)))
+        return xi, ze
+
+    def _nodes(self, a, w=None):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        n = self.B * self.Nx * (self.npde if w is None else w)
+        if a.size != n:
+            raise ValueError("expected %d values ([B=%d][Nx=%d][%d]), got %d" % (n, self.B, self.Nx, n // (self.B * self.Nx), a.size))
+        return a
+
+    def upload(self, u):
+        u = self._nodes(u)
+        _lib.check(self.lib.sb_state_upload(self._h, _lib.ptr(u)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty((self.B, self.Nx, self.npde))
+        _lib.check(self.lib.sb_state_download(self._h, _lib.ptr(out)))
+        return out
+
+    def mass_flags(self, t0, stationary=False):
+        _lib.check(self.lib.sb_mass_flags(self._h, float(t0), int(bool(stationary))))
+
+    def mass(self):
+        out = np.empty((self.B, self.Nx, self.npde))
+        _lib.check(self.lib.sb_mass_download(self._h, _lib.ptr(out)))
+        return out
+
+    def assemble(self, u, t):
+        du = np.empty((self.B, self.Nx, self.npde))
+        uu = None if u is None else self._nodes(u)
+        _lib.check(self.lib.sb_assemble(self._h, _lib.ptr(uu), float(t), _lib.ptr(du)))
+        return du
+
+    def begin_step(self, t_next, inv_tau):
+        _lib.check(self.lib.sb_begin_step(self._h, float(t_next), float(inv_tau)))
+
+    def residual_jacobian(self):
+        _lib.check(self.lib.sb_residual_jacobian(self._h))
+
+    def solve_update_norm(self, tol):
+        _lib.check(self.lib.sb_solve_update_norm(self._h, float(tol)))
+
+    def newton_iteration(self, tol):
+        _lib.check(self.lib.sb_newton_iteration(self._h, float(tol)))
+
+    def poll_active(self, blocking=True):
+        n = ctypes.c_int64()
+        _lib.check(self.lib.sb_poll_active(self._h, int(bool(blocking)), ctypes.byref(n)))
+        return n.value
+
+    def wait_iteration(self, it):
+        n = ctypes.c_int64()
+        _lib.check(self.lib.sb_wait_iteration(self._h, int(it), ctypes.byref(n)))
+        return n.value
+
+    def newton_solve(self, tol, maxit):
+        """C-side pipelined Newton loop; raises ConvergenceFailed like the reference's throw."""
+        it = ctypes.c_int()
+        rc = self.lib.sb_newton_solve(self._h, float(tol), int(maxit), ctypes.byref(it))
+        if rc == _lib.SB_ERR_CONVERGENCE:
+            raise ConvergenceFailed("convergence failed")
+        _lib.check(rc)
+        return it.value
+
+    def _get(self, fn, dtype):
+        out = np.empty(self.B, dtype=dtype)
+        _lib.check(fn(self._h, _lib.ptr(out)))
+        return out
+
+    def step_iters(self):
+        return self._get(self.lib.sb_get_step_iters, np.int32)
+
+    def total_iters(self):
+        return self._get(self.lib.sb_get_total_iters, np.int64)
+
+    def last_norm(self):
+        return self._get(self.lib.sb_get_last_norm, np.float64)
+
+    def status(self):
+        return self._get(self.lib.sb_get_status, np.int32)
+
+    def enable_history(self, cap):
+        _lib.check(self.lib.sb_enable_history(self._h, int(cap)))
+        self._hist_cap = int(cap)
+
+    def history(self):
+        out = np.empty((self.B, self._hist_cap))
+        _lib.check(self.lib.sb_get_history(self._h, _lib.ptr(out), self._hist_cap))
+        return out
+
+    def total_active_iterations(self):
+        n = ctypes.c_int64()
+        _lib.check(self.lib.sb_total_active_iterations(self._h, ctypes.byref(n)))
+        return n.value
+
+    def debug_system(self):
+        P = self.npde
+        F = np.empty((self.B, self.Nx, P))
+        Jl, Jd, Ju = (np.empty((self.B, self.Nx, P, P)) for _ in range(3))
+        _lib.check(self.lib.sb_debug_download_system(self._h, _lib.ptr(F), _lib.ptr(Jl), _lib.ptr(Jd), _lib.ptr(Ju)))
+        return F, Jl, Jd, Ju
+
+    def debug_solve(self, Jl, Jd, Ju, F):
+        P = self.npde
+        Jl, Jd, Ju = (self._nodes(a, P * P) for a in (Jl, Jd, Ju))
+        F = self._nodes(F)
+        x = np.empty((self.B, self.Nx, P))
+        _lib.check(self.lib.sb_debug_solve(self._h, _lib.ptr(Jl), _lib.ptr(Jd), _lib.ptr(Ju), _lib.ptr(F), _lib.ptr(x)))
+        return x
+
+
+@dataclass
+class ProblemDefinition:
+    """Problem record (src/utils.jl:113-182), same field names; `jac` lives on the device as
+    block-tridiagonal scratch (Jl, Jd, Ju) and is rewritten every Newton iteration like pb.jac."""
+    npde: int
+    Nx: int
+    xmesh: np.ndarray
+    tspan: tuple
+    singular: bool
+    m: int
+    nb_design_var: int
+    inival: np.ndarray          # [B, Nx*npde] flattened, component fastest (src/utils.jl:632)
+    xi: np.ndarray              # ξ
+    zeta: np.ndarray            # ζ
+    pdefunction: Functor
+    icfunction: object
+    bdfunction: Functor
+    device: DeviceProblem = field(repr=False, default=None)
+
+    @property
+    def jac(self):
+        return self.device.debug_system()[1:]
+
+    def __len__(self):  # Base.length(pb) = nb_design_var, src/utils.jl:665
+        return self.nb_design_var
+
+
+SkeelBerzinsDiscretization = ProblemDefinition  # name used by the north_star for this record
+
+
+class DiffEqArray:
+    """Result container of the transient solve (RecursiveArrayTools.DiffEqArray, src/pdepe.jl:110):
+    `u[k]` is the state at `t[k]`: [B, Nx] for npde == 1, [B, npde, Nx] otherwise (squeezed to the
+    reference's Vector[Nx] / Matrix(npde, Nx) when the batch axis was not requested)."""
+
+    def __init__(self, u, t):
+        self.u, self.t = u, np.asarray(t)
+
+    def __len__(self):
+        return len(self.u)
+
+    def __getitem__(self, k):
+        return self.u[k]
+
+
+def _merge_params(params, kwargs, stationary):
+    # src/pdepe.jl:44-52 / :158-166 -- kwargs override the fields of params
+    names = ("solver", "tstep", "hist", "sparsity", "linsolve", "maxit", "tol", "data", "nb_design_var")
+    over = {k: kwargs.pop(k) for k in names if k in kwargs}
+    p = replace(params, **over)
+    if stationary and "tstep" not in over:
+        p = replace(p, tstep=np.inf)                      # :159
+    return p
+
+
+def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design="fused"):
+    """problem_init (src/utils.jl:609-663) for the whole batch."""
+    if not isinstance(pdefun, Functor):
+        raise TypeError("pdefun must be a registry Functor (device-compiled); arbitrary host closures cannot run "
+                        "on the GPU and there is no CPU fallback")
+    if bdfun is not None and bdfun is not pdefun:
+        if not (isinstance(bdfun, Functor) and bdfun.id == pdefun.id):
+            raise TypeError("bdfun must be the same registry Functor as pdefun (the registry couples them)")
+    if params.sparsity not in ("sparseArrays", "banded"):
+        # src/utils.jl:641
+        raise ValueError("Error: Invalid sparsity pattern selected. Please choose from the available options: "
+                         ":sparseArrays, :banded")
+    x = np.ascontiguousarray(xmesh, dtype=np.float64)
+    ctx = ctx or default_context(0)
+    dev = DeviceProblem(ctx, m, x, pdefun, design)
+    B, Nx, npde = pdefun.batch, x.size, pdefun.npde
+    if callable(icfun):
+        u0 = np.asarray(icfun(x), dtype=np.float64)
+    else:
+        u0 = np.asarray(icfun, dtype=np.float64)
+    if u0.size == Nx * npde:
+        u0 = np.broadcast_to(u0.reshape(1, Nx, npde), (B, Nx, npde))
+    inival = np.ascontiguousarray(u0.reshape(B, Nx * npde))
+    xi, zeta = dev.quadrature()
+    info = dev.info()
+    pb = ProblemDefinition(npde, Nx, x, tuple(tspan), info["singular"], int(m), params.nb_design_var, inival, xi,
+                           zeta, pdefun, icfun, pdefun, dev)
+    return Nx, npde, inival, pb
+
+
+def mass_matrix(pb, t0=None):
+    """mass_matrix(pb) (src/assembler.jl:138-174): (diag[B, Nx*npde], flag_DAE) from the initial value."""
+    pb.device.upload(pb.inival)
+    pb.device.mass_flags(pb.tspan[0] if t0 is None else t0)
+    M = pb.device.mass().reshape(pb.inival.shape)
+    return M, bool((M == 0).any())
+
+
+def assemble_(du, u, pb, t):
+    """assemble!(du, u, pb, t) (src/assembler.jl:19-125): in place on flat vectors [B, Nx*npde]; returns the
+    reshaped du like the reference does (:124)."""
+    out = pb.device.assemble(u, t)
+    du = np.asarray(du)
+    du.reshape(-1)[:] = out.reshape(-1)
+    return du.reshape(pb.device.B, pb.Nx, pb.npde)
+
+
+def _newton_loop(dev, tol, maxit, depth=2):
+    """The loop of src/utils.jl:311-336 for the batch, host-owned.  Up to `depth` iterations are kept
+    enqueued behind the one whose "still active" counter the host waits for, so the GPU never idles on
+    the host round trip (converged instances are frozen on the device: surplus launches are no-ops and
+    per-instance iteration counts stay exact)."""
+    launched = done = 0
+    while True:
+        while launched < maxit and launched - done < depth:
+            dev.newton_iteration(tol)
+            launched += 1
+        n_active = dev.wait_iteration(done)
+        done += 1
+        if n_active == 0:
+            return launched
+        if done >= maxit:
+            raise ConvergenceFailed("convergence failed")      # src/utils.jl:336
+
+
+def newton(pb, tau, timeStep, tol=1.0e-10, maxit=100, hist_flag=False, c_loop=False):
+    """newton(b, tau, timeStep, pb, mass, cache, rhs; ...) (src/utils.jl:303-337) on the resident state:
+    b = M .* u_n is formed on the device (src/pdepe.jl:94), unP1 = copy(b) (:309), then the Newton loop.
+    Returns per-instance history [B, maxit] when hist_flag."""
+    dev = pb.device
+    dev.begin_step(timeStep, 0.0 if np.isinf(tau) else 1.0 / tau)
+    if c_loop:
+        dev.newton_solve(tol, maxit)
+    else:
+        _newton_loop(dev, tol, maxit)
+    if hist_flag:
+        return dev.history()
+    return None
+
+
+newton_stat = newton  # src/utils.jl:344-378: same loop, residual without mass matrix (flags all 1, inv_tau = 0)
+
+
+def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused", save="all",
+          squeeze=None, c_loop=False, return_device=False, **kwargs):
+    """Batched pdepe.  With `tspan`: transient solve by implicit Euler (src/pdepe.jl:42-128); without:
+    stationary solve by one Newton solve with tau = Inf, t = 1 (src/pdepe.jl:156-192).
+
+    Extra keyword arguments of this implementation: ctx (Context / GPU), design ("fused" | "split"),
+    save ("all": every time step as the reference does | "last": only u(t_end), for very large batches),
+    squeeze (drop the batch axis; default: when the functor has a single instance).
+    Returns what the reference returns: sol | (sol, pb) | (sol, storage) | (sol, pb, storage); stationary:
+    u | (u, hist) | (u, pb) | (u, pb, hist).  Unlike the reference stored states are the
+    true states, not the in-place masked aliases.
+    """
+    stationary = tspan is None
+    params = _merge_params(params or Params(tstep=np.inf if stationary else 1e-2), kwargs, stationary)
+    if kwargs:
+        raise TypeError("unknown keyword arguments: %s" % sorted(kwargs))
+    x = np.asarray(xmesh, dtype=np.float64)
+    # src/pdepe.jl:55-59 / :168-169
+    assert m in (0, 1, 2), "Parameter m invalid"
+    assert m == 0 or (m > 0 and x[0] >= 0), "Non-conforming mesh"
+    if stationary:
+        assert params.solver == "euler", "Elliptic problems can only be solved using the Euler method"
+        assert np.isscalar(params.tstep) and np.isinf(params.tstep), \
+            "Time step should be set to Inf to obtain the stationary solution"
+    else:
+        assert not (np.isscalar(params.tstep) and np.isinf(params.tstep)), \
+            "Adjust time step or try the alternative method for solving elliptic problems"
+
+    Nx, npde, inival, pb = problem_init(m, x, (0, 1) if stationary else tspan, pdefun, icfun, bdfun, params, ctx, design)
+    dev = pb.device
+    B = dev.B
+    if squeeze is None:
+        squeeze = (B == 1)
+    if params.solver == "DiffEq":
+        return pb                                              # src/pdepe.jl:123-126
+    if params.hist:
+        dev.enable_history(params.maxit)
+
+    def shape(u):  # [B,Nx,npde] -> reference shapes
+        u = u[:, :, 0] if npde == 1 else np.ascontiguousarray(np.transpose(u, (0, 2, 1)))
+        return u[0] if squeeze else u
+
+    dev.upload(inival)
+    if stationary:
+        dev.mass_flags(1.0, stationary=True)
+        hist = newton_stat(pb, np.inf, 1.0, params.tol, params.maxit, params.hist, c_loop)   # src/pdepe.jl:180
+        u = dev.download()
+        flat = u.reshape(B, Nx * npde)
+        flat = flat[0] if squeeze else flat                    # reference returns the flat vector
+        if params.hist:
+            it = dev.step_iters()
+            hist = [hist[k, :it[k]] for k in range(B)]
+            hist = hist[0] if squeeze else hist
+        out = [flat]
+        if params.data:
+            out.append(pb)
+        if params.hist:
+            out.append(hist)
+        if return_device:
+            out.append(dev)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    timeSteps, tau = time_grid(tspan, params.tstep)            # src/pdepe.jl:82-85
+    dev.mass_flags(timeSteps[0])                               # src/pdepe.jl:78-79
+    results = [shape(inival.reshape(B, Nx, npde))] if save == "all" else []
+    storage = []
+    for i in range(timeSteps.size - 1):                        # src/pdepe.jl:90
+        time_val = timeSteps[i + 1]
+        tstep_val = tau if tau is not None else timeSteps[i + 1] - timeSteps[i]
+        h = newton(pb, tstep_val, time_val, params.tol, params.maxit, params.hist, c_loop)      # :94-96
+        if params.hist:
+            it = dev.step_iters()
+            hs = [h[k, :it[k]] for k in range(B)]
+            storage.append(hs[0] if squeeze else hs)
+        if save == "all":
+            results.append(shape(dev.download()))
+    if save != "all":
+        results.append(shape(dev.download()))
+        sol = DiffEqArray(results, timeSteps[-1:])
+    else:
+        sol = DiffEqArray(results, timeSteps)
+    out = [sol]
+    if params.data:
+        out.append(pb)
+    if params.hist:
+        out.append(storage)
+    if return_device:
+        out.append(dev)
+    return out[0] if len(out) == 1 else tuple(out)

@@ -1,0 +1,764 @@
+// sb_api.cu -- C ABI of the B200-native batched Skeel-Berzins solve path (include/skeelberzins_b200.h).
+//
+// Host responsibilities kept here (all O(Nx) or O(B) and once per problem): problem_init
+// (src/utils.jl:609-663) incl. the quadrature points/weights (src/utils.jl:683-718) and the
+// interpolation weights (src/utils.jl:18-48), choice of the thread decomposition (R rows per thread,
+// T threads per system), device allocation, layout transforms, the Newton software pipeline.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/skeelberzins_b200.h"
+#include "sb_registry.h"
+
+using namespace sb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(SB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
+
+// reference layout [B][Nx][W] <-> device layout [B][R][T][W]   (W doubles per node)
+// identity != 0: padding nodes receive the W = P*P identity block (used for Jd)
+__global__ void k_to_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
+                                   int T, int W, int identity_P) {
+    const size_t L = (size_t)R * T;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*L*W device elements
+    if (idx >= (size_t)B * L * W) return;
+    const int w = (int)(idx % W);
+    const size_t ns = idx / W;
+    const int64_t k = ns / L;
+    const int s = (int)(ns - (size_t)k * L);
+    const int r = s / T, t = s - r * T;
+    const int i = t * R + r;
+    double pad = 0.0;
+    if (identity_P > 0 && (w / identity_P) == (w % identity_P)) pad = 1.0;
+    dst[idx] = (i < Nx) ? src[((size_t)k * Nx + i) * W + w] : pad;
+}
+
+__global__ void k_from_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
+                                     int T, int W) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*Nx*W reference elements
+    if (idx >= (size_t)B * Nx * W) return;
+    const int w = (int)(idx % W);
+    const size_t ni = idx / W;
+    const int64_t k = ni / Nx;
+    const int i = (int)(ni - (size_t)k * Nx);
+    const int r = i % R, t = i / R;
+    dst[idx] = src[(((size_t)k * R + r) * T + t) * W + w];
+}
+
+const FunctorEntry* registry() {
+    static FunctorEntry table[SB_NUM_BUILTIN_FUNCTORS];
+    static bool init = false;
+    if (!init) {
+        table[SB_LIN_DIFF] = entry_lin_diff();
+        table[SB_NONLIN_DIFF] = entry_nonlin_diff();
+        table[SB_LIN_DIFF_CYL] = entry_lin_diff_cyl();
+        table[SB_POISSON] = entry_poisson();
+        table[SB_STAT_NONLIN] = entry_stat_nonlin();
+        table[SB_REACT_DIFF] = entry_react_diff();
+        table[SB_LIN_DIFF_SPH] = entry_lin_diff_sph();
+        table[SB_CONV_DIFF] = entry_conv_diff();
+        table[SB_LIN_REACT] = entry_lin_react();
+        table[SB_GENERIC_SCALAR] = entry_generic_scalar();
+        init = true;
+    }
+    return table;
+}
+
+SolveKernel solve_kernel(int P, int ri, int warp) {
+#define SB_SOLVE_ROW(PP, RR) {k_solve<PP, RR, false>, k_solve<PP, RR, true>}
+    static const SolveKernel t1[kNumR][2] = {SB_SOLVE_ROW(1, 1), SB_SOLVE_ROW(1, 2), SB_SOLVE_ROW(1, 4), SB_SOLVE_ROW(1, 8),
+                                             SB_SOLVE_ROW(1, 16)};
+    static const SolveKernel t2[kNumR][2] = {SB_SOLVE_ROW(2, 1), SB_SOLVE_ROW(2, 2), SB_SOLVE_ROW(2, 4), SB_SOLVE_ROW(2, 8),
+                                             {nullptr, nullptr}};
+#undef SB_SOLVE_ROW
+    return P == 1 ? t1[ri][warp] : t2[ri][warp];
+}
+
+inline double ipow(double x, int n) {
+    double r = 1.0;
+    for (int k = 0; k < n; ++k) r *= x;
+    return r;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return SB_OK;
+}
+
+}  // namespace
+
+struct sb_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+};
+
+struct sb_problem {
+    sb_ctx* ctx;
+    const FunctorEntry* fe;
+    ProbDev pd;
+    int P, ri, warp, design;
+    std::vector<double> xmesh, xi, zeta;
+    // device allocations
+    double *d_mesh = nullptr, *d_prm = nullptr, *d_u = nullptr, *d_b = nullptr, *d_F = nullptr, *d_J = nullptr,
+           *d_mass = nullptr, *d_norm = nullptr, *d_hist = nullptr, *d_tmp = nullptr;
+    size_t tmp_elems = 0;
+    int *d_active = nullptr, *d_iters = nullptr, *d_status = nullptr;
+    long long* d_total = nullptr;
+    unsigned int* d_count = nullptr;
+    unsigned int* h_count = nullptr;  // pinned
+    cudaEvent_t ev[kSlots];
+    bool ev_ok = false;
+    // step state
+    double t_next = 0.0, inv_tau = 0.0;
+    long launched = 0, confirmed = 0;
+    int64_t last_active = 0;
+    bool mass_ready = false;
+};
+
+namespace {
+
+size_t node_elems(const sb_problem* pb) { return (size_t)pb->pd.B * pb->pd.L * pb->P; }
+
+int ensure_tmp(sb_problem* pb, size_t elems) {
+    if (pb->tmp_elems >= elems) return SB_OK;
+    if (pb->d_tmp) cudaFree(pb->d_tmp);
+    pb->d_tmp = nullptr; pb->tmp_elems = 0;
+    CU(cudaMalloc((void**)&pb->d_tmp, elems * sizeof(double)));
+    pb->tmp_elems = elems;
+    return SB_OK;
+}
+
+int ensure_jacobian(sb_problem* pb) {
+    if (pb->d_J) return SB_OK;
+    const size_t n = node_elems(pb) * pb->P;
+    CU(cudaMalloc((void**)&pb->d_J, 3 * n * sizeof(double)));
+    pb->pd.Jl = pb->d_J; pb->pd.Jd = pb->d_J + n; pb->pd.Ju = pb->d_J + 2 * n;
+    return SB_OK;
+}
+
+void launch_geometry(const sb_problem* pb, dim3& grid, dim3& block, size_t& smem) {
+    if (pb->warp) {
+        block = dim3(kWarpBlockThreads);
+        grid = dim3((unsigned)((pb->pd.B + (kWarpBlockThreads / 32) - 1) / (kWarpBlockThreads / 32)));
+        smem = 0;
+    } else {
+        block = dim3(pb->pd.T);
+        grid = dim3((unsigned)pb->pd.B);
+        smem = (size_t)(2 * pb->P * pb->P + pb->P) * pb->pd.T * sizeof(double);
+    }
+}
+
+int to_device(sb_problem* pb, const double* src_ref_dev, double* dst, int W, int identity_P) {
+    const size_t n = (size_t)pb->pd.B * pb->pd.L * W;
+    const int bs = 256;
+    k_to_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src_ref_dev, dst, pb->pd.B, pb->pd.Nx, pb->pd.R,
+                                                                               pb->pd.T, W, identity_P);
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+int from_device(sb_problem* pb, const double* src, double* dst_ref_dev, int W) {
+    const size_t n = (size_t)pb->pd.B * pb->pd.Nx * W;
+    const int bs = 256;
+    k_from_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src, dst_ref_dev, pb->pd.B, pb->pd.Nx, pb->pd.R,
+                                                                                 pb->pd.T, W);
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+// host array (reference layout, W per node) -> device array in device layout, through d_tmp
+int upload_nodes(sb_problem* pb, const double* host, double* dst, int W, int identity_P) {
+    const size_t n = (size_t)pb->pd.B * pb->pd.Nx * W;
+    int rc = ensure_tmp(pb, n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pb->d_tmp, host, n * sizeof(double), cudaMemcpyHostToDevice, pb->ctx->stream));
+    return to_device(pb, pb->d_tmp, dst, W, identity_P);
+}
+
+int download_nodes(sb_problem* pb, const double* src, double* host, int W) {
+    const size_t n = (size_t)pb->pd.B * pb->pd.Nx * W;
+    int rc = ensure_tmp(pb, n);
+    if (rc) return rc;
+    rc = from_device(pb, src, pb->d_tmp, W);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host, pb->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, pb->ctx->stream));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    return SB_OK;
+}
+
+int pick_decomposition(int Nx, int P, int* R_out, int* T_out, int* warp_out) {
+    // user override for tuning: SB_ROWS_PER_THREAD = 1,2,4,8,16
+    int Rmax = (P == 1) ? 8 : 4;
+    if (const char* e = getenv("SB_ROWS_PER_THREAD")) {
+        int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || (v == 16 && P == 1)) Rmax = v;
+    }
+    const int Rcap = (P == 1) ? 16 : 8;
+    int R = 1;
+    while (R < Rmax && R * 32 < Nx) R *= 2;          // smallest R whose single warp covers the mesh
+    int T = ((Nx + R - 1) / R + 31) / 32 * 32;
+    while (T > kMaxBlockT && R < Rcap) { R *= 2; T = ((Nx + R - 1) / R + 31) / 32 * 32; }
+    if (T > kMaxBlockT) return SB_ERR_UNSUPPORTED;
+    *R_out = R; *T_out = T; *warp_out = (T == 32);
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sb_version(void) { return "skeelberzins_b200 0.1.0 (sm_100a)"; }
+const char* sb_last_error(void) { return g_err.c_str(); }
+
+int sb_device_count(int* count) {
+    if (!count) return fail(SB_ERR_INVALID, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return fail(SB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return SB_OK;
+}
+
+int sb_ctx_create(int device, void* stream, sb_ctx** out) {
+    if (!out) return fail(SB_ERR_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(SB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SB_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    sb_ctx* c = new sb_ctx;
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { delete c; return fail(SB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return SB_OK;
+}
+
+int sb_ctx_destroy(sb_ctx* ctx) {
+    if (!ctx) return SB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SB_OK;
+}
+
+int sb_ctx_synchronize(sb_ctx* ctx) {
+    if (!ctx) return fail(SB_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name) {
+    if (functor_id < 0 || functor_id >= SB_NUM_BUILTIN_FUNCTORS) return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
+    const FunctorEntry& e = registry()[functor_id];
+    if (npde) *npde = e.npde;
+    if (nparams) *nparams = e.nparams;
+    if (name) *name = e.name;
+    return SB_OK;
+}
+
+int sb_register_user_functor(sb_ctx*, const char*, const char*, int, int, int*) {
+    return fail(SB_ERR_UNSUPPORTED, "user functor plugin slot (NVRTC) is not built in this version");
+}
+
+int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh, int functor_id, const double* params,
+                      int nparams, sb_problem** out) {
+    if (!ctx || !out || !xmesh) return fail(SB_ERR_INVALID, "NULL argument");
+    // asserts of src/pdepe.jl:55-57
+    if (!(m == 0 || m == 1 || m == 2)) return fail(SB_ERR_INVALID, "Parameter m invalid");
+    if (m > 0 && !(xmesh[0] >= 0)) return fail(SB_ERR_INVALID, "Non-conforming mesh");
+    if (Nx < 3) return fail(SB_ERR_INVALID, "Nx = %d: need at least 3 mesh points", Nx);
+    if (B < 1) return fail(SB_ERR_INVALID, "B = %lld: need at least one instance", (long long)B);
+    for (int i = 0; i + 1 < Nx; ++i)
+        if (!(xmesh[i + 1] > xmesh[i])) return fail(SB_ERR_INVALID, "xmesh must be strictly increasing (at index %d)", i);
+    if (functor_id < 0 || functor_id >= SB_NUM_BUILTIN_FUNCTORS) return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
+    const FunctorEntry* fe = &registry()[functor_id];
+    if (nparams != fe->nparams)
+        return fail(SB_ERR_INVALID, "functor %s takes %d parameters per instance, got %d", fe->name, fe->nparams, nparams);
+    if (fe->nparams > 0 && !params) return fail(SB_ERR_INVALID, "params is NULL");
+    CU(cudaSetDevice(ctx->device));
+
+    sb_problem* pb = new sb_problem;
+    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = SB_DESIGN_FUSED;
+    int R, T, warp;
+    if (pick_decomposition(Nx, pb->P, &R, &T, &warp) != SB_OK) {
+        delete pb;
+        return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) of this build", Nx,
+                    kMaxBlockT * (fe->npde == 1 ? 16 : 8));
+    }
+    pb->warp = warp;
+    pb->ri = 0;
+    while ((1 << pb->ri) < R) pb->ri++;
+    ProbDev& pd = pb->pd;
+    memset(&pd, 0, sizeof pd);
+    pd.Nx = Nx; pd.R = R; pd.T = T; pd.L = R * T; pd.m = m; pd.nprm = fe->nparams; pd.B = B;
+    pd.singular = (m >= 1) && (xmesh[0] == 0);  // src/utils.jl:616
+    pb->xmesh.assign(xmesh, xmesh + Nx);
+
+    // quadrature points / weights, src/utils.jl:683-718
+    const int NI = Nx - 1, mp = m + 1;
+    pb->xi.resize(NI); pb->zeta.resize(NI);
+    for (int i = 0; i < NI; ++i) {
+        const double a = xmesh[i], b = xmesh[i + 1], g = (a + b) / 2;
+        double xi, ze;
+        if (m == 0) { xi = g; ze = g; }
+        else if (m == 1) {
+            if (pd.singular) { xi = (2.0 / 3.0) * (a + b - ((a * b) / (a + b))); ze = std::pow((b * b - a * a) / (2 * std::log(b / a)), 0.5); }
+            else { xi = (b - a) / std::log(b / a); ze = std::pow(xi * g, 0.5); }
+        } else {
+            if (pd.singular) xi = (2.0 / 3.0) * (a + b - ((a * b) / (a + b)));
+            else xi = (a * b * std::log(b / a)) / (b - a);
+            ze = std::pow(a * b * g, 1.0 / 3.0);
+        }
+        pb->xi[i] = xi; pb->zeta[i] = ze;
+    }
+    // per-interval interpolation weights (src/utils.jl:18-48) and flux weights, per-node volume weights
+    // (src/assembler.jl:36,68-69,74,84,98), written straight in the [r][t] device layout
+    const size_t L = pd.L;
+    std::vector<double> mesh(7 * L, 0.0);
+    double *h_xi = &mesh[0], *h_aw = &mesh[L], *h_bw = &mesh[2 * L], *h_gw = &mesh[3 * L], *h_wf = &mesh[4 * L],
+           *h_fR = &mesh[5 * L], *h_fL = &mesh[6 * L];
+    for (int i = 0; i < Nx; ++i) {
+        const size_t s = (size_t)(i % R) * T + i / R;
+        if (i < NI) {
+            const double xl = xmesh[i], xr = xmesh[i + 1], q = pb->xi[i];
+            double aw, bw, gw;
+            if (pd.singular) { const double h = xr * xr - xl * xl, th = (q * q - xl * xl) / h; aw = 1 - th; bw = th; gw = (2 * q) / h; }
+            else if (m == 0) { const double h = xr - xl; aw = (xr - q) / h; bw = (q - xl) / h; gw = 1.0 / h; }
+            else if (m == 1) { const double lg = std::log(xr / xl), th = std::log(q / xl) / lg; aw = 1 - th; bw = th; gw = 1.0 / (q * lg); }
+            else { const double h = xr - xl, th = (xr * (q - xl)) / (q * h); aw = 1 - th; bw = th; gw = (xr * xl) / (q * q * h); }
+            h_xi[s] = q; h_aw[s] = aw; h_bw[s] = bw; h_gw[s] = gw;
+            h_wf[s] = pd.singular ? ipow(pb->zeta[i], mp) / q : ipow(q, m);
+            h_fR[s] = (ipow(pb->zeta[i], mp) - ipow(xmesh[i], mp)) / mp;
+        }
+        if (i >= 1) h_fL[s] = (ipow(xmesh[i], mp) - ipow(pb->zeta[i - 1], mp)) / mp;
+    }
+    pd.x0 = xmesh[0]; pd.xN = xmesh[Nx - 1]; pd.x0m = ipow(xmesh[0], m); pd.xNm = ipow(xmesh[Nx - 1], m); pd.xi0 = pb->xi[0];
+
+    int rc = SB_OK;
+    const size_t n = (size_t)B * L * pb->P;
+#define TRY(x) do { if (rc == SB_OK) rc = (x); } while (0)
+    TRY(dev_alloc(&pb->d_mesh, 7 * L));
+    TRY(dev_alloc(&pb->d_prm, (size_t)B * fe->nparams));
+    TRY(dev_alloc(&pb->d_u, n));
+    TRY(dev_alloc(&pb->d_b, n));
+    TRY(dev_alloc(&pb->d_F, n));
+    TRY(dev_alloc(&pb->d_mass, (size_t)B * 3 * pb->P));
+    TRY(dev_alloc(&pb->d_norm, (size_t)B));
+    TRY(dev_alloc(&pb->d_active, (size_t)B));
+    TRY(dev_alloc(&pb->d_iters, (size_t)B));
+    TRY(dev_alloc(&pb->d_status, (size_t)B));
+    TRY(dev_alloc(&pb->d_total, (size_t)B));
+    TRY(dev_alloc(&pb->d_count, (size_t)kSlots));
+#undef TRY
+    if (rc != SB_OK) { sb_problem_destroy(pb); return rc; }
+    cudaError_t e = cudaHostAlloc((void**)&pb->h_count, kSlots * sizeof(unsigned int), cudaHostAllocDefault);
+    if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    for (int i = 0; i < kSlots; ++i) {
+        e = cudaEventCreateWithFlags(&pb->ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+    }
+    pb->ev_ok = true;
+    cudaStream_t st = ctx->stream;
+    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 7 * L * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && fe->nparams > 0)
+        e = cudaMemcpyAsync(pb->d_prm, params, (size_t)B * fe->nparams * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_u, 0, n * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_b, 0, n * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_F, 0, n * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_active, 0, B * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_iters, 0, B * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_status, 0, B * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_total, 0, B * sizeof(long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_norm, 0, B * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
+    if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "problem upload: %s", cudaGetErrorString(e)); }
+    // all-ones mass flags until sb_mass_flags is called
+    {
+        std::vector<double> ones((size_t)B * 3 * pb->P, 1.0);
+        e = cudaMemcpy(pb->d_mass, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "mass init: %s", cudaGetErrorString(e)); }
+    }
+    pd.mesh.xi = pb->d_mesh; pd.mesh.aw = pb->d_mesh + L; pd.mesh.bw = pb->d_mesh + 2 * L; pd.mesh.gw = pb->d_mesh + 3 * L;
+    pd.mesh.wf = pb->d_mesh + 4 * L; pd.mesh.fracR = pb->d_mesh + 5 * L; pd.mesh.fracL = pb->d_mesh + 6 * L;
+    pd.prm = pb->d_prm; pd.u = pb->d_u; pd.b = pb->d_b; pd.F = pb->d_F; pd.mass = pb->d_mass;
+    pd.active = pb->d_active; pd.iters = pb->d_iters; pd.total_iters = pb->d_total; pd.norm = pb->d_norm;
+    pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;
+    pb->last_active = B;
+    *out = pb;
+    return SB_OK;
+}
+
+int sb_problem_destroy(sb_problem* pb) {
+    if (!pb) return SB_OK;
+    cudaSetDevice(pb->ctx->device);
+    cudaStreamSynchronize(pb->ctx->stream);
+    cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
+    cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
+    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count);
+    if (pb->h_count) cudaFreeHost(pb->h_count);
+    if (pb->ev_ok) for (int i = 0; i < kSlots; ++i) cudaEventDestroy(pb->ev[i]);
+    delete pb;
+    return SB_OK;
+}
+
+int sb_problem_info(sb_problem* pb, int* npde, int* Nx, int64_t* B, int* singular) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (npde) *npde = pb->P;
+    if (Nx) *Nx = pb->pd.Nx;
+    if (B) *B = pb->pd.B;
+    if (singular) *singular = pb->pd.singular;
+    return SB_OK;
+}
+
+int sb_problem_layout(sb_problem* pb, int* R, int* T, int* warp) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (R) *R = pb->pd.R;
+    if (T) *T = pb->pd.T;
+    if (warp) *warp = pb->warp;
+    return SB_OK;
+}
+
+int sb_problem_quadrature(sb_problem* pb, double* xi, double* zeta) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (xi) memcpy(xi, pb->xi.data(), pb->xi.size() * sizeof(double));
+    if (zeta) memcpy(zeta, pb->zeta.data(), pb->zeta.size() * sizeof(double));
+    return SB_OK;
+}
+
+int sb_problem_set_design(sb_problem* pb, int design) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED) return fail(SB_ERR_INVALID, "unknown design %d", design);
+    pb->design = design;
+    return SB_OK;
+}
+
+int sb_state_upload(sb_problem* pb, const double* u_host) {
+    if (!pb || !u_host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc = upload_nodes(pb, u_host, pb->d_u, pb->P, 0);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(pb->d_total, 0, pb->pd.B * sizeof(long long), pb->ctx->stream));
+    CU(cudaMemsetAsync(pb->d_status, 0, pb->pd.B * sizeof(int), pb->ctx->stream));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    return SB_OK;
+}
+
+int sb_state_download(sb_problem* pb, double* u_host) {
+    if (!pb || !u_host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    return download_nodes(pb, pb->d_u, u_host, pb->P);
+}
+
+int sb_mass_flags(sb_problem* pb, double t0, int stationary) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    const int bs = 128;
+    pb->fe->mass<<<(unsigned)((pb->pd.B + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(pb->pd, t0, pb->d_mass, stationary);
+    CU(cudaGetLastError());
+    pb->mass_ready = true;
+    return SB_OK;
+}
+
+int sb_mass_download(sb_problem* pb, double* mass_host) {
+    if (!pb || !mass_host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    const int P = pb->P, Nx = pb->pd.Nx;
+    std::vector<double> f((size_t)pb->pd.B * 3 * P);
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    CU(cudaMemcpy(f.data(), pb->d_mass, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < pb->pd.B; ++k)
+        for (int i = 0; i < Nx; ++i) {
+            const int cls = (i == 0) ? 0 : ((i == Nx - 1) ? 2 : 1);
+            for (int p = 0; p < P; ++p) mass_host[((size_t)k * Nx + i) * P + p] = f[(size_t)k * 3 * P + cls * P + p];
+        }
+    return SB_OK;
+}
+
+int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host) {
+    if (!pb || !du_host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    ProbDev pd = pb->pd;
+    double* d_uin = nullptr;
+    if (u_host) {
+        CU(cudaMalloc((void**)&d_uin, node_elems(pb) * sizeof(double)));
+        int rc = upload_nodes(pb, u_host, d_uin, pb->P, 0);
+        if (rc) { cudaFree(d_uin); return rc; }
+        pd.u = d_uin;
+    }
+    dim3 grid, block; size_t smem;
+    launch_geometry(pb, grid, block, smem);
+    AssembleKernel kern = pb->fe->assemble_val[pb->ri][pb->warp];
+    kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
+    cudaError_t e = cudaGetLastError();
+    int rc = SB_OK;
+    if (e != cudaSuccess) rc = fail(SB_ERR_CUDA, "k_assemble launch: %s", cudaGetErrorString(e));
+    if (rc == SB_OK) rc = download_nodes(pb, pb->d_F, du_host, pb->P);
+    if (d_uin) cudaFree(d_uin);
+    return rc;
+}
+
+int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    pb->t_next = t_next; pb->inv_tau = inv_tau;
+    cudaStream_t st = pb->ctx->stream;
+    CU(cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st));
+    const size_t total = (size_t)pb->pd.B * pb->pd.L;
+    const int bs = 256;
+    if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    else k_begin_step<2><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    CU(cudaGetLastError());
+    pb->launched = 0; pb->confirmed = 0; pb->last_active = pb->pd.B;
+    return SB_OK;
+}
+
+static int prepare_slot(sb_problem* pb, int* slot) {
+    const int s = (int)(pb->launched % kSlots);
+    if (pb->launched >= kSlots) {  // ring wrapped: the slot's previous value must have been delivered, then re-zero it
+        CU(cudaEventSynchronize(pb->ev[s]));
+        if (pb->confirmed < pb->launched - kSlots + 1) pb->confirmed = pb->launched - kSlots + 1;
+        CU(cudaMemsetAsync(pb->d_count + s, 0, sizeof(unsigned int), pb->ctx->stream));
+    }
+    *slot = s;
+    return SB_OK;
+}
+
+static int finish_slot(sb_problem* pb, int slot) {
+    CU(cudaMemcpyAsync(pb->h_count + slot, pb->d_count + slot, sizeof(unsigned int), cudaMemcpyDeviceToHost, pb->ctx->stream));
+    CU(cudaEventRecord(pb->ev[slot], pb->ctx->stream));
+    pb->launched++;
+    return SB_OK;
+}
+
+int sb_residual_jacobian(sb_problem* pb) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc = ensure_jacobian(pb);
+    if (rc) return rc;
+    dim3 grid, block; size_t smem;
+    launch_geometry(pb, grid, block, smem);
+    pb->fe->assemble_jac[pb->ri][pb->warp]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+int sb_solve_update_norm(sb_problem* pb, double tol) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (!pb->d_J) return fail(SB_ERR_INVALID, "sb_solve_update_norm called before sb_residual_jacobian");
+    CU(cudaSetDevice(pb->ctx->device));
+    int slot;
+    int rc = prepare_slot(pb, &slot);
+    if (rc) return rc;
+    dim3 grid, block; size_t smem;
+    launch_geometry(pb, grid, block, smem);
+    solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
+    CU(cudaGetLastError());
+    return finish_slot(pb, slot);
+}
+
+int sb_newton_iteration(sb_problem* pb, double tol) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (pb->design == SB_DESIGN_SPLIT) {
+        int rc = sb_residual_jacobian(pb);
+        if (rc) return rc;
+        return sb_solve_update_norm(pb, tol);
+    }
+    CU(cudaSetDevice(pb->ctx->device));
+    int slot;
+    int rc = prepare_slot(pb, &slot);
+    if (rc) return rc;
+    dim3 grid, block; size_t smem;
+    launch_geometry(pb, grid, block, smem);
+    pb->fe->fused[pb->ri][pb->warp]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
+    CU(cudaGetLastError());
+    return finish_slot(pb, slot);
+}
+
+int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active) {
+    if (!pb || !n_active) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    if (pb->launched == 0) { *n_active = pb->last_active; return SB_OK; }
+    if (blocking) {
+        const int s = (int)((pb->launched - 1) % kSlots);
+        CU(cudaEventSynchronize(pb->ev[s]));
+        pb->confirmed = pb->launched;
+        pb->last_active = pb->h_count[s];
+    } else {
+        while (pb->confirmed < pb->launched) {
+            const int s = (int)(pb->confirmed % kSlots);
+            cudaError_t e = cudaEventQuery(pb->ev[s]);
+            if (e == cudaErrorNotReady) break;
+            if (e != cudaSuccess) return fail(SB_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+            pb->last_active = pb->h_count[s];
+            pb->confirmed++;
+        }
+    }
+    *n_active = pb->last_active;
+    return SB_OK;
+}
+
+int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active) {
+    if (!pb || !n_active) return fail(SB_ERR_INVALID, "NULL argument");
+    if (it < 0 || it >= pb->launched) return fail(SB_ERR_INVALID, "iteration %d has not been launched in this step", it);
+    if (it < pb->launched - kSlots) return fail(SB_ERR_INVALID, "iteration %d is older than the %d-slot counter ring", it, kSlots);
+    CU(cudaSetDevice(pb->ctx->device));
+    const int s = it % kSlots;
+    CU(cudaEventSynchronize(pb->ev[s]));
+    *n_active = pb->h_count[s];
+    if (pb->confirmed < it + 1) { pb->confirmed = it + 1; pb->last_active = *n_active; }
+    return SB_OK;
+}
+
+int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (maxit < 1) return fail(SB_ERR_INVALID, "maxit must be >= 1");
+    CU(cudaSetDevice(pb->ctx->device));
+    const long depth = 2;  // iterations kept in flight beyond the last one whose count has been read
+    const long base = pb->launched;
+    long done = 0;          // iterations whose active count has been read
+    int64_t n_act = pb->pd.B;
+    while (true) {
+        while (pb->launched - base < maxit && (pb->launched - base) - done < depth) {
+            int rc = sb_newton_iteration(pb, tol);
+            if (rc) return rc;
+        }
+        const int s = (int)((base + done) % kSlots);
+        CU(cudaEventSynchronize(pb->ev[s]));
+        n_act = pb->h_count[s];
+        done++;
+        pb->confirmed = base + done;
+        pb->last_active = n_act;
+        if (n_act == 0) break;
+        if (done >= maxit) break;
+    }
+    if (iters_done) *iters_done = (int)(pb->launched - base);
+    if (n_act != 0) return fail(SB_ERR_CONVERGENCE, "convergence failed");  // src/utils.jl:336
+    return SB_OK;
+}
+
+#define SB_GET(NAME, TYPE, DEVPTR)                                                                       \
+    int NAME(sb_problem* pb, TYPE* host) {                                                               \
+        if (!pb || !host) return fail(SB_ERR_INVALID, "NULL argument");                                  \
+        CU(cudaSetDevice(pb->ctx->device));                                                              \
+        CU(cudaStreamSynchronize(pb->ctx->stream));                                                      \
+        CU(cudaMemcpy(host, pb->DEVPTR, (size_t)pb->pd.B * sizeof(TYPE), cudaMemcpyDeviceToHost));       \
+        return SB_OK;                                                                                    \
+    }
+SB_GET(sb_get_step_iters, int32_t, d_iters)
+SB_GET(sb_get_last_norm, double, d_norm)
+SB_GET(sb_get_status, int32_t, d_status)
+#undef SB_GET
+
+int sb_get_total_iters(sb_problem* pb, int64_t* host) {
+    if (!pb || !host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    CU(cudaMemcpy(host, pb->d_total, (size_t)pb->pd.B * sizeof(long long), cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+int sb_total_active_iterations(sb_problem* pb, int64_t* total) {
+    if (!pb || !total) return fail(SB_ERR_INVALID, "NULL argument");
+    std::vector<int64_t> h((size_t)pb->pd.B);
+    int rc = sb_get_total_iters(pb, h.data());
+    if (rc) return rc;
+    int64_t s = 0;
+    for (int64_t v : h) s += v;
+    *total = s;
+    return SB_OK;
+}
+
+int sb_enable_history(sb_problem* pb, int cap) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    if (pb->d_hist) { cudaFree(pb->d_hist); pb->d_hist = nullptr; }
+    pb->pd.hist = nullptr; pb->pd.hist_cap = 0;
+    if (cap > 0) {
+        CU(cudaMalloc((void**)&pb->d_hist, (size_t)pb->pd.B * cap * sizeof(double)));
+        CU(cudaMemset(pb->d_hist, 0, (size_t)pb->pd.B * cap * sizeof(double)));
+        pb->pd.hist = pb->d_hist; pb->pd.hist_cap = cap;
+    }
+    return SB_OK;
+}
+
+int sb_get_history(sb_problem* pb, double* hist_host, int cap) {
+    if (!pb || !hist_host) return fail(SB_ERR_INVALID, "NULL argument");
+    if (!pb->d_hist || cap != pb->pd.hist_cap) return fail(SB_ERR_INVALID, "history not enabled with cap %d", cap);
+    CU(cudaSetDevice(pb->ctx->device));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    CU(cudaMemcpy(hist_host, pb->d_hist, (size_t)pb->pd.B * cap * sizeof(double), cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+int sb_debug_download_system(sb_problem* pb, double* F, double* Jl, double* Jd, double* Ju) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (!pb->d_J) return fail(SB_ERR_INVALID, "no Jacobian has been assembled");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc = SB_OK;
+    if (F) rc = download_nodes(pb, pb->d_F, F, pb->P);
+    if (!rc && Jl) rc = download_nodes(pb, pb->pd.Jl, Jl, pb->P * pb->P);
+    if (!rc && Jd) rc = download_nodes(pb, pb->pd.Jd, Jd, pb->P * pb->P);
+    if (!rc && Ju) rc = download_nodes(pb, pb->pd.Ju, Ju, pb->P * pb->P);
+    return rc;
+}
+
+int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const double* Ju, const double* F, double* x) {
+    if (!pb || !Jl || !Jd || !Ju || !F || !x) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc = ensure_jacobian(pb);
+    if (rc) return rc;
+    const int PP = pb->P * pb->P;
+    if ((rc = upload_nodes(pb, Jl, pb->pd.Jl, PP, 0))) return rc;
+    if ((rc = upload_nodes(pb, Jd, pb->pd.Jd, PP, pb->P))) return rc;
+    if ((rc = upload_nodes(pb, Ju, pb->pd.Ju, PP, 0))) return rc;
+    if ((rc = upload_nodes(pb, F, pb->d_F, pb->P, 0))) return rc;
+    dim3 grid, block; size_t smem;
+    launch_geometry(pb, grid, block, smem);
+    solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, 0.0, 0, 0);
+    CU(cudaGetLastError());
+    return download_nodes(pb, pb->d_F, x, pb->P);
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/skeelberzins_b200.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sb_build", os.path.join(ROOT, "skeelberzins.jl_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "skeelberzins_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
+
+
+def test_python_binding_covers_header(built_lib):
+    import skeelberzins_jl_b200 as sb
+    from skeelberzins_jl_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    _lib.load()
+    assert b"sm_100a" in _lib.load().sb_version()
+    assert sb.functor_info(5) == (2, 3, "REACT_DIFF")
+    for fid in range(10):
+        npde, nprm, _ = sb.functor_info(fid)
+        from skeelberzins_jl_b200 import examples as ex
+        assert npde == ex.FUNCTOR_NPDE[fid] and nprm == ex.FUNCTOR_NPARAMS[fid]
+
+
+def test_no_cpu_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import skeelberzins_jl_b200 as sb
+    with pytest.raises(sb.SBError, match="no CPU fallback"):
+        sb.Context(0)
+    from skeelberzins_jl_b200 import examples as ex
+    c = ex.example101()
+    with pytest.raises(sb.SBError):
+        sb.pdepe(c.m, sb.Functor(c.functor, c.params), c.icfun, None, c.xmesh, c.tspan)
+
+
+def test_oracle_is_not_imported_by_product():
+    pkg = os.path.join(ROOT, "skeelberzins.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "sb_oracle" not in src and "libsb_oracle" not in src, f
+
+
+def test_time_grid_matches_julia_ranges():
+    import numpy as np
+    import skeelberzins_jl_b200 as sb
+    g = sb.julia_range(0, 1e-2, 1)
+    assert g.size == 101 and all(g[i] == i / 100 for i in range(101))
+    g = sb.julia_range(0.001, 1e-4, 0.01)
+    assert g.size == 91 and g[0] == 0.001 and g[-1] == 0.01 and g[45] == 0.0055
+    g = sb.julia_range(0, 1 / 49, 1)          # Example201: tstep = 1/(n-1)
+    assert g.size == 50 and all(g[i] == i / 49 for i in range(50))
+    g = sb.julia_range(0.0, 1e-2, 0.8)
+    assert g.size == 81 and g[-1] == 0.8
+    grid, tau = sb.time_grid((0, 1), np.array([0.0, 0.1, 0.3, 1.0]))
+    assert tau is None and grid.tolist() == [0.0, 0.1, 0.3, 1.0]
