@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- mesh-point x Newton-steps per second of the batched implicit-Euler path on B200.
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) cfg 2): Example102 nonlinear diffusion
+f = a_k*u*u_x, a_k = 1 + 2k/B, B = 4096 instances per GPU x Nx = 1024 mesh points on [-1, 1],
+implicit Euler t = 0.001 .. 0.01 with tau = 1e-4 (90 time steps), Newton tol 1e-10 / maxit 100.
+
+One bench "step" = one complete batched pdepe solve (all 90 time steps) of the per-GPU batch.
+unit of work = one mesh node of one ACTIVE instance for one Newton iteration; the per-instance
+iteration counters live on the device, frozen (converged) instances do not count.
+
+  value : whole-job units/s with inputs resident in HBM (state restored from a device-side copy)
+  e2e   : the same metric through the public pdepe() call with HOST buffers (pinned u0 H2D,
+          problem set-up, solve, final state D2H inside the timed region)
+  roofline : the dominant kernel (fused Newton iteration, or assemble/solve for --design split):
+          algorithmic bytes per launch / average launch duration, timed with CUDA events on the
+          launching stream in a separate profiled solve inside this script
+  cpu_baseline : the CPU oracle (restatement of the reference algorithm, OpenMP over instances) on
+          a bounded sample of the same workload.  The reference itself is Julia and cannot run here.
+
+python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU)
+python bench.py --impl reference ...                     (CPU arm: oracle port on all host threads)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mesh-point*Newton-steps/sec, batched implicit Euler"
+UNIT = "mesh-point*Newton-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", help="BASELINE config: 2 (default), 3a, 3b, 4")
+    ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused"), choices=["fused", "split"])
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's B)")
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--time-steps", type=int, default=0, help="truncate the time loop (testing only)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="instances in the cpu_baseline sample")
+    ap.add_argument("--python-loop", action="store_true", help="drive Newton from Python instead of the C loop")
+    return ap.parse_args()
+
+
+def make_case(args, world):
+    from skeelberzins_jl_b200 import examples as ex
+    base = ex.baseline_case(args.config)
+    Bp = args.batch or base.B
+    Nx = args.nx or base.xmesh.size
+    case = ex.baseline_case(args.config, B=Bp * world, Nx=Nx)   # the sweep spans the whole job
+    return case, Bp, Nx
+
+
+def time_grid_of(case, args):
+    import skeelberzins_jl_b200 as sb
+    tg, tau = sb.time_grid(case.tspan, case.tstep)
+    if args.time_steps:
+        tg = tg[:args.time_steps + 1]
+    return tg, tau
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            hi = [v for v in sm if v >= 0.5 * max(sm)] or sm
+            out.update(sm_mhz=float(np.median(hi)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes_per_unit(design, P):
+    """fp64 SoA bytes one mesh node of one active instance moves per Newton iteration:
+    fused: read u, read b, write u.  split: assemble R u,b / W F,J ; solve R J,F,u / W u."""
+    if design == "fused":
+        return {"fused": 24 * P}
+    return {"assemble": 16 * P + 8 * P + 24 * P * P, "solve": 24 * P * P + 16 * P + 8 * P}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_baseline(args, case_full, Nx, tg, tau, sample, nthreads=0):
+    """CPU oracle (port of the reference algorithm) on a bounded sample of the same sweep."""
+    from oracle import sb_oracle
+    from skeelberzins_jl_b200 import examples as ex
+    B = case_full.B
+    idx = np.unique(np.linspace(0, B - 1, min(sample, B)).astype(np.int64))
+    prm = case_full.params[idx]
+    u0 = np.asarray(case_full.icfun(case_full.xmesh), dtype=np.float64).reshape(1, Nx, case_full.npde)
+    u0 = np.broadcast_to(u0, (idx.size, Nx, case_full.npde))
+    t0 = time.perf_counter()
+    r = sb_oracle.pdepe_transient(case_full.functor, case_full.m, case_full.xmesh, prm, u0, tg, tau, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    units = float(r["iters"].sum()) * Nx
+    return units / dt, dt, int(idx.size), sb_oracle.num_threads(), r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import sb_oracle
+    sb_oracle.build()
+    case, Bp, Nx = make_case(args, 1)
+    tg, tau = time_grid_of(case, args)
+    sample = max(8, min(args.cpu_sample, 32))
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(args, case, Nx, tg, tau, 8)
+    vals, times = [], []
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, n, th, _ = cpu_baseline(args, case, Nx, tg, tau, sample)
+        vals.append(v)
+        times.append(dt)
+        if time.perf_counter() - t_start > 150:
+            break
+    value = float(np.mean(vals))
+    cores = sb_oracle.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg%s %s: CPU oracle (port of the reference algorithm; the Julia reference cannot run "
+                               "here), %d-instance sample of the %d x %d sweep per step, %d time steps"
+                               % (args.config, case.name, sample, Bp, Nx, tg.size - 1)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d instances x %d nodes x %d time steps per step, OpenMP over instances" % (sample, Nx, tg.size - 1)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import skeelberzins_jl_b200 as sb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    case, Bp, Nx = make_case(args, world)
+    tg, tau = time_grid_of(case, args)
+    P = case.npde
+    lo, hi = rank * Bp, (rank + 1) * Bp                       # shard by instance index, no collective on the path
+    prm = np.ascontiguousarray(case.params[lo:hi])
+    u0_t = torch.empty((Bp, Nx, P), dtype=torch.float64).pin_memory()
+    u0 = u0_t.numpy()
+    u0[:] = np.asarray(case.icfun(case.xmesh), dtype=np.float64).reshape(1, Nx, P)
+    out_t = torch.empty((Bp, Nx, P), dtype=torch.float64).pin_memory()
+
+    stream = torch.cuda.Stream()
+    ctx = sb.Context(local, stream=stream.cuda_stream)
+    fn = sb.Functor(case.functor, prm)
+    dev = sb.DeviceProblem(ctx, case.m, case.xmesh, fn, design=args.design)
+    dev.upload(u0)
+    dev.checkpoint()
+    tol, maxit = 1e-10, 100
+    nsteps = tg.size - 1
+
+    def solve_resident():
+        dev.rollback()
+        dev.mass_flags(tg[0])
+        for i in range(nsteps):
+            tau_i = tau if tau is not None else tg[i + 1] - tg[i]
+            dev.begin_step(tg[i + 1], 1.0 / tau_i)
+            if args.python_loop:
+                sb.api._newton_loop(dev, tol, maxit)
+            else:
+                dev.newton_solve(tol, maxit)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solve_resident()
+    ctx.synchronize()
+    inst_iters = dev.total_active_iterations()                 # per solve (deterministic)
+    units_per_step = inst_iters * Nx
+
+    # ---- value: K solves from HBM-resident inputs --------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.start()
+    l0 = sb.kernel_launches()
+    e0.record(stream)
+    for _ in range(args.steps):
+        solve_resident()
+    e1.record(stream)
+    barrier()
+    launches = sb.kernel_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    assert dev.total_active_iterations() == inst_iters
+    status_bad = int((dev.status() != 0).sum())
+
+    # ---- e2e: the public pdepe() call with host buffers ---------------------------------------------
+    tstep_arg = case.tstep if not args.time_steps else tg
+    tspan_arg = (tg[0], tg[-1])
+
+    def solve_e2e():
+        f2 = sb.Functor(case.functor, prm)
+        sol = sb.pdepe(case.m, f2, u0, f2, case.xmesh, tspan_arg, ctx=ctx, design=args.design, tstep=tstep_arg,
+                       save="last", squeeze=False, c_loop=not args.python_loop)
+        return sol.u[-1]
+
+    last = solve_e2e()                                         # warm-up (allocator, page-ins)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(1, min(args.steps, 4))
+    barrier()
+    f0.record(stream)
+    for _ in range(n_e2e):
+        last = solve_e2e()
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    checksum = float(np.asarray(last).sum())
+    h2d = u0.nbytes + prm.nbytes + 7 * 8 * Nx
+    d2h = u0.nbytes + 4 * int(launches // max(args.steps, 1))   # final state + one 4-byte active counter per launch
+
+    # ---- roofline: profiled solve, CUDA events around every Newton-iteration launch -------------------
+    dev.rollback()
+    dev.mass_flags(tg[0])
+    dev.profile_begin()
+    for i in range(nsteps):
+        tau_i = tau if tau is not None else tg[i + 1] - tg[i]
+        dev.begin_step(tg[i + 1], 1.0 / tau_i)
+        dev.newton_solve(tol, maxit)
+    prof = dev.profile_end()
+    bpu = algorithmic_bytes_per_unit(args.design, P)
+    peak, peak_kind = hbm_peak()
+    kern = {}
+    if args.design == "fused":
+        kern["fused"] = prof["ms_solve"]
+    else:
+        kern["assemble"], kern["solve"] = prof["ms_assemble"], prof["ms_solve"]
+    dom = max(kern, key=lambda k: kern[k])
+    n_launch = max(prof["launches"], 1)
+    bytes_total = prof["instance_iterations"] * Nx * bpu[dom]
+    achieved = bytes_total / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("%s_%s" % (args.design, dom))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind if peak_kind == "measured" else "of fallback",
+        "kernel": "k_newton_fused" if dom == "fused" else "k_" + dom,
+        "avg_launch_us": 1e3 * kern[dom] / n_launch, "launches_profiled": prof["launches"],
+        "noop_launches_profiled": prof["noop_launches"],
+        "algorithmic_bytes_per_unit": bpu[dom], "units_per_launch_avg": prof["instance_iterations"] * Nx / n_launch,
+        "kernel_ms_per_step": {k: v for k, v in kern.items()},
+        "kernel_share_of_step": sum(kern.values()) / (ms / args.steps),
+        "lockstep_efficiency": prof["instance_iterations"] / float(n_launch * Bp),
+    }
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------
+    tot_units, max_ms, max_ms_e2e = float(units_per_step), float(ms), float(ms_e2e)
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms, max_ms_e2e = float(t[0]), float(t[1])
+        s = torch.tensor([float(units_per_step), float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        tot_units, launches = float(s[0]), int(s[1])
+    value = tot_units * args.steps / (max_ms * 1e-3)
+    e2e_value = tot_units * n_e2e / (max_ms_e2e * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import sb_oracle
+        sb_oracle.build()
+        v, dt, n, th, r = cpu_baseline(args, case, Nx, tg, tau, args.cpu_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+               "sample": "%d evenly spaced instances of the sweep x %d nodes x %d time steps, OpenMP over instances, "
+                         "%.1f s; CPU restatement (oracle), not the Julia reference" % (n, Nx, nsteps, dt)}
+
+    if rank == 0:
+        lay = dev.layout()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg%s %s: B=%d instances/GPU x Nx=%d, %d implicit-Euler steps per bench step, "
+                                   "tol 1e-10, maxit 100" % (args.config, case.name, Bp, Nx, nsteps),
+                       "design": args.design, "rows_per_thread": lay["R"], "threads_per_system": lay["T"],
+                       "l2_policy": "inputs larger than L2 (state + rhs = %.0f MB per GPU%s)"
+                                    % (2 * u0.nbytes / 1e6, "; split design adds %.0f MB of F/J" % (4 * P * u0.nbytes / 1e6) if args.design == "split" else ""),
+                       "newton_loop": "python" if args.python_loop else "C (sb_newton_solve)",
+                       "instances_total": Bp * world, "units_per_step": tot_units},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": max_ms_e2e / n_e2e, "steps": n_e2e, "result_checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "instances_not_converged_or_nonfinite": status_bad,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,6 +98,8 @@ enum sb_design {
 const char* sb_version(void);
 const char* sb_last_error(void);
 int sb_device_count(int* count);
+/* number of CUDA kernels this library has launched so far in the process (bench.py's gpu_launches) */
+int sb_kernel_launches(int64_t* count);
 /* stream == NULL: the context creates its own non-blocking stream; otherwise a cudaStream_t of the
  * caller (e.g. the torch current stream, so that the caller's events bracket the kernels).       */
 int sb_ctx_create(int device, void* stream, sb_ctx** out);
@@ -139,6 +141,11 @@ int sb_problem_layout(sb_problem* pb, int* R, int* T, int* warp);
 /* state u (reference layout on the host side; the device keeps a chunk-transposed SoA layout)   */
 int sb_state_upload(sb_problem* pb, const double* u_host);
 int sb_state_download(sb_problem* pb, double* u_host);
+
+/* device-side copy of the state (device layout) and its restore; rollback also clears the iteration
+ * counters.  Lets a caller re-run a solve from HBM-resident inputs (bench.py's `value` leg).      */
+int sb_state_checkpoint(sb_problem* pb);
+int sb_state_rollback(sb_problem* pb);
 
 /* mass_matrix (src/assembler.jl:138-174): 0/1 flags per (instance, component, node class) from the
  * CURRENT state at time t0 (call right after uploading the initial condition).  stationary != 0
@@ -190,6 +197,14 @@ int sb_enable_history(sb_problem* pb, int cap);
 int sb_get_history(sb_problem* pb, double* hist_host, int cap);
 /* sum over instances of Newton iterations since upload (the work counter of the metric)         */
 int sb_total_active_iterations(sb_problem* pb, int64_t* total);
+
+/* Profiling window: between begin and end every Newton-iteration launch is bracketed by timed CUDA
+ * events on the context's stream.  end() returns the summed kernel time (ms) of the launches that
+ * had work (split: assemble and solve separately; fused: ms_assemble = 0), their number, the number
+ * of no-op launches (every instance already converged) and the active instance-iterations executed. */
+int sb_profile_begin(sb_problem* pb);
+int sb_profile_end(sb_problem* pb, double* ms_assemble, double* ms_solve, int64_t* launches,
+                   int64_t* noop_launches, int64_t* instance_iterations);
 
 /* device-side scratch access for parity tests of the assemble kernel: F and J of the last
  * sb_residual_jacobian in reference layout: F[B][Nx][npde], Jl/Jd/Ju[B][Nx][npde][npde]

@@ -22,6 +22,7 @@ SIGNATURES = {
     "sb_version": (_c.c_char_p, []),
     "sb_last_error": (_c.c_char_p, []),
     "sb_device_count": (_c.c_int, [_c.POINTER(_c.c_int)]),
+    "sb_kernel_launches": (_c.c_int, [_c.POINTER(_c.c_int64)]),
     "sb_ctx_create": (_c.c_int, [_c.c_int, _vp, _c.POINTER(_vp)]),
     "sb_ctx_destroy": (_c.c_int, [_vp]),
     "sb_ctx_synchronize": (_c.c_int, [_vp]),
@@ -35,6 +36,11 @@ SIGNATURES = {
     "sb_problem_set_design": (_c.c_int, [_vp, _c.c_int]),
     "sb_state_upload": (_c.c_int, [_vp, _vp]),
     "sb_state_download": (_c.c_int, [_vp, _vp]),
+    "sb_state_checkpoint": (_c.c_int, [_vp]),
+    "sb_state_rollback": (_c.c_int, [_vp]),
+    "sb_profile_begin": (_c.c_int, [_vp]),
+    "sb_profile_end": (_c.c_int, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double), _c.POINTER(_c.c_int64),
+                                  _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "sb_mass_flags": (_c.c_int, [_vp, _c.c_double, _c.c_int]),
     "sb_mass_download": (_c.c_int, [_vp, _vp]),
     "sb_assemble": (_c.c_int, [_vp, _vp, _c.c_double, _vp]),

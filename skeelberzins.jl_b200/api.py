@@ -75,6 +75,13 @@ def functor_info(fid):
     return npde.value, nprm.value, name.value.decode()
 
 
+def kernel_launches():
+    """CUDA kernels launched by the library so far in this process."""
+    n = ctypes.c_int64()
+    _lib.check(_lib.load().sb_kernel_launches(ctypes.byref(n)))
+    return n.value
+
+
 class Context:
     """One per GPU (sb_ctx).  stream: a cudaStream_t handle (int) to run on, or None for an own stream."""
 
@@ -170,6 +177,23 @@ class DeviceProblem:
             out = np.empty((self.B, self.Nx, self.npde))
         _lib.check(self.lib.sb_state_download(self._h, _lib.ptr(out)))
         return out
+
+    def checkpoint(self):
+        _lib.check(self.lib.sb_state_checkpoint(self._h))
+
+    def rollback(self):
+        _lib.check(self.lib.sb_state_rollback(self._h))
+
+    def profile_begin(self):
+        _lib.check(self.lib.sb_profile_begin(self._h))
+
+    def profile_end(self):
+        a, s = ctypes.c_double(), ctypes.c_double()
+        n, z, ii = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.sb_profile_end(self._h, ctypes.byref(a), ctypes.byref(s), ctypes.byref(n), ctypes.byref(z),
+                                           ctypes.byref(ii)))
+        return dict(ms_assemble=a.value, ms_solve=s.value, launches=n.value, noop_launches=z.value,
+                    instance_iterations=ii.value)
 
     def mass_flags(self, t0, stationary=False):
         _lib.check(self.lib.sb_mass_flags(self._h, float(t0), int(bool(stationary))))

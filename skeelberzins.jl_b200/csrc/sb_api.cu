@@ -43,6 +43,8 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
 
+long long g_launches = 0;  // kernels launched by this library (all contexts; not thread-safe by design)
+
 // reference layout [B][Nx][W] <-> device layout [B][R][T][W]   (W doubles per node)
 // identity != 0: padding nodes receive the W = P*P identity block (used for Jd)
 __global__ void k_to_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
@@ -143,6 +145,14 @@ struct sb_problem {
     long launched = 0, confirmed = 0;
     int64_t last_active = 0;
     bool mass_ready = false;
+    double* d_ckpt = nullptr;  // sb_state_checkpoint copy of u (device layout)
+    // profiling (sb_profile_begin/end): timed events around every Newton-iteration launch
+    bool prof = false, prof_ev_ok = false;
+    cudaEvent_t evA[kSlots], evM[kSlots], evB[kSlots];
+    long prof_harvested = 0;
+    int64_t prof_prev_active = 0;
+    double prof_ms_assemble = 0.0, prof_ms_solve = 0.0;
+    int64_t prof_launches = 0, prof_noop = 0, prof_inst_iters = 0;
 };
 
 namespace {
@@ -183,6 +193,7 @@ int to_device(sb_problem* pb, const double* src_ref_dev, double* dst, int W, int
     const int bs = 256;
     k_to_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src_ref_dev, dst, pb->pd.B, pb->pd.Nx, pb->pd.R,
                                                                                pb->pd.T, W, identity_P);
+    ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
 }
@@ -192,6 +203,7 @@ int from_device(sb_problem* pb, const double* src, double* dst_ref_dev, int W) {
     const int bs = 256;
     k_from_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src, dst_ref_dev, pb->pd.B, pb->pd.Nx, pb->pd.R,
                                                                                  pb->pd.T, W);
+    ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
 }
@@ -239,6 +251,12 @@ extern "C" {
 
 const char* sb_version(void) { return "skeelberzins_b200 0.1.0 (sm_100a)"; }
 const char* sb_last_error(void) { return g_err.c_str(); }
+
+int sb_kernel_launches(int64_t* count) {
+    if (!count) return fail(SB_ERR_INVALID, "count is NULL");
+    *count = g_launches;
+    return SB_OK;
+}
 
 int sb_device_count(int* count) {
     if (!count) return fail(SB_ERR_INVALID, "count is NULL");
@@ -435,7 +453,8 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
     cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
-    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count);
+    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt);
+    if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ev_ok) for (int i = 0; i < kSlots; ++i) cudaEventDestroy(pb->ev[i]);
     delete pb;
@@ -495,6 +514,7 @@ int sb_mass_flags(sb_problem* pb, double t0, int stationary) {
     CU(cudaSetDevice(pb->ctx->device));
     const int bs = 128;
     pb->fe->mass<<<(unsigned)((pb->pd.B + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(pb->pd, t0, pb->d_mass, stationary);
+    ++g_launches;
     CU(cudaGetLastError());
     pb->mass_ready = true;
     return SB_OK;
@@ -530,6 +550,7 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     launch_geometry(pb, grid, block, smem);
     AssembleKernel kern = pb->fe->assemble_val[pb->ri][pb->warp];
     kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     int rc = SB_OK;
     if (e != cudaSuccess) rc = fail(SB_ERR_CUDA, "k_assemble launch: %s", cudaGetErrorString(e));
@@ -538,9 +559,36 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     return rc;
 }
 
+// profiling: fold the timed events of iterations [prof_harvested, launched) of the current step into the totals
+static int prof_harvest(sb_problem* pb) {
+    if (!pb->prof || pb->prof_harvested >= pb->launched) return SB_OK;
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    for (long j = pb->prof_harvested; j < pb->launched; ++j) {
+        const int s = (int)(j % kSlots);
+        const int64_t before = (j == 0) ? pb->pd.B : pb->prof_prev_active;
+        float ms_a = 0.f, ms_s = 0.f;
+        if (pb->design == SB_DESIGN_SPLIT) {
+            CU(cudaEventElapsedTime(&ms_a, pb->evA[s], pb->evM[s]));
+            CU(cudaEventElapsedTime(&ms_s, pb->evM[s], pb->evB[s]));
+        } else {
+            CU(cudaEventElapsedTime(&ms_s, pb->evA[s], pb->evB[s]));
+        }
+        if (before > 0) {
+            pb->prof_ms_assemble += ms_a; pb->prof_ms_solve += ms_s;
+            pb->prof_launches += 1; pb->prof_inst_iters += before;
+        } else {
+            pb->prof_noop += 1;
+        }
+        pb->prof_prev_active = pb->h_count[s];
+    }
+    pb->prof_harvested = pb->launched;
+    return SB_OK;
+}
+
 int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
+    if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; pb->prof_harvested = 0; }
     pb->t_next = t_next; pb->inv_tau = inv_tau;
     cudaStream_t st = pb->ctx->stream;
     CU(cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st));
@@ -548,6 +596,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     const int bs = 256;
     if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
     else k_begin_step<2><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    ++g_launches;
     CU(cudaGetLastError());
     pb->launched = 0; pb->confirmed = 0; pb->last_active = pb->pd.B;
     return SB_OK;
@@ -556,6 +605,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
 static int prepare_slot(sb_problem* pb, int* slot) {
     const int s = (int)(pb->launched % kSlots);
     if (pb->launched >= kSlots) {  // ring wrapped: the slot's previous value must have been delivered, then re-zero it
+        if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; }
         CU(cudaEventSynchronize(pb->ev[s]));
         if (pb->confirmed < pb->launched - kSlots + 1) pb->confirmed = pb->launched - kSlots + 1;
         CU(cudaMemsetAsync(pb->d_count + s, 0, sizeof(unsigned int), pb->ctx->stream));
@@ -578,8 +628,12 @@ int sb_residual_jacobian(sb_problem* pb) {
     if (rc) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
+    const int ps = (int)(pb->launched % kSlots);
+    if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
     pb->fe->assemble_jac[pb->ri][pb->warp]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+    ++g_launches;
     CU(cudaGetLastError());
+    if (pb->prof) CU(cudaEventRecord(pb->evM[ps], pb->ctx->stream));
     return SB_OK;
 }
 
@@ -593,7 +647,9 @@ int sb_solve_update_norm(sb_problem* pb, double tol) {
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
+    ++g_launches;
     CU(cudaGetLastError());
+    if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
     return finish_slot(pb, slot);
 }
 
@@ -610,8 +666,11 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
     if (rc) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
+    if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
     pb->fe->fused[pb->ri][pb->warp]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
+    ++g_launches;
     CU(cudaGetLastError());
+    if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
     return finish_slot(pb, slot);
 }
 
@@ -709,6 +768,58 @@ int sb_total_active_iterations(sb_problem* pb, int64_t* total) {
     return SB_OK;
 }
 
+int sb_state_checkpoint(sb_problem* pb) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    const size_t bytes = node_elems(pb) * sizeof(double);
+    if (!pb->d_ckpt) CU(cudaMalloc((void**)&pb->d_ckpt, bytes));
+    CU(cudaMemcpyAsync(pb->d_ckpt, pb->d_u, bytes, cudaMemcpyDeviceToDevice, pb->ctx->stream));
+    return SB_OK;
+}
+
+int sb_state_rollback(sb_problem* pb) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (!pb->d_ckpt) return fail(SB_ERR_INVALID, "no checkpoint taken");
+    CU(cudaSetDevice(pb->ctx->device));
+    cudaStream_t st = pb->ctx->stream;
+    CU(cudaMemcpyAsync(pb->d_u, pb->d_ckpt, node_elems(pb) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(pb->d_total, 0, pb->pd.B * sizeof(long long), st));
+    CU(cudaMemsetAsync(pb->d_status, 0, pb->pd.B * sizeof(int), st));
+    return SB_OK;
+}
+
+int sb_profile_begin(sb_problem* pb) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    if (!pb->prof_ev_ok) {
+        for (int i = 0; i < kSlots; ++i) {
+            CU(cudaEventCreate(&pb->evA[i])); CU(cudaEventCreate(&pb->evM[i])); CU(cudaEventCreate(&pb->evB[i]));
+        }
+        pb->prof_ev_ok = true;
+    }
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    pb->prof = true; pb->prof_harvested = pb->launched; pb->prof_prev_active = pb->last_active;
+    pb->prof_ms_assemble = pb->prof_ms_solve = 0.0;
+    pb->prof_launches = pb->prof_noop = pb->prof_inst_iters = 0;
+    return SB_OK;
+}
+
+int sb_profile_end(sb_problem* pb, double* ms_assemble, double* ms_solve, int64_t* launches, int64_t* noop_launches,
+                   int64_t* instance_iterations) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (!pb->prof) return fail(SB_ERR_INVALID, "profiling is not active");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc = prof_harvest(pb);
+    if (rc) return rc;
+    pb->prof = false;
+    if (ms_assemble) *ms_assemble = pb->prof_ms_assemble;
+    if (ms_solve) *ms_solve = pb->prof_ms_solve;
+    if (launches) *launches = pb->prof_launches;
+    if (noop_launches) *noop_launches = pb->prof_noop;
+    if (instance_iterations) *instance_iterations = pb->prof_inst_iters;
+    return SB_OK;
+}
+
 int sb_enable_history(sb_problem* pb, int cap) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
@@ -757,6 +868,7 @@ int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const dou
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, 0.0, 0, 0);
+    ++g_launches;
     CU(cudaGetLastError());
     return download_nodes(pb, pb->d_F, x, pb->P);
 }

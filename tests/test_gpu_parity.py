@@ -156,7 +156,8 @@ def test_reference_examples_stationary(ctx, oracle, design, make, c0):
     assert u.sum() == pytest.approx(c.golden, rel=RTOL)
     assert _relerr(u, r["u"][0, :, 0]) < RTOL
     assert len(hist) == r["iters"][0]
-    assert np.allclose(hist[:3], r["hist"][0, :3], rtol=1e-8)
+    n = min(3, len(hist) - 1)   # the last norm is round-off of a converged iterate
+    assert np.allclose(hist[:n], r["hist"][0, :n], rtol=1e-8)
 
 
 def test_example201_boundary_flux_golden(ctx):
