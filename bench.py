@@ -164,9 +164,11 @@ def run_reference(args):
     sb_oracle.build()
     case, Bp, Nx = make_case(args, 1)
     tg, tau = time_grid_of(case, args)
-    sample = max(8, min(args.cpu_sample, 32))
+    v0, dt0, n0, _, _ = cpu_baseline(args, case, Nx, tg, tau, 16)   # warm-up + calibration
+    # each step: a bounded sample sized for ~8 s of CPU work on all host threads
+    sample = int(min(case.B, max(16, n0 * 8.0 / max(dt0, 1e-3))))
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline(args, case, Nx, tg, tau, 8)
+        cpu_baseline(args, case, Nx, tg, tau, 16)
     vals, times = [], []
     t_start = time.perf_counter()
     for _ in range(args.steps):
@@ -345,7 +347,11 @@ def run_ours(args):
     if rank == 0 and world == 1:
         from oracle import sb_oracle
         sb_oracle.build()
-        v, dt, n, th, r = cpu_baseline(args, case, Nx, tg, tau, args.cpu_sample)
+        v, dt, n, th, r = cpu_baseline(args, case, Nx, tg, tau, min(args.cpu_sample, 64))   # calibration
+        target_s = 12.0                                          # bounded sample: ~10-30 s of CPU work
+        n_big = int(min(case.B, max(n, n * target_s / max(dt, 1e-3))))
+        if n_big > n:
+            v, dt, n, th, r = cpu_baseline(args, case, Nx, tg, tau, n_big)
         cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
                "sample": "%d evenly spaced instances of the sweep x %d nodes x %d time steps, OpenMP over instances, "
                          "%.1f s; CPU restatement (oracle), not the Julia reference" % (n, Nx, nsteps, dt)}

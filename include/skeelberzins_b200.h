@@ -134,6 +134,9 @@ int sb_problem_destroy(sb_problem* pb);
 int sb_problem_info(sb_problem* pb, int* npde, int* Nx, int64_t* B, int* singular);
 int sb_problem_quadrature(sb_problem* pb, double* xi_host, double* zeta_host);
 int sb_problem_set_design(sb_problem* pb, int design);
+/* replace the per-instance functor parameters [B*nparams] of an existing problem (same batch, same
+ * mesh): lets a host re-use the device allocations across solves of a parameter study.            */
+int sb_problem_set_params(sb_problem* pb, const double* params_host);
 /* thread decomposition chosen for the batch: R rows per thread, T threads per system (T == 32: one warp
  * per system, shuffles only; T > 32: one CTA per system, shared-memory exchange)                      */
 int sb_problem_layout(sb_problem* pb, int* R, int* T, int* warp);

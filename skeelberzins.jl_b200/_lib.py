@@ -34,6 +34,7 @@ SIGNATURES = {
     "sb_problem_layout": (_c.c_int, [_vp, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int)]),
     "sb_problem_quadrature": (_c.c_int, [_vp, _vp, _vp]),
     "sb_problem_set_design": (_c.c_int, [_vp, _c.c_int]),
+    "sb_problem_set_params": (_c.c_int, [_vp, _vp]),
     "sb_state_upload": (_c.c_int, [_vp, _vp]),
     "sb_state_download": (_c.c_int, [_vp, _vp]),
     "sb_state_checkpoint": (_c.c_int, [_vp]),

@@ -128,6 +128,8 @@ class DeviceProblem:
                                               ctypes.byref(h)))
         self._h = h
         self.B, self.Nx, self.npde = functor.batch, x.size, functor.npde
+        self.nparams, self.functor_id, self.m = functor.nparams, int(functor.id), int(m)
+        self._mesh_key = x.tobytes()
         self.set_design(design)
 
     def close(self):
@@ -140,6 +142,12 @@ class DeviceProblem:
             self.close()
         except Exception:
             pass
+
+    def set_params(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        if p.shape != (self.B, self.nparams):
+            raise ValueError("expected params of shape %r" % ((self.B, self.nparams),))
+        _lib.check(self.lib.sb_problem_set_params(self._h, _lib.ptr(p)))
 
     def set_design(self, design):
         d = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED}[design] if isinstance(design, str) else int(design)
@@ -287,6 +295,45 @@ class DeviceProblem:
         return x
 
 
+# Pool of device problems that pdepe() created and no caller holds: a parameter study calls pdepe() again and
+# again with the same mesh / batch / functor, and re-using the device allocations (cudaMalloc/cudaFree
+# synchronise the device) is what keeps the end-to-end call close to the kernel time.
+_pool = {}
+_POOL_MAX = 2
+
+
+def _pool_key(ctx, m, x, functor):
+    return (id(ctx), int(m), int(functor.id), functor.batch, x.tobytes())
+
+
+def _acquire(ctx, m, x, functor, design):
+    lst = _pool.get(_pool_key(ctx, m, x, functor))
+    if lst:
+        dev = lst.pop()
+        dev.set_params(functor.params)
+        dev.set_design(design)
+        return dev
+    return DeviceProblem(ctx, m, x, functor, design)
+
+
+def _release(dev):
+    key = (id(dev.ctx), dev.m, dev.functor_id, dev.B, dev._mesh_key)
+    lst = _pool.setdefault(key, [])
+    if len(lst) < 1 and sum(len(v) for v in _pool.values()) < _POOL_MAX:
+        if getattr(dev, "_hist_cap", 0):
+            dev.enable_history(0)
+        lst.append(dev)
+    else:
+        dev.close()
+
+
+def clear_pool():
+    for lst in _pool.values():
+        for dev in lst:
+            dev.close()
+    _pool.clear()
+
+
 @dataclass
 class ProblemDefinition:
     """Problem record (src/utils.jl:113-182), same field names; `jac` lives on the device as
@@ -356,7 +403,7 @@ def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design
                          ":sparseArrays, :banded")
     x = np.ascontiguousarray(xmesh, dtype=np.float64)
     ctx = ctx or default_context(0)
-    dev = DeviceProblem(ctx, m, x, pdefun, design)
+    dev = _acquire(ctx, m, x, pdefun, design)
     B, Nx, npde = pdefun.batch, x.size, pdefun.npde
     if callable(icfun):
         u0 = np.asarray(icfun(x), dtype=np.float64)
@@ -485,6 +532,9 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
             out.append(hist)
         if return_device:
             out.append(dev)
+        elif not params.data:
+            pb.device = None
+            _release(dev)
         return out[0] if len(out) == 1 else tuple(out)
 
     timeSteps, tau = time_grid(tspan, params.tstep)            # src/pdepe.jl:82-85
@@ -513,4 +563,7 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
         out.append(storage)
     if return_device:
         out.append(dev)
+    elif not params.data:
+        pb.device = None
+        _release(dev)
     return out[0] if len(out) == 1 else tuple(out)

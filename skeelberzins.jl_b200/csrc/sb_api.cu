@@ -492,6 +492,17 @@ int sb_problem_set_design(sb_problem* pb, int design) {
     return SB_OK;
 }
 
+int sb_problem_set_params(sb_problem* pb, const double* params_host) {
+    if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (pb->fe->nparams == 0) return SB_OK;
+    if (!params_host) return fail(SB_ERR_INVALID, "params is NULL");
+    CU(cudaSetDevice(pb->ctx->device));
+    CU(cudaMemcpyAsync(pb->d_prm, params_host, (size_t)pb->pd.B * pb->fe->nparams * sizeof(double), cudaMemcpyHostToDevice,
+                       pb->ctx->stream));
+    CU(cudaStreamSynchronize(pb->ctx->stream));
+    return SB_OK;
+}
+
 int sb_state_upload(sb_problem* pb, const double* u_host) {
     if (!pb || !u_host) return fail(SB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(pb->ctx->device));
