@@ -94,14 +94,15 @@ const FunctorEntry* registry() {
     return table;
 }
 
-SolveKernel solve_kernel(int P, int ri, int warp) {
-#define SB_SOLVE_ROW(PP, RR) {k_solve<PP, RR, false>, k_solve<PP, RR, true>}
-    static const SolveKernel t1[kNumR][2] = {SB_SOLVE_ROW(1, 1), SB_SOLVE_ROW(1, 2), SB_SOLVE_ROW(1, 4), SB_SOLVE_ROW(1, 8),
-                                             SB_SOLVE_ROW(1, 16)};
-    static const SolveKernel t2[kNumR][2] = {SB_SOLVE_ROW(2, 1), SB_SOLVE_ROW(2, 2), SB_SOLVE_ROW(2, 4), SB_SOLVE_ROW(2, 8),
-                                             {nullptr, nullptr}};
-#undef SB_SOLVE_ROW
-    return P == 1 ? t1[ri][warp] : t2[ri][warp];
+SolveKernel solve_kernel(int P, int dec) {
+    static SolveKernel t1[kNumDecomp], t2[kNumDecomp];
+    static bool init = false;
+    if (!init) {
+        fill_solve<1>(t1, std::make_integer_sequence<int, kNumDecomp>{});
+        fill_solve<2>(t2, std::make_integer_sequence<int, kNumDecomp>{});
+        init = true;
+    }
+    return P == 1 ? t1[dec] : t2[dec];
 }
 
 inline double ipow(double x, int n) {
@@ -128,7 +129,7 @@ struct sb_problem {
     sb_ctx* ctx;
     const FunctorEntry* fe;
     ProbDev pd;
-    int P, ri, warp, design;
+    int P, dec, sym0, warp, design;  // dec: index into kDecomp
     std::vector<double> xmesh, xi, zeta;
     // device allocations
     double *d_mesh = nullptr, *d_prm = nullptr, *d_u = nullptr, *d_b = nullptr, *d_F = nullptr, *d_J = nullptr,
@@ -180,12 +181,11 @@ void launch_geometry(const sb_problem* pb, dim3& grid, dim3& block, size_t& smem
     if (pb->warp) {
         block = dim3(kWarpBlockThreads);
         grid = dim3((unsigned)((pb->pd.B + (kWarpBlockThreads / 32) - 1) / (kWarpBlockThreads / 32)));
-        smem = 0;
     } else {
         block = dim3(pb->pd.T);
         grid = dim3((unsigned)pb->pd.B);
-        smem = (size_t)(2 * pb->P * pb->P + pb->P) * pb->pd.T * sizeof(double);
     }
+    smem = solve_smem_bytes(pb->P, pb->dec);
 }
 
 int to_device(sb_problem* pb, const double* src_ref_dev, double* dst, int W, int identity_P) {
@@ -228,21 +228,35 @@ int download_nodes(sb_problem* pb, const double* src, double* host, int W) {
     return SB_OK;
 }
 
-int pick_decomposition(int Nx, int P, int* R_out, int* T_out, int* warp_out) {
-    // user override for tuning: SB_ROWS_PER_THREAD = 1,2,4,8,16
-    int Rmax = (P == 1) ? 8 : 4;
-    if (const char* e = getenv("SB_ROWS_PER_THREAD")) {
-        int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || (v == 16 && P == 1)) Rmax = v;
+// Choose the thread decomposition (index into kDecomp).  Default: the smallest warp-per-system
+// decomposition that covers the mesh with R <= Rpref rows per thread, else the CTA-per-system one with
+// the preferred R and the fewest threads.  SB_ROWS_PER_THREAD / SB_THREADS_PER_SYSTEM override (tuning).
+int pick_decomposition(int Nx, int P) {
+    const int Rpref = (P == 1) ? 8 : 4;
+    int want_R = 0, want_T = 0;
+    if (const char* e = getenv("SB_ROWS_PER_THREAD")) want_R = atoi(e);
+    if (const char* e = getenv("SB_THREADS_PER_SYSTEM")) want_T = atoi(e);
+    if (want_R || want_T) {
+        int best = -1;
+        for (int d = 0; d < kNumDecomp; ++d) {
+            if (!decomp_ok(P, d) || kDecomp[d].R * kDecomp[d].TT < Nx) continue;
+            if (want_R && kDecomp[d].R != want_R) continue;
+            if (want_T && kDecomp[d].TT != want_T) continue;
+            if (best < 0 || kDecomp[d].R * kDecomp[d].TT < kDecomp[best].R * kDecomp[best].TT) best = d;
+        }
+        if (best >= 0) return best;
     }
-    const int Rcap = (P == 1) ? 16 : 8;
-    int R = 1;
-    while (R < Rmax && R * 32 < Nx) R *= 2;          // smallest R whose single warp covers the mesh
-    int T = ((Nx + R - 1) / R + 31) / 32 * 32;
-    while (T > kMaxBlockT && R < Rcap) { R *= 2; T = ((Nx + R - 1) / R + 31) / 32 * 32; }
-    if (T > kMaxBlockT) return SB_ERR_UNSUPPORTED;
-    *R_out = R; *T_out = T; *warp_out = (T == 32);
-    return SB_OK;
+    int best = -1;
+    long best_cost = 0;
+    for (int d = 0; d < kNumDecomp; ++d) {
+        if (!decomp_ok(P, d) || kDecomp[d].R * kDecomp[d].TT < Nx) continue;
+        const int R = kDecomp[d].R, TT = kDecomp[d].TT;
+        // cost: padded size first, then distance from the preferred R (warp mode only up to Rpref)
+        long cost = (long)R * TT * 64 + (R > Rpref ? 32 * (R / Rpref) : (Rpref / R)) + (TT == 32 ? 0 : 1);
+        if (TT == 32 && R > Rpref) cost += (long)R * TT * 64;   // prefer a CTA decomposition over R > Rpref warps
+        if (best < 0 || cost < best_cost) { best = d; best_cost = cost; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -337,15 +351,15 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
 
     sb_problem* pb = new sb_problem;
     pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = SB_DESIGN_FUSED;
-    int R, T, warp;
-    if (pick_decomposition(Nx, pb->P, &R, &T, &warp) != SB_OK) {
+    pb->dec = pick_decomposition(Nx, pb->P);
+    if (pb->dec < 0) {
         delete pb;
         return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) of this build", Nx,
                     kMaxBlockT * (fe->npde == 1 ? 16 : 8));
     }
-    pb->warp = warp;
-    pb->ri = 0;
-    while ((1 << pb->ri) < R) pb->ri++;
+    const int R = kDecomp[pb->dec].R, T = kDecomp[pb->dec].TT;
+    pb->warp = (T == 32);
+    pb->sym0 = (m == 0);
     ProbDev& pd = pb->pd;
     memset(&pd, 0, sizeof pd);
     pd.Nx = Nx; pd.R = R; pd.T = T; pd.L = R * T; pd.m = m; pd.nprm = fe->nparams; pd.B = B;
@@ -372,11 +386,13 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     // per-interval interpolation weights (src/utils.jl:18-48) and flux weights, per-node volume weights
     // (src/assembler.jl:36,68-69,74,84,98), written straight in the [r][t] device layout
     const size_t L = pd.L;
-    std::vector<double> mesh(7 * L, 0.0);
-    double *h_xi = &mesh[0], *h_aw = &mesh[L], *h_bw = &mesh[2 * L], *h_gw = &mesh[3 * L], *h_wf = &mesh[4 * L],
-           *h_fR = &mesh[5 * L], *h_fL = &mesh[6 * L];
+    // device image: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L] | ivol[L]
+    std::vector<double> mesh(9 * L, 0.0);
+    double *h_xi = &mesh[0], *h_awbw = &mesh[L], *h_gwwf = &mesh[3 * L], *h_frac = &mesh[5 * L], *h_gw = &mesh[7 * L],
+           *h_ivol = &mesh[8 * L];
     for (int i = 0; i < Nx; ++i) {
         const size_t s = (size_t)(i % R) * T + i / R;
+        double fR = 0.0, fL = 0.0;
         if (i < NI) {
             const double xl = xmesh[i], xr = xmesh[i + 1], q = pb->xi[i];
             double aw, bw, gw;
@@ -384,18 +400,20 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
             else if (m == 0) { const double h = xr - xl; aw = (xr - q) / h; bw = (q - xl) / h; gw = 1.0 / h; }
             else if (m == 1) { const double lg = std::log(xr / xl), th = std::log(q / xl) / lg; aw = 1 - th; bw = th; gw = 1.0 / (q * lg); }
             else { const double h = xr - xl, th = (xr * (q - xl)) / (q * h); aw = 1 - th; bw = th; gw = (xr * xl) / (q * q * h); }
-            h_xi[s] = q; h_aw[s] = aw; h_bw[s] = bw; h_gw[s] = gw;
-            h_wf[s] = pd.singular ? ipow(pb->zeta[i], mp) / q : ipow(q, m);
-            h_fR[s] = (ipow(pb->zeta[i], mp) - ipow(xmesh[i], mp)) / mp;
+            h_xi[s] = q; h_awbw[2 * s] = aw; h_awbw[2 * s + 1] = bw; h_gwwf[2 * s] = gw; h_gw[s] = gw;
+            h_gwwf[2 * s + 1] = pd.singular ? ipow(pb->zeta[i], mp) / q : ipow(q, m);
+            fR = (ipow(pb->zeta[i], mp) - ipow(xmesh[i], mp)) / mp;
         }
-        if (i >= 1) h_fL[s] = (ipow(xmesh[i], mp) - ipow(pb->zeta[i - 1], mp)) / mp;
+        if (i >= 1) fL = (ipow(xmesh[i], mp) - ipow(pb->zeta[i - 1], mp)) / mp;
+        h_frac[2 * s] = fR; h_frac[2 * s + 1] = fL;
+        if (i >= 1 && i < NI) h_ivol[s] = 1.0 / (fR + fL);
     }
     pd.x0 = xmesh[0]; pd.xN = xmesh[Nx - 1]; pd.x0m = ipow(xmesh[0], m); pd.xNm = ipow(xmesh[Nx - 1], m); pd.xi0 = pb->xi[0];
 
     int rc = SB_OK;
     const size_t n = (size_t)B * L * pb->P;
 #define TRY(x) do { if (rc == SB_OK) rc = (x); } while (0)
-    TRY(dev_alloc(&pb->d_mesh, 7 * L));
+    TRY(dev_alloc(&pb->d_mesh, 9 * L));
     TRY(dev_alloc(&pb->d_prm, (size_t)B * fe->nparams));
     TRY(dev_alloc(&pb->d_u, n));
     TRY(dev_alloc(&pb->d_b, n));
@@ -417,7 +435,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     }
     pb->ev_ok = true;
     cudaStream_t st = ctx->stream;
-    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 7 * L * sizeof(double), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && fe->nparams > 0)
         e = cudaMemcpyAsync(pb->d_prm, params, (size_t)B * fe->nparams * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_u, 0, n * sizeof(double), st);
@@ -437,8 +455,12 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         e = cudaMemcpy(pb->d_mass, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "mass init: %s", cudaGetErrorString(e)); }
     }
-    pd.mesh.xi = pb->d_mesh; pd.mesh.aw = pb->d_mesh + L; pd.mesh.bw = pb->d_mesh + 2 * L; pd.mesh.gw = pb->d_mesh + 3 * L;
-    pd.mesh.wf = pb->d_mesh + 4 * L; pd.mesh.fracR = pb->d_mesh + 5 * L; pd.mesh.fracL = pb->d_mesh + 6 * L;
+    pd.mesh.xi = pb->d_mesh;
+    pd.mesh.awbw = reinterpret_cast<const double2*>(pb->d_mesh + L);
+    pd.mesh.gwwf = reinterpret_cast<const double2*>(pb->d_mesh + 3 * L);
+    pd.mesh.frac = reinterpret_cast<const double2*>(pb->d_mesh + 5 * L);
+    pd.mesh.gw = pb->d_mesh + 7 * L;
+    pd.mesh.ivol = pb->d_mesh + 8 * L;
     pd.prm = pb->d_prm; pd.u = pb->d_u; pd.b = pb->d_b; pd.F = pb->d_F; pd.mass = pb->d_mass;
     pd.active = pb->d_active; pd.iters = pb->d_iters; pd.total_iters = pb->d_total; pd.norm = pb->d_norm;
     pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;
@@ -559,7 +581,7 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     }
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    AssembleKernel kern = pb->fe->assemble_val[pb->ri][pb->warp];
+    AssembleKernel kern = pb->fe->assemble_val[pb->dec][pb->sym0];
     kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -641,7 +663,7 @@ int sb_residual_jacobian(sb_problem* pb) {
     launch_geometry(pb, grid, block, smem);
     const int ps = (int)(pb->launched % kSlots);
     if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
-    pb->fe->assemble_jac[pb->ri][pb->warp]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+    pb->fe->assemble_jac[pb->dec][pb->sym0]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
     ++g_launches;
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evM[ps], pb->ctx->stream));
@@ -657,7 +679,7 @@ int sb_solve_update_norm(sb_problem* pb, double tol) {
     if (rc) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
+    solve_kernel(pb->P, pb->dec)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
     ++g_launches;
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
@@ -678,7 +700,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
-    pb->fe->fused[pb->ri][pb->warp]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
+    pb->fe->fused[pb->dec][pb->sym0]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
     ++g_launches;
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
@@ -878,7 +900,7 @@ int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const dou
     if ((rc = upload_nodes(pb, F, pb->d_F, pb->P, 0))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    solve_kernel(pb->P, pb->ri, pb->warp)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, 0.0, 0, 0);
+    solve_kernel(pb->P, pb->dec)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, 0.0, 0, 0);
     ++g_launches;
     CU(cudaGetLastError());
     return download_nodes(pb, pb->d_F, x, pb->P);

@@ -7,6 +7,8 @@
 // parameter vector of the sweep.  ql/qr are value-only (plain doubles): in every registry entry
 // they are constants, exactly as in the reference examples.
 // Ids and parameter order: include/skeelberzins_b200.h (enum sb_functor_id).
+// Traits: c_unit = the capacity c is identically 1, s_zero = the source s is identically 0; they let
+// the assembler drop dual arithmetic on structural zeros (the values are still what pde() returns).
 #pragma once
 #include "sb_dual.cuh"
 
@@ -15,6 +17,7 @@ namespace sb {
 // f = D * ux family with Neumann ends -- examples/Example101_LinearDiffusion.jl:21-38
 struct FnLinDiff {
     static constexpr int npde = 1, nparams = 1;
+    static constexpr bool c_unit = true, s_zero = true;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * ux[0]; s[0] = S(0.0);
     }
@@ -26,6 +29,7 @@ struct FnLinDiff {
 // examples/Example102_NonlinearDiffusion.jl:44-65 : f = a*u*ux
 struct FnNonlinDiff {
     static constexpr int npde = 1, nparams = 1;
+    static constexpr bool c_unit = true, s_zero = true;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * u[0] * ux[0]; s[0] = S(0.0);
     }
@@ -37,6 +41,7 @@ struct FnNonlinDiff {
 // examples/Example103_LinearDiffusionCylindrical.jl:35-58 : right Dirichlet g*exp(-D n^2 t)
 struct FnLinDiffCyl {
     static constexpr int npde = 1, nparams = 3;
+    static constexpr bool c_unit = true, s_zero = true;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * ux[0]; s[0] = S(0.0);
     }
@@ -49,6 +54,7 @@ struct FnLinDiffCyl {
 // examples/Example104_Poisson.jl:20-41 ; test/test_solveStationary.jl:6-23 (c0 = 0)
 struct FnPoisson {
     static constexpr int npde = 1, nparams = 3;
+    static constexpr bool c_unit = false, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(p[0]); f[0] = ux[0]; s[0] = S(p[1]);
     }
@@ -60,6 +66,7 @@ struct FnPoisson {
 // examples/Example105_StationaryNonlinearDiffusion.jl:30-51
 struct FnStatNonlin {
     static constexpr int npde = 1, nparams = 3;
+    static constexpr bool c_unit = true, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * u[0] * ux[0]; s[0] = S(p[1]);
     }
@@ -71,6 +78,7 @@ struct FnStatNonlin {
 // examples/Example106_SystemReactionDiffusion.jl:42-64 (npde = 2)
 struct FnReactDiff {
     static constexpr int npde = 2, nparams = 3;
+    static constexpr bool c_unit = true, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); c[1] = S(1.0);
         f[0] = p[0] * ux[0]; f[1] = p[1] * ux[1];
@@ -86,6 +94,7 @@ struct FnReactDiff {
 // examples/Example107_LinearDiffusionSpherical.jl:34-55 : right Dirichlet 1 + 6 D t
 struct FnLinDiffSph {
     static constexpr int npde = 1, nparams = 1;
+    static constexpr bool c_unit = true, s_zero = true;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * ux[0]; s[0] = S(0.0);
     }
@@ -98,6 +107,7 @@ struct FnLinDiffSph {
 // examples/Example201_PartialDerivativeApprox.jl:34-51
 struct FnConvDiff {
     static constexpr int npde = 1, nparams = 3;
+    static constexpr bool c_unit = true, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * ux[0]; s[0] = -(p[0] * p[1] / p[2]) * ux[0];
     }
@@ -109,6 +119,7 @@ struct FnConvDiff {
 // examples/Example301_PDEOptimSciMLSensitivity.jl:31-48
 struct FnLinReact {
     static constexpr int npde = 1, nparams = 2;
+    static constexpr bool c_unit = true, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[1] * ux[0]; s[0] = 2.0 * p[0] * u[0];
     }
@@ -120,6 +131,7 @@ struct FnLinReact {
 // quasi-linear scalar family (parameter order in include/skeelberzins_b200.h)
 struct FnGenericScalar {
     static constexpr int npde = 1, nparams = 19;
+    static constexpr bool c_unit = false, s_zero = false;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = p[0] + p[1] * u[0];
         f[0] = (p[2] + p[3] * u[0]) * ux[0];

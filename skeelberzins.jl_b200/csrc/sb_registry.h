@@ -2,11 +2,23 @@
 // One translation unit per functor (sb_inst.cu compiled with -DSB_FN=...) fills one entry, so the
 // instantiations build in parallel.
 #pragma once
+#include <utility>
+
 #include "sb_kernels.cuh"
 
 namespace sb {
 
-constexpr int kNumR = 5;  // rows per thread R = 1, 2, 4, 8, 16  (index = log2 R)
+// Thread decompositions the kernels are compiled for: R rows per thread x TT threads per system.
+// TT == 32: one warp per system (shuffles only); TT > 32: one CTA per system.
+struct Decomp { int R, TT; };
+constexpr int kNumDecomp = 13;
+constexpr Decomp kDecomp[kNumDecomp] = {
+    {1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32},   // warp per system: Nx <= 32 .. 512
+    {4, 64}, {8, 64}, {16, 64},                     // CTA per system
+    {4, 128}, {8, 128},
+    {4, 256}, {8, 256}, {16, 256},
+};
+constexpr bool decomp_ok(int P, int d) { return P == 1 || kDecomp[d].R <= 8; }  // R = 16 only for scalar PDEs
 
 typedef void (*AssembleKernel)(ProbDev, double, double, int);
 typedef void (*FusedKernel)(ProbDev, double, double, double, int);
@@ -16,34 +28,52 @@ typedef void (*MassKernel)(ProbDev, double, double*, int);
 struct FunctorEntry {
     const char* name;
     int npde, nparams;
-    AssembleKernel assemble_jac[kNumR][2];  // [log2 R][WARP]
-    AssembleKernel assemble_val[kNumR][2];
-    FusedKernel fused[kNumR][2];
+    AssembleKernel assemble_jac[kNumDecomp][2];  // [decomposition][SYM0]
+    AssembleKernel assemble_val[kNumDecomp][2];
+    FusedKernel fused[kNumDecomp][2];
     MassKernel mass;
 };
 
-template <class Fn, int R>
-void fill_r(FunctorEntry& e, int ri) {
-    e.assemble_jac[ri][0] = k_assemble<Fn, R, false, true>;
-    e.assemble_jac[ri][1] = k_assemble<Fn, R, true, true>;
-    e.assemble_val[ri][0] = k_assemble<Fn, R, false, false>;
-    e.assemble_val[ri][1] = k_assemble<Fn, R, true, false>;
-    e.fused[ri][0] = k_newton_fused<Fn, R, false>;
-    e.fused[ri][1] = k_newton_fused<Fn, R, true>;
+template <class Fn, int D>
+void fill_one(FunctorEntry& e) {
+    if constexpr (decomp_ok(Fn::npde, D)) {
+        constexpr int R = kDecomp[D].R, TT = kDecomp[D].TT;
+        e.assemble_jac[D][0] = k_assemble<Fn, R, TT, false, true>;
+        e.assemble_jac[D][1] = k_assemble<Fn, R, TT, true, true>;
+        e.assemble_val[D][0] = k_assemble<Fn, R, TT, false, false>;
+        e.assemble_val[D][1] = k_assemble<Fn, R, TT, true, false>;
+        e.fused[D][0] = k_newton_fused<Fn, R, TT, false>;
+        e.fused[D][1] = k_newton_fused<Fn, R, TT, true>;
+    } else {
+        for (int s = 0; s < 2; ++s) { e.assemble_jac[D][s] = nullptr; e.assemble_val[D][s] = nullptr; e.fused[D][s] = nullptr; }
+    }
 }
+
+template <class Fn, int... D>
+void fill_all(FunctorEntry& e, std::integer_sequence<int, D...>) { (fill_one<Fn, D>(e), ...); }
 
 template <class Fn>
 FunctorEntry make_entry(const char* name) {
     FunctorEntry e;
     e.name = name; e.npde = Fn::npde; e.nparams = Fn::nparams;
-    fill_r<Fn, 1>(e, 0);
-    fill_r<Fn, 2>(e, 1);
-    fill_r<Fn, 4>(e, 2);
-    fill_r<Fn, 8>(e, 3);
-    if constexpr (Fn::npde == 1) fill_r<Fn, 16>(e, 4);
-    else { for (int w = 0; w < 2; ++w) { e.assemble_jac[4][w] = nullptr; e.assemble_val[4][w] = nullptr; e.fused[4][w] = nullptr; } }
+    fill_all<Fn>(e, std::make_integer_sequence<int, kNumDecomp>{});
     e.mass = k_mass_flags<Fn>;
     return e;
+}
+
+template <int P, int D>
+void fill_solve_one(SolveKernel (&tab)[kNumDecomp]) {
+    if constexpr (decomp_ok(P, D)) tab[D] = k_solve<P, kDecomp[D].R, kDecomp[D].TT>;
+    else tab[D] = nullptr;
+}
+template <int P, int... D>
+void fill_solve(SolveKernel (&tab)[kNumDecomp], std::integer_sequence<int, D...>) { (fill_solve_one<P, D>(tab), ...); }
+
+// shared memory (bytes) of the solve / fused kernels for a decomposition
+inline size_t solve_smem_bytes(int P, int d) {
+    const int TT = kDecomp[d].TT;
+    if (TT == 32) return 0;
+    return (size_t)(2 * (2 * P * P + P) + P) * TT * sizeof(double);
 }
 
 // defined in the per-functor translation units
