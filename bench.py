@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", help="BASELINE config: 2 (default), 3a, 3b, 4")
-    ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused"), choices=["fused", "split"])
+    ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused"), choices=["fused", "fused_tma", "split"])
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's B)")
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--time-steps", type=int, default=0, help="truncate the time loop (testing only)")
@@ -127,7 +127,7 @@ class ClockSampler:
 def algorithmic_bytes_per_unit(design, P):
     """fp64 SoA bytes one mesh node of one active instance moves per Newton iteration:
     fused: read u, read b, write u.  split: assemble R u,b / W F,J ; solve R J,F,u / W u."""
-    if design == "fused":
+    if design in ("fused", "fused_tma"):
         return {"fused": 24 * P}
     return {"assemble": 16 * P + 8 * P + 24 * P * P, "solve": 24 * P * P + 16 * P + 8 * P}
 
@@ -305,7 +305,7 @@ def run_ours(args):
     bpu = algorithmic_bytes_per_unit(args.design, P)
     peak, peak_kind = hbm_peak()
     kern = {}
-    if args.design == "fused":
+    if args.design in ("fused", "fused_tma"):
         kern["fused"] = prof["ms_solve"]
     else:
         kern["assemble"], kern["solve"] = prof["ms_assemble"], prof["ms_solve"]
@@ -322,7 +322,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind if peak_kind == "measured" else "of fallback",
-        "kernel": "k_newton_fused" if dom == "fused" else "k_" + dom,
+        "kernel": ("k_newton_fused_p" if args.design == "fused_tma" else "k_newton_fused") if dom == "fused" else "k_" + dom,
         "avg_launch_us": 1e3 * kern[dom] / n_launch, "launches_profiled": prof["launches"],
         "noop_launches_profiled": prof["noop_launches"],
         "algorithmic_bytes_per_unit": bpu[dom], "units_per_launch_avg": prof["instance_iterations"] * Nx / n_launch,

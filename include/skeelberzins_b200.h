@@ -91,7 +91,10 @@ typedef struct sb_problem sb_problem;
 enum sb_design {
     SB_DESIGN_SPLIT = 0, /* assemble kernel writes F and the block-tridiagonal J to HBM; solve kernel
                             reads them (the two calls sb_residual_jacobian + sb_solve_update_norm)  */
-    SB_DESIGN_FUSED = 1  /* one kernel per iteration; J and F never leave the SM                    */
+    SB_DESIGN_FUSED = 1, /* one kernel per iteration; J and F never leave the SM                    */
+    SB_DESIGN_FUSED_TMA = 2 /* fused, persistent CTAs: u and b of the next instance are prefetched by the
+                            bulk-copy engine (cp.async.bulk + mbarrier) while the current one is solved;
+                            only instances still active are visited (compacted list)                */
 };
 
 /* ---- library / context ---------------------------------------------------------------------- */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libskeelberzins_b200.so")
 
 SB_OK = 0
 SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_UNSUPPORTED, SB_ERR_CONVERGENCE, SB_ERR_PLUGIN = -1, -2, -3, -4, -5
-DESIGN_SPLIT, DESIGN_FUSED = 0, 1
+DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA = 0, 1, 2
 
 _c = ctypes
 _dp = _c.POINTER(_c.c_double)

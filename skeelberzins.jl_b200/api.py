@@ -150,9 +150,10 @@ class DeviceProblem:
         _lib.check(self.lib.sb_problem_set_params(self._h, _lib.ptr(p)))
 
     def set_design(self, design):
-        d = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED}[design] if isinstance(design, str) else int(design)
+        names = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED, "fused_tma": _lib.DESIGN_FUSED_TMA}
+        d = names[design] if isinstance(design, str) else int(design)
         _lib.check(self.lib.sb_problem_set_design(self._h, d))
-        self.design = "fused" if d == _lib.DESIGN_FUSED else "split"
+        self.design = {v: k for k, v in names.items()}[d]
 
     def layout(self):
         R, T, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

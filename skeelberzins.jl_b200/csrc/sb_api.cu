@@ -129,7 +129,10 @@ struct sb_problem {
     sb_ctx* ctx;
     const FunctorEntry* fe;
     ProbDev pd;
-    int P, dec, sym0, warp, design;  // dec: index into kDecomp
+    int P, dec, sym0, warp, design, design_pending;  // dec: index into kDecomp
+    int* d_list = nullptr;          // 2*B compacted active lists (fused_tma design)
+    int p_grid = 0;                 // persistent grid of the fused_tma kernel (0: not configured yet)
+    size_t p_smem = 0;
     std::vector<double> xmesh, xi, zeta;
     // device allocations
     double *d_mesh = nullptr, *d_prm = nullptr, *d_u = nullptr, *d_b = nullptr, *d_F = nullptr, *d_J = nullptr,
@@ -350,7 +353,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     CU(cudaSetDevice(ctx->device));
 
     sb_problem* pb = new sb_problem;
-    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = SB_DESIGN_FUSED;
+    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = pb->design_pending = SB_DESIGN_FUSED;
     pb->dec = pick_decomposition(Nx, pb->P);
     if (pb->dec < 0) {
         delete pb;
@@ -362,7 +365,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pb->sym0 = (m == 0);
     ProbDev& pd = pb->pd;
     memset(&pd, 0, sizeof pd);
-    pd.Nx = Nx; pd.R = R; pd.T = T; pd.L = R * T; pd.m = m; pd.nprm = fe->nparams; pd.B = B;
+    pd.Nx = Nx; pd.R = R; pd.T = T; pd.L = R * T; pd.m = m; pd.nprm = fe->nparams; pd.nprm_s = (fe->nparams + 1) / 2 * 2; pd.iter_no = 0; pd.B = B;
     pd.singular = (m >= 1) && (xmesh[0] == 0);  // src/utils.jl:616
     pb->xmesh.assign(xmesh, xmesh + Nx);
 
@@ -414,17 +417,18 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     const size_t n = (size_t)B * L * pb->P;
 #define TRY(x) do { if (rc == SB_OK) rc = (x); } while (0)
     TRY(dev_alloc(&pb->d_mesh, 9 * L));
-    TRY(dev_alloc(&pb->d_prm, (size_t)B * fe->nparams));
+    TRY(dev_alloc(&pb->d_prm, (size_t)B * pd.nprm_s));
     TRY(dev_alloc(&pb->d_u, n));
     TRY(dev_alloc(&pb->d_b, n));
     TRY(dev_alloc(&pb->d_F, n));
-    TRY(dev_alloc(&pb->d_mass, (size_t)B * 3 * pb->P));
+    TRY(dev_alloc(&pb->d_mass, (size_t)B * 4 * pb->P));
     TRY(dev_alloc(&pb->d_norm, (size_t)B));
     TRY(dev_alloc(&pb->d_active, (size_t)B));
     TRY(dev_alloc(&pb->d_iters, (size_t)B));
     TRY(dev_alloc(&pb->d_status, (size_t)B));
     TRY(dev_alloc(&pb->d_total, (size_t)B));
     TRY(dev_alloc(&pb->d_count, (size_t)kSlots));
+    TRY(dev_alloc(&pb->d_list, (size_t)2 * B));
 #undef TRY
     if (rc != SB_OK) { sb_problem_destroy(pb); return rc; }
     cudaError_t e = cudaHostAlloc((void**)&pb->h_count, kSlots * sizeof(unsigned int), cudaHostAllocDefault);
@@ -437,7 +441,8 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     cudaStream_t st = ctx->stream;
     e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && fe->nparams > 0)
-        e = cudaMemcpyAsync(pb->d_prm, params, (size_t)B * fe->nparams * sizeof(double), cudaMemcpyHostToDevice, st);
+        e = cudaMemcpy2DAsync(pb->d_prm, pd.nprm_s * sizeof(double), params, fe->nparams * sizeof(double),
+                              fe->nparams * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_u, 0, n * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_b, 0, n * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_F, 0, n * sizeof(double), st);
@@ -451,7 +456,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "problem upload: %s", cudaGetErrorString(e)); }
     // all-ones mass flags until sb_mass_flags is called
     {
-        std::vector<double> ones((size_t)B * 3 * pb->P, 1.0);
+        std::vector<double> ones((size_t)B * 4 * pb->P, 1.0);
         e = cudaMemcpy(pb->d_mass, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "mass init: %s", cudaGetErrorString(e)); }
     }
@@ -464,6 +469,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.prm = pb->d_prm; pd.u = pb->d_u; pd.b = pb->d_b; pd.F = pb->d_F; pd.mass = pb->d_mass;
     pd.active = pb->d_active; pd.iters = pb->d_iters; pd.total_iters = pb->d_total; pd.norm = pb->d_norm;
     pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;
+    pd.list[0] = pb->d_list; pd.list[1] = pb->d_list + B;
     pb->last_active = B;
     *out = pb;
     return SB_OK;
@@ -475,7 +481,7 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
     cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
-    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt);
+    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ev_ok) for (int i = 0; i < kSlots; ++i) cudaEventDestroy(pb->ev[i]);
@@ -509,8 +515,10 @@ int sb_problem_quadrature(sb_problem* pb, double* xi, double* zeta) {
 
 int sb_problem_set_design(sb_problem* pb, int design) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
-    if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED) return fail(SB_ERR_INVALID, "unknown design %d", design);
-    pb->design = design;
+    if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED && design != SB_DESIGN_FUSED_TMA)
+        return fail(SB_ERR_INVALID, "unknown design %d", design);
+    pb->design_pending = design;  // takes effect at the next sb_begin_step (a step is never mixed)
+    if (pb->launched == 0) pb->design = design;
     return SB_OK;
 }
 
@@ -519,8 +527,8 @@ int sb_problem_set_params(sb_problem* pb, const double* params_host) {
     if (pb->fe->nparams == 0) return SB_OK;
     if (!params_host) return fail(SB_ERR_INVALID, "params is NULL");
     CU(cudaSetDevice(pb->ctx->device));
-    CU(cudaMemcpyAsync(pb->d_prm, params_host, (size_t)pb->pd.B * pb->fe->nparams * sizeof(double), cudaMemcpyHostToDevice,
-                       pb->ctx->stream));
+    CU(cudaMemcpy2DAsync(pb->d_prm, pb->pd.nprm_s * sizeof(double), params_host, pb->fe->nparams * sizeof(double),
+                         pb->fe->nparams * sizeof(double), (size_t)pb->pd.B, cudaMemcpyHostToDevice, pb->ctx->stream));
     CU(cudaStreamSynchronize(pb->ctx->stream));
     return SB_OK;
 }
@@ -557,13 +565,13 @@ int sb_mass_download(sb_problem* pb, double* mass_host) {
     if (!pb || !mass_host) return fail(SB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(pb->ctx->device));
     const int P = pb->P, Nx = pb->pd.Nx;
-    std::vector<double> f((size_t)pb->pd.B * 3 * P);
+    std::vector<double> f((size_t)pb->pd.B * 4 * P);
     CU(cudaStreamSynchronize(pb->ctx->stream));
     CU(cudaMemcpy(f.data(), pb->d_mass, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
     for (int64_t k = 0; k < pb->pd.B; ++k)
         for (int i = 0; i < Nx; ++i) {
             const int cls = (i == 0) ? 0 : ((i == Nx - 1) ? 2 : 1);
-            for (int p = 0; p < P; ++p) mass_host[((size_t)k * Nx + i) * P + p] = f[(size_t)k * 3 * P + cls * P + p];
+            for (int p = 0; p < P; ++p) mass_host[((size_t)k * Nx + i) * P + p] = f[(size_t)k * 4 * P + cls * P + p];
         }
     return SB_OK;
 }
@@ -623,6 +631,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     CU(cudaSetDevice(pb->ctx->device));
     if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; pb->prof_harvested = 0; }
     pb->t_next = t_next; pb->inv_tau = inv_tau;
+    pb->design = pb->design_pending;
     cudaStream_t st = pb->ctx->stream;
     CU(cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st));
     const size_t total = (size_t)pb->pd.B * pb->pd.L;
@@ -637,6 +646,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
 
 static int prepare_slot(sb_problem* pb, int* slot) {
     const int s = (int)(pb->launched % kSlots);
+    pb->pd.iter_no = (int)pb->launched;  // Newton iteration number inside the step (lock-step: same for all active instances)
     if (pb->launched >= kSlots) {  // ring wrapped: the slot's previous value must have been delivered, then re-zero it
         if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; }
         CU(cudaEventSynchronize(pb->ev[s]));
@@ -699,6 +709,27 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
     if (rc) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
+    if (pb->design == SB_DESIGN_FUSED_TMA) {
+        FusedPKernel kern = pb->fe->fused_p[pb->dec][pb->sym0];
+        if (pb->p_grid == 0) {  // one-time configuration: opt in to the shared memory, size the persistent grid
+            pb->p_smem = pb->fe->fused_p_smem[pb->dec][pb->sym0];
+            CU(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->p_smem));
+            int occ = 0, sms = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, (int)block.x, pb->p_smem));
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pb->ctx->device));
+            if (occ < 1) return fail(SB_ERR_UNSUPPORTED, "fused_tma kernel does not fit on an SM (%zu bytes of shared memory)", pb->p_smem);
+            if (const char* e = getenv("SB_PERSISTENT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < occ) occ = v; }
+            pb->p_grid = (int)std::min<int64_t>((int64_t)occ * sms, (int64_t)grid.x);
+        }
+        const int prev_slot = (pb->launched == 0) ? -1 : (int)((pb->launched - 1) % kSlots);
+        const int parity = (int)(pb->launched & 1);
+        if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
+        kern<<<pb->p_grid, block, pb->p_smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity);
+        ++g_launches;
+        CU(cudaGetLastError());
+        if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
+        return finish_slot(pb, slot);
+    }
     if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
     pb->fe->fused[pb->dec][pb->sym0]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
     ++g_launches;

@@ -36,20 +36,27 @@ struct MeshDev {           // [R][TT] each; interval j = (node j, node j+1) is s
     const double* ivol;    // 1/(frac1 + frac2): reciprocal control-volume weight of interior nodes (c == 1 functors)
 };
 
+// weight loads: through the read-only data path when the arrays are in global memory (GLOB), plain loads
+// when a kernel has staged them in shared memory
+template <bool GLOB> SB_D double ldw(const double* p, int i) { if constexpr (GLOB) return __ldg(p + i); else return p[i]; }
+template <bool GLOB> SB_D double2 ldw(const double2* p, int i) { if constexpr (GLOB) return __ldg(p + i); else return p[i]; }
+
 struct ProbDev {
     int Nx, R, T, L;       // L = R*T padded nodes
     int m, singular, nprm;
+    int nprm_s;            // stride of the per-instance parameter block (even, so every block is 16-byte aligned)
+    int iter_no;           // Newton iteration number inside the current step (same for every active instance)
     int64_t B;
     double x0, xN, x0m, xNm, xi0;  // first/last mesh point, x^m of both, first quadrature point
     MeshDev mesh;
-    const double* prm;     // [B][nprm]
+    const double* prm;     // [B][nprm_s]
     double* u;             // Newton iterate          [B][R][T][P]
     double* b;             // M .* u_n                [B][R][T][P]
     double* F;             // residual / rhs          [B][R][T][P]
     double* Jl;            // sub-diagonal blocks     [B][R][T][P*P]
     double* Jd;
     double* Ju;
-    const double* mass;    // [B][3][P]: left node, interior, right node (0/1)
+    const double* mass;    // [B][4][P]: left node, interior, right node (0/1), padding (16-byte aligned blocks)
     int* active;           // [B]
     int* iters;            // [B] Newton iterations this step
     long long* total_iters;  // [B]
@@ -58,6 +65,7 @@ struct ProbDev {
     double* hist;          // [B][hist_cap] or null
     int hist_cap;
     unsigned int* active_count;  // [slots]
+    int* list[2];          // compacted indices of the instances still active (ping-pong between iterations)
 };
 
 // reciprocal without the special-case slow path of 1.0/x: MUFU.RCP64H seed + two Newton steps
@@ -285,16 +293,16 @@ struct IntervalRes {  // (c,f,s) of one interval; partials w.r.t. (u_left[0..P),
     double wf;
 };
 
-template <class Fn, int ND, bool SYM0>
-SB_D void eval_interval(const ProbDev& pd, int slot, const double* ul, const double* ur, double tt, const double* prm,
+template <class Fn, int ND, bool SYM0, bool GLOB = true>
+SB_D void eval_interval(const MeshDev& mesh, int slot, const double* ul, const double* ur, double tt, const double* prm,
                         IntervalRes<Fn::npde, ND>& out) {
     constexpr int P = Fn::npde;
-    const double xi = __ldg(pd.mesh.xi + slot);
+    const double xi = __ldg(mesh.xi + slot);  // always global; dead (and removed) when the functor ignores x
     double aw, bw, gw;
     if constexpr (SYM0) {  // m == 0: xi is the midpoint, linear interpolation, unit flux weight
-        aw = 0.5; bw = 0.5; gw = __ldg(pd.mesh.gw + slot); out.wf = 1.0;
+        aw = 0.5; bw = 0.5; gw = ldw<GLOB>(mesh.gw, slot); out.wf = 1.0;
     } else {
-        const double2 ab = __ldg(pd.mesh.awbw + slot), gf = __ldg(pd.mesh.gwwf + slot);
+        const double2 ab = ldw<GLOB>(mesh.awbw, slot), gf = ldw<GLOB>(mesh.gwwf, slot);
         aw = ab.x; bw = ab.y; gw = gf.x; out.wf = gf.y;
     }
     Dual<ND> U[P], Ux[P];
@@ -316,15 +324,13 @@ struct RowOut { Mat<P> A, Bm, C; Vec<P> d; };
 // Boundary rows (src/assembler.jl:36-57 left, :98-122 right).  side = 0: node 0 with I = interval 0;
 // side = 1: node Nx-1 with I = interval Nx-2.  ui/bi: u and b at the boundary node.
 // JAC: out = (Jl, Jd, Ju, F); !JAC: out.d = du.
-template <class Fn, bool JAC, int ND>
-SB_D void boundary_row(const ProbDev& pd, int64_t k, int side, double tt, double inv_tau, const double* prm,
-                       const IntervalRes<Fn::npde, ND>& I, const double* ui, const double* bi, int slot,
-                       RowOut<Fn::npde>& out) {
+template <class Fn, bool JAC, int ND, bool GFRAC = true>
+SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* ub, const double* mass, int side, double tt,
+                       double inv_tau, const double* prm, const IntervalRes<Fn::npde, ND>& I, const double* ui,
+                       const double* bi, int slot, RowOut<Fn::npde>& out) {
     constexpr int P = Fn::npde;
     constexpr int PO = JAC ? P : 0;
     const int R = pd.R, T = pd.T, Nx = pd.Nx;
-    const double* ub = pd.u + (size_t)k * pd.L * P;
-    const double* mass = pd.mass + (size_t)k * 3 * P;
     const int s0 = 0, sN = ((Nx - 1) % R) * T + (Nx - 1) / R;
     Dual<PO> ul_[P], ur_[P], pl[P], pr[P];
     double ql[P], qr[P];
@@ -343,7 +349,7 @@ SB_D void boundary_row(const ProbDev& pd, int64_t k, int side, double tt, double
         for (int q = 0; q < P; ++q) { dm[j][q] = 0.0; dc[j][q] = 0.0; dp[j][q] = 0.0; }
     }
     if (side == 0) {
-        const double frac = __ldg(pd.mesh.frac + slot).x;
+        const double frac = ldw<GFRAC>(mesh.frac, slot).x;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             mss[j] = mass[j];
@@ -387,7 +393,7 @@ SB_D void boundary_row(const ProbDev& pd, int64_t k, int side, double tt, double
             }
         }
     } else {  // src/assembler.jl:98-122
-        const double frac = __ldg(pd.mesh.frac + slot).y;
+        const double frac = ldw<GFRAC>(mesh.frac, slot).y;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             mss[j] = mass[2 * P + j];
@@ -437,18 +443,20 @@ SB_D void boundary_row(const ProbDev& pd, int64_t k, int side, double tt, double
 }
 
 // Sink concept: row(r, Jl, Jd, Ju, F) when JAC, value(r, du) otherwise.
-template <class Fn, int R, int TT, bool SYM0, bool JAC, class Sink>
-SB_D void assemble_chunk(const ProbDev& pd, int64_t k, int t, double tt, double inv_tau, const double* prm,
-                         const double (&uc)[R][Fn::npde], const double (&bc)[R][Fn::npde], Sink& sink) {
+template <class Fn, int R, int TT, bool SYM0, bool JAC, bool GLOB = true, class Sink>
+// mesh: weight arrays (global or shared memory); ub/bb: this instance's u and b in device layout (global or
+// shared memory); mass: its 3*P mass flags; prm: its functor parameters.
+SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* ub, const double* bb, const double* mass,
+                         int t, double tt, double inv_tau, const double* prm, const double (&uc)[R][Fn::npde],
+                         const double (&bc)[R][Fn::npde], Sink& sink) {
     constexpr int P = Fn::npde;
     constexpr int ND = JAC ? 2 * P : 0;
     constexpr int PO = JAC ? P : 0;
     const int Nx = pd.Nx;
     const int i0 = t * R;
-    const double* ub = pd.u + (size_t)k * pd.L * P;
     double mI[P];  // interior mass flags * inv_tau
 #pragma unroll
-    for (int p = 0; p < P; ++p) mI[p] = inv_tau * __ldg(pd.mass + (size_t)k * 3 * P + P + p);
+    for (int p = 0; p < P; ++p) mI[p] = inv_tau * mass[P + p];
 
     // The right boundary row is prepared once, by the thread that owns node Nx-1 (one inlined copy of the
     // boundary code instead of one per unrolled row); the left one in the r == 0 copy of the loop below.
@@ -461,11 +469,11 @@ SB_D void assemble_chunk(const ProbDev& pd, int64_t k, int t, double tt, double 
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             uM[p] = ub[(size_t)sM * P + p]; uN[p] = ub[(size_t)sN * P + p];
-            bN[p] = JAC ? pd.b[((size_t)k * pd.L + sN) * P + p] : 0.0;
+            bN[p] = JAC ? bb[(size_t)sN * P + p] : 0.0;
         }
         IntervalRes<P, ND> IN;
-        eval_interval<Fn, ND, SYM0>(pd, sM, uM, uN, tt, prm, IN);
-        boundary_row<Fn, JAC, ND>(pd, k, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
+        eval_interval<Fn, ND, SYM0, GLOB>(mesh, sM, uM, uN, tt, prm, IN);
+        boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, ub, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
     }
 
     double un[P];  // first node of the next chunk
@@ -475,7 +483,7 @@ SB_D void assemble_chunk(const ProbDev& pd, int64_t k, int t, double tt, double 
         const int slot = (R - 1) * TT + t - 1;
 #pragma unroll
         for (int p = 0; p < P; ++p) ul[p] = ub[(size_t)slot * P + p];
-        eval_interval<Fn, ND, SYM0>(pd, slot, ul, uc[0], tt, prm, Lr);
+        eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, ul, uc[0], tt, prm, Lr);
     } else {
 #pragma unroll
         for (int p = 0; p < P; ++p) { Lr.c[p] = Dual<ND>(1.0); Lr.f[p] = Dual<ND>(0.0); Lr.s[p] = Dual<ND>(0.0); }
@@ -489,13 +497,13 @@ SB_D void assemble_chunk(const ProbDev& pd, int64_t k, int t, double tt, double 
     for (int r = 0; r < R; ++r) {
         const int i = i0 + r;
         const int slot = r * TT + t;
-        if (i <= Nx - 2) eval_interval<Fn, ND, SYM0>(pd, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr);
+        if (i <= Nx - 2) eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr);
 
         // interior node, src/assembler.jl:60-95 (computed for every row; boundary / padding rows are replaced below)
         double frR = 0.0, frL = 0.0;
-        if constexpr (!(Fn::c_unit && Fn::s_zero)) { const double2 fr = __ldg(pd.mesh.frac + slot); frR = fr.x; frL = fr.y; }
+        if constexpr (!(Fn::c_unit && Fn::s_zero)) { const double2 fr = ldw<GLOB>(mesh.frac, slot); frR = fr.x; frL = fr.y; }
         double ivol = 0.0;
-        if constexpr (Fn::c_unit) ivol = __ldg(pd.mesh.ivol + slot);
+        if constexpr (Fn::c_unit) ivol = ldw<GLOB>(mesh.ivol, slot);
         RowOut<P> row;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -540,7 +548,7 @@ SB_D void assemble_chunk(const ProbDev& pd, int64_t k, int t, double tt, double 
             double b0[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) b0[p] = JAC ? bc[0][p] : 0.0;
-            boundary_row<Fn, JAC, ND>(pd, k, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
+            boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, ub, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
         }
         if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
             if (i == Nx - 1) row = rowN;
@@ -584,10 +592,27 @@ SB_D void load_chunk(const double* base, int t, double (&v)[R][P]) {
     }
 }
 
+// bookkeeping of one instance after its Newton update (thread t == 0 of the system; src/utils.jl:323-333).
+// No global loads: the iteration number is the same for every active instance of a step and comes from the
+// host; the total counter is a fire-and-forget reduction.  Returns the position in the compacted list of
+// still-active instances (-1 when the instance converged); the caller stores list_out[pos] = k later, so
+// the latency of the returning atomic is not exposed.
+SB_D int finalize_system(const ProbDev& pd, int64_t k, double ss, double tol, int slot) {
+    const double nm = ::sqrt(ss);
+    const int it = pd.iter_no;
+    pd.norm[k] = nm;
+    if (pd.hist && it < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it] = nm;
+    pd.iters[k] = it + 1;
+    atomicAdd((unsigned long long*)(pd.total_iters + k), 1ull);
+    if (!(nm == nm) || nm > 1.0e300) pd.status[k] = 2;
+    if (nm < tol) { pd.active[k] = 0; return -1; }
+    return (int)atomicAdd(pd.active_count + slot, 1u);
+}
+
 // update u, ||h||_2, iteration counter and stop test (src/utils.jl:321-333)
 template <int P, int R, int TT>
 SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc)[R][P], const Vec<P> (&h)[R],
-                          double tol, int slot, double* sm) {
+                          double tol, int slot, double* sm, int* list_out = nullptr) {
     double* ub = pd.u + (size_t)k * pd.L * P;
     double ss = 0.0;
 #pragma unroll
@@ -602,16 +627,8 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
     }
     ss = system_sum<TT>(ss, sm, t);
     if (t == 0) {
-        const double nm = ::sqrt(ss);
-        const int it = pd.iters[k];
-        pd.norm[k] = nm;
-        if (pd.hist && it < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it] = nm;
-        pd.iters[k] = it + 1;
-        pd.total_iters[k] += 1;
-        const bool still = !(nm < tol);
-        if (!still) pd.active[k] = 0;
-        else atomicAdd(pd.active_count + slot, 1u);
-        if (!(nm == nm) || nm > 1.0e300) pd.status[k] = 2;
+        const int pos = finalize_system(pd, k, ss, tol, slot);
+        if (pos >= 0 && list_out) list_out[pos] = (int)k;
     }
 }
 
@@ -635,7 +652,10 @@ struct StoreSink {
     }
 };
 
-#define SB_LAUNCH_BOUNDS(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT))
+#ifndef SB_MIN_BLOCKS
+#define SB_MIN_BLOCKS 1
+#endif
+#define SB_LAUNCH_BOUNDS(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), ((TT) <= 128 ? SB_MIN_BLOCKS : 1))
 
 template <class Fn, int R, int TT, bool SYM0, bool JAC>
 __global__ void SB_LAUNCH_BOUNDS(TT) k_assemble(ProbDev pd, double tt, double inv_tau, int all_instances) {
@@ -647,7 +667,8 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_assemble(ProbDev pd, double tt, double in
     load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
     if constexpr (JAC) load_chunk<P, R, TT>(pd.b + (size_t)k * pd.L * P, t, bc);
     StoreSink<P, TT> sink{pd, k, t};
-    assemble_chunk<Fn, R, TT, SYM0, JAC>(pd, k, t, tt, inv_tau, pd.prm + (size_t)k * pd.nprm, uc, bc, sink);
+    assemble_chunk<Fn, R, TT, SYM0, JAC>(pd, pd.mesh, pd.u + (size_t)k * pd.L * P, pd.b + (size_t)k * pd.L * P,
+                                         pd.mass + (size_t)k * 4 * P, t, tt, inv_tau, pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -698,10 +719,195 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_newton_fused(ProbDev pd, double tt, doubl
     load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
     load_chunk<P, R, TT>(pd.b + (size_t)k * pd.L * P, t, bc);
     ChunkThomas<P, R> th;
-    assemble_chunk<Fn, R, TT, SYM0, true>(pd, k, t, tt, inv_tau, pd.prm + (size_t)k * pd.nprm, uc, bc, th);
+    assemble_chunk<Fn, R, TT, SYM0, true>(pd, pd.mesh, pd.u + (size_t)k * pd.L * P, pd.b + (size_t)k * pd.L * P,
+                                          pd.mass + (size_t)k * 4 * P, t, tt, inv_tau, pd.prm + (size_t)k * pd.nprm_s, uc, bc, th);
     Vec<P> h[R];
     th.template finish<TT>(h, sm, t);
     update_and_test<P, R, TT>(pd, k, t, uc, h, tol, slot, sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent fused Newton iteration with TMA prefetch.
+// One CTA per SM slot loops over the compacted list of still-active instances.  While instance j is
+// being assembled/eliminated out of shared memory, the bulk-copy engine (cp.async.bulk, completion on
+// an mbarrier) already streams u and b of instance j+stride into the other stage, so DRAM latency is off
+// the critical path; the mesh weights are copied to shared memory once per CTA.  TT == 32: every warp
+// of the CTA runs its own pipeline (own stages, own mbarriers, warp-level syncs only).
+// ---------------------------------------------------------------------------------------------
+SB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SB_D void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+SB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SB_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+SB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <class Fn, int R, int TT, bool SYM0>
+struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
+    static constexpr int P = Fn::npde, L = R * TT, G = (TT == 32) ? kWarpBlockThreads / 32 : 1;
+    static constexpr int NPS = (Fn::nparams + 1) / 2 * 2;  // parameter block stride (even)
+    static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
+    static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
+    static constexpr int oGw = 0, oAB = oGw + nGw, oIvol = oAB + nAB, oFrac = oIvol + nIvol, mesh_doubles = oFrac + nFrac;
+    static constexpr int scratch = ChunkThomas<P, R>::template smem_doubles<TT>();
+    // per group: u[2][L*P], b[2][L*P], prm[2][NPS], mass[2][4P], scratch, partial sums [2][8], instance index [2]
+    static constexpr int oU = 0, oB = oU + 2 * L * P, oPrm = oB + 2 * L * P, oMass = oPrm + 2 * NPS, oScr = oMass + 8 * P,
+                         oSum = oScr + scratch, oK = oSum + 16, group_doubles = oK + 2;
+    static constexpr int bar_doubles = 2 * G;  // one mbarrier (8 bytes) per stage and group
+    static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
+};
+
+#define SB_LAUNCH_BOUNDS_P(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), 512 / ((TT) == 32 ? kWarpBlockThreads : (TT)))
+template <class Fn, int R, int TT, bool SYM0>
+__global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
+                                                          int prev_slot, int parity) {
+    using LY = FusedPLayout<Fn, R, TT, SYM0>;
+    constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS;
+    extern __shared__ __align__(16) double smp[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smp);
+    double* mesh_sm = smp + LY::bar_doubles;
+    const int g = (TT == 32) ? (threadIdx.x >> 5) : 0;
+    const int t = (TT == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    double* grp = mesh_sm + LY::mesh_doubles + (size_t)g * LY::group_doubles;
+    double* ubuf = grp + LY::oU;      // [2][L*P]
+    double* bbuf = grp + LY::oB;      // [2][L*P]
+    double* pbuf = grp + LY::oPrm;    // [2][NPS]
+    double* mbuf = grp + LY::oMass;   // [2][4P]
+    double* scratch = grp + LY::oScr;
+    double* sums = grp + LY::oSum;    // [2][8]
+    long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index of each stage
+    uint64_t* bar = bars + 2 * g;
+
+    const int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
+    const int* list_in = (prev_slot < 0) ? nullptr : pd.list[parity];
+    int* list_out = pd.list[parity ^ 1];
+    const int stride = gridDim.x * G;
+    int j = blockIdx.x * G + g;
+    if (blockIdx.x * G >= n_in) return;  // whole CTA has nothing to do
+
+    // mesh weights -> shared memory, once per CTA
+    MeshDev mesh = pd.mesh;
+    if constexpr (SYM0) {
+        for (int i = threadIdx.x; i < L; i += blockDim.x) mesh_sm[LY::oGw + i] = pd.mesh.gw[i];
+        mesh.gw = mesh_sm + LY::oGw;
+    } else {
+        const double* src = reinterpret_cast<const double*>(pd.mesh.awbw);  // awbw[2L] and gwwf[2L] are contiguous
+        for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) mesh_sm[LY::oAB + i] = src[i];
+        mesh.awbw = reinterpret_cast<const double2*>(mesh_sm + LY::oAB);
+        mesh.gwwf = reinterpret_cast<const double2*>(mesh_sm + LY::oAB + 2 * L);
+    }
+    if constexpr (Fn::c_unit) {
+        for (int i = threadIdx.x; i < L; i += blockDim.x) mesh_sm[LY::oIvol + i] = pd.mesh.ivol[i];
+        mesh.ivol = mesh_sm + LY::oIvol;
+    }
+    if constexpr (LY::kFrac) {
+        const double* src = reinterpret_cast<const double*>(pd.mesh.frac);
+        for (int i = threadIdx.x; i < 2 * L; i += blockDim.x) mesh_sm[LY::oFrac + i] = src[i];
+        mesh.frac = reinterpret_cast<const double2*>(mesh_sm + LY::oFrac);
+    }
+    if (t == 0) {
+        mbar_init(bar + 0, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr uint32_t kBytes = (uint32_t)(L * P * sizeof(double));
+    constexpr uint32_t kPrmBytes = (uint32_t)(NPS * sizeof(double)), kMassBytes = (uint32_t)(4 * P * sizeof(double));
+    // thread t == 0 of the group is the producer: it knows the instance indices two stages ahead
+    long long k_next = -1, k_next2 = -1;
+    if (t == 0) {
+        if (j < n_in) k_next = list_in ? list_in[j] : j;
+        if (j + stride < n_in) k_next2 = list_in ? list_in[j + stride] : j + stride;
+    }
+    auto issue = [&](long long kk, int stage) {
+        kslot[stage] = kk;
+        mbar_expect_tx(bar + stage, 2 * kBytes + kPrmBytes + kMassBytes);
+        bulk_g2s(ubuf + (size_t)stage * L * P, pd.u + (size_t)kk * L * P, kBytes, bar + stage);
+        bulk_g2s(bbuf + (size_t)stage * L * P, pd.b + (size_t)kk * L * P, kBytes, bar + stage);
+        bulk_g2s(pbuf + stage * NPS, pd.prm + (size_t)kk * NPS, kPrmBytes, bar + stage);
+        bulk_g2s(mbuf + stage * 4 * P, pd.mass + (size_t)kk * 4 * P, kMassBytes, bar + stage);
+    };
+    if (t == 0 && k_next >= 0) issue(k_next, 0);
+    if constexpr (TT == 32) __syncwarp();
+    else __syncthreads();  // kslot[0] visible
+
+    int pend_pos = -1, pend_k = 0;  // deferred list write of the previous instance (thread t == 0)
+    int it = 0;
+    for (; j < n_in; j += stride, ++it) {
+        const int stage = it & 1;
+        if (t == 0) {
+            // refill the other stage (released by the barrier inside the previous iteration's reduction)
+            if (k_next2 >= 0) issue(k_next2, stage ^ 1);
+            k_next = k_next2;
+            const int j3 = j + 2 * stride;
+            k_next2 = (j3 < n_in) ? (list_in ? (long long)list_in[j3] : (long long)j3) : -1;
+            if (pend_pos >= 0) { list_out[pend_pos] = pend_k; pend_pos = -1; }
+        }
+        const double* us = ubuf + (size_t)stage * L * P;
+        const double* bs = bbuf + (size_t)stage * L * P;
+        const double* prm = pbuf + stage * NPS;
+        const double* mass = mbuf + stage * 4 * P;
+        mbar_wait(bar + stage, (it >> 1) & 1);
+        const int64_t k = kslot[stage];
+
+        double uc[R][P], bc[R][P];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < P; ++p) { uc[r][p] = us[(r * TT + t) * P + p]; bc[r][p] = bs[(r * TT + t) * P + p]; }
+        ChunkThomas<P, R> th;
+        assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, us, bs, mass, t, tt, inv_tau, prm, uc, bc, th);
+        Vec<P> h[R];
+        th.template finish<TT>(h, scratch, t);
+
+        // update, ||h||^2 of the system; the barrier of this reduction also releases the stage and the scratch
+        double* ug = pd.u + (size_t)k * L * P;
+        double ss = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (t * R + r < pd.Nx) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    ug[(size_t)(r * TT + t) * P + p] = uc[r][p] - h[r].a[p];
+                    ss += h[r].a[p] * h[r].a[p];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
+        if constexpr (TT > 32) {
+            double* sl = sums + (it & 1) * 8;
+            if ((t & 31) == 0) sl[t >> 5] = ss;
+            __syncthreads();
+            if (t == 0) {
+#pragma unroll
+                for (int w = 1; w < TT / 32; ++w) ss += sl[w];
+            }
+        } else {
+            __syncwarp();
+        }
+        if (t == 0) {
+            pend_pos = finalize_system(pd, k, ss, tol, slot);
+            pend_k = (int)k;
+        }
+    }
+    if (t == 0 && pend_pos >= 0) list_out[pend_pos] = pend_k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -712,13 +918,13 @@ __global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary
     constexpr int P = Fn::npde;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= pd.B) return;
-    double* mk = mass + (size_t)k * 3 * P;
+    double* mk = mass + (size_t)k * 4 * P;
     if (stationary) {
         for (int i = 0; i < 3 * P; ++i) mk[i] = 1.0;
         return;
     }
     const double* ub = pd.u + (size_t)k * pd.L * P;
-    const double* prm = pd.prm + (size_t)k * pd.nprm;
+    const double* prm = pd.prm + (size_t)k * pd.nprm_s;
     const int R = pd.R, T = pd.T, Nx = pd.Nx;
     auto slot_of = [&](int i) { return (i % R) * T + i / R; };
     double u0[P], u1[P], uN[P];
@@ -732,7 +938,7 @@ __global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary
     for (int p = 0; p < P; ++p) { ul_[p] = Dual<0>(u0[p]); ur_[p] = Dual<0>(uN[p]); }
     Fn::template bc<Dual<0>>(pd.x0, ul_, pd.xN, ur_, t0, prm, pl, ql, pr, qr);
     IntervalRes<P, 0> res;
-    eval_interval<Fn, 0, false>(pd, slot_of(0), u0, u1, t0, prm, res);
+    eval_interval<Fn, 0, false>(pd.mesh, slot_of(0), u0, u1, t0, prm, res);
     for (int i = 0; i < P; ++i) {
         mk[i] = (ql[i] == 0.0 && !pd.singular) ? 0.0 : 1.0;   // :162-165
         mk[P + i] = (res.c[i].v == 0.0) ? 0.0 : 1.0;           // :157-160
@@ -751,7 +957,7 @@ __global__ void k_begin_step(ProbDev pd) {
     const int r = s / pd.T, t = s - r * pd.T;
     const int i = t * pd.R + r;
     if (s == 0) { pd.active[k] = 1; pd.iters[k] = 0; }
-    const double* mass = pd.mass + (size_t)k * 3 * P;
+    const double* mass = pd.mass + (size_t)k * 4 * P;
     const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);
 #pragma unroll
     for (int p = 0; p < P; ++p) {

@@ -22,6 +22,7 @@ constexpr bool decomp_ok(int P, int d) { return P == 1 || kDecomp[d].R <= 8; }  
 
 typedef void (*AssembleKernel)(ProbDev, double, double, int);
 typedef void (*FusedKernel)(ProbDev, double, double, double, int);
+typedef void (*FusedPKernel)(ProbDev, double, double, double, int, int, int);
 typedef void (*SolveKernel)(ProbDev, double, int, int);
 typedef void (*MassKernel)(ProbDev, double, double*, int);
 
@@ -31,6 +32,8 @@ struct FunctorEntry {
     AssembleKernel assemble_jac[kNumDecomp][2];  // [decomposition][SYM0]
     AssembleKernel assemble_val[kNumDecomp][2];
     FusedKernel fused[kNumDecomp][2];
+    FusedPKernel fused_p[kNumDecomp][2];      // persistent TMA-prefetch variant
+    size_t fused_p_smem[kNumDecomp][2];       // its dynamic shared memory (bytes)
     MassKernel mass;
 };
 
@@ -44,8 +47,15 @@ void fill_one(FunctorEntry& e) {
         e.assemble_val[D][1] = k_assemble<Fn, R, TT, true, false>;
         e.fused[D][0] = k_newton_fused<Fn, R, TT, false>;
         e.fused[D][1] = k_newton_fused<Fn, R, TT, true>;
+        e.fused_p[D][0] = k_newton_fused_p<Fn, R, TT, false>;
+        e.fused_p[D][1] = k_newton_fused_p<Fn, R, TT, true>;
+        e.fused_p_smem[D][0] = FusedPLayout<Fn, R, TT, false>::bytes;
+        e.fused_p_smem[D][1] = FusedPLayout<Fn, R, TT, true>::bytes;
     } else {
-        for (int s = 0; s < 2; ++s) { e.assemble_jac[D][s] = nullptr; e.assemble_val[D][s] = nullptr; e.fused[D][s] = nullptr; }
+        for (int s = 0; s < 2; ++s) {
+            e.assemble_jac[D][s] = nullptr; e.assemble_val[D][s] = nullptr; e.fused[D][s] = nullptr;
+            e.fused_p[D][s] = nullptr; e.fused_p_smem[D][s] = 0;
+        }
     }
 }
 

@@ -123,7 +123,7 @@ def _gpu_transient(ctx, c, design, **kw):
                     return_device=True, **kw)
 
 
-@pytest.mark.parametrize("design", ["fused", "split"])
+@pytest.mark.parametrize("design", ["fused", "fused_tma", "split"])
 @pytest.mark.parametrize("make", [ex.example101, ex.example102, ex.example103, ex.example106, ex.example107,
                                   ex.example201], ids=lambda f: f.__name__)
 def test_reference_examples_transient(ctx, oracle, design, make):
@@ -146,7 +146,7 @@ def test_reference_examples_transient(ctx, oracle, design, make):
     assert np.allclose(h0, r["hist"][0, :, 0], rtol=1e-8)
 
 
-@pytest.mark.parametrize("design", ["fused", "split"])
+@pytest.mark.parametrize("design", ["fused", "fused_tma", "split"])
 @pytest.mark.parametrize("make,c0", [(ex.example104, 1.0), (ex.example104, 0.0), (ex.example105, None)])
 def test_reference_examples_stationary(ctx, oracle, design, make, c0):
     c = make() if c0 is None else make(c0=c0)
@@ -180,7 +180,7 @@ def test_example201_boundary_flux_golden(ctx):
 
 @pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 48, 1024, 6), ("3a", 40, 512, 12), ("3b", 40, 512, 12),
                                             ("4", 40, 256, 25)])
-@pytest.mark.parametrize("design", ["fused", "split"])
+@pytest.mark.parametrize("design", ["fused", "fused_tma", "split"])
 def test_baseline_configs_batched(ctx, oracle, cfg, B, Nx, nsteps, design):
     """BASELINE configs at full mesh size, reduced batch and step count: every instance against the
     oracle (1e-10 relative, identical per-step iteration counts)."""
