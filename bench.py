@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", help="BASELINE config: 2 (default), 3a, 3b, 4")
-    ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused"), choices=["fused", "fused_tma", "split"])
+    ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused_tma"), choices=["fused", "fused_tma", "split"])
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's B)")
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--time-steps", type=int, default=0, help="truncate the time loop (testing only)")

@@ -108,6 +108,10 @@ int sb_kernel_launches(int64_t* count);
 int sb_ctx_create(int device, void* stream, sb_ctx** out);
 int sb_ctx_destroy(sb_ctx* ctx);
 int sb_ctx_synchronize(sb_ctx* ctx);
+/* page-locked host memory for upload/download buffers (the copies of sb_state_upload/download run at
+ * full PCIe/NVLink-C2C speed only from pinned memory)                                             */
+int sb_host_alloc(size_t bytes, void** out);
+int sb_host_free(void* p);
 
 /* functor metadata: npde and number of per-instance parameters of a registry entry              */
 int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name);

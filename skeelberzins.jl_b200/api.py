@@ -19,6 +19,7 @@ per-instance parameter matrix -- that is the parameter sweep.  ``icfun`` stays a
 in the reference (src/utils.jl:629-632).
 """
 import ctypes
+import weakref
 from dataclasses import dataclass, field, replace
 from typing import Optional, Sequence, Union
 
@@ -82,6 +83,46 @@ def kernel_launches():
     return n.value
 
 
+class _PinnedPool:
+    """Page-locked host buffers for results.  A buffer goes back to the pool when the numpy array that wraps
+    it (and every view of it) has been garbage-collected, so repeated solves re-use the same pinned pages."""
+
+    def __init__(self, max_cached=4):
+        self.free, self.max_cached = {}, max_cached
+
+    def empty(self, shape):
+        n = int(np.prod(shape))
+        nbytes = max(n, 1) * 8
+        lst = self.free.get(nbytes)
+        if lst:
+            ptr = lst.pop()
+        else:
+            p = ctypes.c_void_p()
+            _lib.check(_lib.load().sb_host_alloc(nbytes, ctypes.byref(p)))
+            ptr = p.value
+        buf = (ctypes.c_double * max(n, 1)).from_address(ptr)
+        weakref.finalize(buf, self._release, ptr, nbytes)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+
+    def _release(self, ptr, nbytes):
+        lst = self.free.setdefault(nbytes, [])
+        if sum(len(v) for v in self.free.values()) < self.max_cached:
+            lst.append(ptr)
+        else:
+            try:
+                _lib.load().sb_host_free(ctypes.c_void_p(ptr))
+            except Exception:
+                pass
+
+
+_pinned = _PinnedPool()
+
+
+def pinned_empty(shape):
+    """float64 array in page-locked host memory (fast H2D/D2H); freed/re-used when garbage-collected."""
+    return _pinned.empty(shape)
+
+
 class Context:
     """One per GPU (sb_ctx).  stream: a cudaStream_t handle (int) to run on, or None for an own stream."""
 
@@ -118,7 +159,7 @@ def default_context(device=0):
 class DeviceProblem:
     """Thin object wrapper of sb_problem: the per-iteration entry points of the C ABI."""
 
-    def __init__(self, ctx, m, xmesh, functor, design="fused"):
+    def __init__(self, ctx, m, xmesh, functor, design="fused_tma"):
         self.lib = _lib.load()
         self.ctx = ctx
         x = np.ascontiguousarray(xmesh, dtype=np.float64)
@@ -183,7 +224,7 @@ class DeviceProblem:
 
     def download(self, out=None):
         if out is None:
-            out = np.empty((self.B, self.Nx, self.npde))
+            out = pinned_empty((self.B, self.Nx, self.npde))
         _lib.check(self.lib.sb_state_download(self._h, _lib.ptr(out)))
         return out
 
@@ -390,7 +431,7 @@ def _merge_params(params, kwargs, stationary):
     return p
 
 
-def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design="fused"):
+def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design="fused_tma"):
     """problem_init (src/utils.jl:609-663) for the whole batch."""
     if not isinstance(pdefun, Functor):
         raise TypeError("pdefun must be a registry Functor (device-compiled); arbitrary host closures cannot run "
@@ -473,7 +514,7 @@ def newton(pb, tau, timeStep, tol=1.0e-10, maxit=100, hist_flag=False, c_loop=Fa
 newton_stat = newton  # src/utils.jl:344-378: same loop, residual without mass matrix (flags all 1, inv_tau = 0)
 
 
-def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused", save="all",
+def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused_tma", save="all",
           squeeze=None, c_loop=False, return_device=False, **kwargs):
     """Batched pdepe.  With `tspan`: transient solve by implicit Euler (src/pdepe.jl:42-128); without:
     stationary solve by one Newton solve with tau = Inf, t = 1 (src/pdepe.jl:156-192).

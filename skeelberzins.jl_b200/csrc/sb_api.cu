@@ -141,9 +141,7 @@ struct sb_problem {
     int *d_active = nullptr, *d_iters = nullptr, *d_status = nullptr;
     long long* d_total = nullptr;
     unsigned int* d_count = nullptr;
-    unsigned int* h_count = nullptr;  // pinned
-    cudaEvent_t ev[kSlots];
-    bool ev_ok = false;
+    unsigned int* h_count = nullptr;  // mapped pinned: the kernels publish the active count of each launch here
     // step state
     double t_next = 0.0, inv_tau = 0.0;
     long launched = 0, confirmed = 0;
@@ -269,6 +267,17 @@ extern "C" {
 const char* sb_version(void) { return "skeelberzins_b200 0.1.0 (sm_100a)"; }
 const char* sb_last_error(void) { return g_err.c_str(); }
 
+int sb_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(SB_ERR_INVALID, "out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SB_OK;
+}
+
+int sb_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return SB_OK;
+}
+
 int sb_kernel_launches(int64_t* count) {
     if (!count) return fail(SB_ERR_INVALID, "count is NULL");
     *count = g_launches;
@@ -353,7 +362,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     CU(cudaSetDevice(ctx->device));
 
     sb_problem* pb = new sb_problem;
-    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = pb->design_pending = SB_DESIGN_FUSED;
+    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
     pb->dec = pick_decomposition(Nx, pb->P);
     if (pb->dec < 0) {
         delete pb;
@@ -427,17 +436,16 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     TRY(dev_alloc(&pb->d_iters, (size_t)B));
     TRY(dev_alloc(&pb->d_status, (size_t)B));
     TRY(dev_alloc(&pb->d_total, (size_t)B));
-    TRY(dev_alloc(&pb->d_count, (size_t)kSlots));
+    TRY(dev_alloc(&pb->d_count, (size_t)2 * kSlots));  // active counts [kSlots] + done tickets [kSlots]
     TRY(dev_alloc(&pb->d_list, (size_t)2 * B));
 #undef TRY
     if (rc != SB_OK) { sb_problem_destroy(pb); return rc; }
-    cudaError_t e = cudaHostAlloc((void**)&pb->h_count, kSlots * sizeof(unsigned int), cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void**)&pb->h_count, kSlots * sizeof(unsigned int), cudaHostAllocMapped);
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
-    for (int i = 0; i < kSlots; ++i) {
-        e = cudaEventCreateWithFlags(&pb->ev[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
-    }
-    pb->ev_ok = true;
+    unsigned int* d_hcount = nullptr;
+    e = cudaHostGetDevicePointer((void**)&d_hcount, pb->h_count, 0);
+    if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
+    for (int i = 0; i < kSlots; ++i) pb->h_count[i] = 0;
     cudaStream_t st = ctx->stream;
     e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && fe->nparams > 0)
@@ -451,7 +459,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_status, 0, B * sizeof(int), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_total, 0, B * sizeof(long long), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_norm, 0, B * sizeof(double), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_count, 0, 2 * kSlots * sizeof(unsigned int), st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "problem upload: %s", cudaGetErrorString(e)); }
     // all-ones mass flags until sb_mass_flags is called
@@ -470,6 +478,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.active = pb->d_active; pd.iters = pb->d_iters; pd.total_iters = pb->d_total; pd.norm = pb->d_norm;
     pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;
     pd.list[0] = pb->d_list; pd.list[1] = pb->d_list + B;
+    pd.done_count = pb->d_count + kSlots; pd.host_count = d_hcount;
     pb->last_active = B;
     *out = pb;
     return SB_OK;
@@ -484,7 +493,6 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
-    if (pb->ev_ok) for (int i = 0; i < kSlots; ++i) cudaEventDestroy(pb->ev[i]);
     delete pb;
     return SB_OK;
 }
@@ -633,7 +641,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     pb->t_next = t_next; pb->inv_tau = inv_tau;
     pb->design = pb->design_pending;
     cudaStream_t st = pb->ctx->stream;
-    CU(cudaMemsetAsync(pb->d_count, 0, kSlots * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(pb->d_count, 0, 2 * kSlots * sizeof(unsigned int), st));
     const size_t total = (size_t)pb->pd.B * pb->pd.L;
     const int bs = 256;
     if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
@@ -644,22 +652,46 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     return SB_OK;
 }
 
+constexpr unsigned int kPending = 0xFFFFFFFFu;  // host_count value of a launch that has not reported yet
+
+// spin until the launch that uses ring slot s has published its active count (mapped host memory)
+static int wait_slot(sb_problem* pb, int s, unsigned int* value) {
+    volatile unsigned int* p = pb->h_count + s;
+    unsigned long spins = 0;
+    unsigned int v;
+    while ((v = *p) == kPending) {
+        if ((++spins & 0x3FFF) == 0) {  // every so often make sure the stream is still alive
+            cudaError_t e = cudaStreamQuery(pb->ctx->stream);
+            if (e == cudaSuccess) {
+                if ((v = *p) != kPending) break;
+                return fail(SB_ERR_CUDA, "Newton-iteration launch finished without reporting its active count");
+            }
+            if (e != cudaErrorNotReady) return fail(SB_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
+        }
+    }
+    *value = v;
+    return SB_OK;
+}
+
 static int prepare_slot(sb_problem* pb, int* slot) {
     const int s = (int)(pb->launched % kSlots);
     pb->pd.iter_no = (int)pb->launched;  // Newton iteration number inside the step (lock-step: same for all active instances)
     if (pb->launched >= kSlots) {  // ring wrapped: the slot's previous value must have been delivered, then re-zero it
         if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; }
-        CU(cudaEventSynchronize(pb->ev[s]));
+        unsigned int v;
+        int rc = wait_slot(pb, s, &v);
+        if (rc) return rc;
         if (pb->confirmed < pb->launched - kSlots + 1) pb->confirmed = pb->launched - kSlots + 1;
         CU(cudaMemsetAsync(pb->d_count + s, 0, sizeof(unsigned int), pb->ctx->stream));
+        CU(cudaMemsetAsync(pb->d_count + kSlots + s, 0, sizeof(unsigned int), pb->ctx->stream));
     }
+    *((volatile unsigned int*)pb->h_count + s) = kPending;
     *slot = s;
     return SB_OK;
 }
 
 static int finish_slot(sb_problem* pb, int slot) {
-    CU(cudaMemcpyAsync(pb->h_count + slot, pb->d_count + slot, sizeof(unsigned int), cudaMemcpyDeviceToHost, pb->ctx->stream));
-    CU(cudaEventRecord(pb->ev[slot], pb->ctx->stream));
+    (void)slot;
     pb->launched++;
     return SB_OK;
 }
@@ -743,17 +775,16 @@ int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active) {
     CU(cudaSetDevice(pb->ctx->device));
     if (pb->launched == 0) { *n_active = pb->last_active; return SB_OK; }
     if (blocking) {
-        const int s = (int)((pb->launched - 1) % kSlots);
-        CU(cudaEventSynchronize(pb->ev[s]));
+        unsigned int v;
+        int rc = wait_slot(pb, (int)((pb->launched - 1) % kSlots), &v);
+        if (rc) return rc;
         pb->confirmed = pb->launched;
-        pb->last_active = pb->h_count[s];
+        pb->last_active = v;
     } else {
         while (pb->confirmed < pb->launched) {
-            const int s = (int)(pb->confirmed % kSlots);
-            cudaError_t e = cudaEventQuery(pb->ev[s]);
-            if (e == cudaErrorNotReady) break;
-            if (e != cudaSuccess) return fail(SB_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
-            pb->last_active = pb->h_count[s];
+            const unsigned int v = *((volatile unsigned int*)pb->h_count + (pb->confirmed % kSlots));
+            if (v == kPending) break;
+            pb->last_active = v;
             pb->confirmed++;
         }
     }
@@ -766,10 +797,11 @@ int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active) {
     if (it < 0 || it >= pb->launched) return fail(SB_ERR_INVALID, "iteration %d has not been launched in this step", it);
     if (it < pb->launched - kSlots) return fail(SB_ERR_INVALID, "iteration %d is older than the %d-slot counter ring", it, kSlots);
     CU(cudaSetDevice(pb->ctx->device));
-    const int s = it % kSlots;
-    CU(cudaEventSynchronize(pb->ev[s]));
-    *n_active = pb->h_count[s];
-    if (pb->confirmed < it + 1) { pb->confirmed = it + 1; pb->last_active = *n_active; }
+    unsigned int v;
+    int rc = wait_slot(pb, it % kSlots, &v);
+    if (rc) return rc;
+    *n_active = v;
+    if (pb->confirmed < it + 1) { pb->confirmed = it + 1; pb->last_active = v; }
     return SB_OK;
 }
 
@@ -786,9 +818,10 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
             int rc = sb_newton_iteration(pb, tol);
             if (rc) return rc;
         }
-        const int s = (int)((base + done) % kSlots);
-        CU(cudaEventSynchronize(pb->ev[s]));
-        n_act = pb->h_count[s];
+        unsigned int v;
+        int rc = wait_slot(pb, (int)((base + done) % kSlots), &v);
+        if (rc) return rc;
+        n_act = v;
         done++;
         pb->confirmed = base + done;
         pb->last_active = n_act;

@@ -66,7 +66,23 @@ struct ProbDev {
     int hist_cap;
     unsigned int* active_count;  // [slots]
     int* list[2];          // compacted indices of the instances still active (ping-pong between iterations)
+    unsigned int* done_count;             // [slots] groups (systems' thread groups / CTAs) that finished the launch
+    volatile unsigned int* host_count;    // [slots] mapped pinned host memory: active count of a finished launch
 };
+
+// Completion notice of a Newton-iteration launch without a copy node in the stream: every thread group takes a
+// ticket when it is done; the last one publishes the number of still-active instances straight into mapped
+// host memory, where the host loop polls it (src/utils.jl:329-333 is the decision it feeds).
+SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(pd.done_count + slot, 1u);
+    if (ticket == total_groups - 1) {
+        __threadfence();
+        const unsigned int c = atomicAdd(pd.active_count + slot, 0u);
+        pd.host_count[slot] = c;
+        __threadfence_system();
+    }
+}
 
 // reciprocal without the special-case slow path of 1.0/x: MUFU.RCP64H seed + two Newton steps
 // (full double precision for normal, non-zero arguments; a zero pivot turns into NaN and is
@@ -629,6 +645,7 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
     if (t == 0) {
         const int pos = finalize_system(pd, k, ss, tol, slot);
         if (pos >= 0 && list_out) list_out[pos] = (int)k;
+        group_done(pd, slot, gridDim.x * (TT == 32 ? kWarpBlockThreads / 32 : 1));
     }
 }
 
@@ -678,8 +695,11 @@ template <int P, int R, int TT>
 __global__ void SB_LAUNCH_BOUNDS(TT) k_solve(ProbDev pd, double tol, int slot, int update) {
     extern __shared__ double sm[];
     int64_t k; int t;
-    if (!locate<TT>(pd, k, t)) return;
-    if (update && !pd.active[k]) return;
+    const bool in_range = locate<TT>(pd, k, t);
+    if (!in_range || (update && !pd.active[k])) {
+        if (update && t == 0) group_done(pd, slot, gridDim.x * (TT == 32 ? kWarpBlockThreads / 32 : 1));
+        return;
+    }
     ChunkThomas<P, R> th;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -713,8 +733,11 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_newton_fused(ProbDev pd, double tt, doubl
     constexpr int P = Fn::npde;
     extern __shared__ double sm[];
     int64_t k; int t;
-    if (!locate<TT>(pd, k, t)) return;
-    if (!pd.active[k]) return;
+    const bool in_range = locate<TT>(pd, k, t);
+    if (!in_range || !pd.active[k]) {
+        if (t == 0) group_done(pd, slot, gridDim.x * (TT == 32 ? kWarpBlockThreads / 32 : 1));
+        return;
+    }
     double uc[R][P], bc[R][P];
     load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
     load_chunk<P, R, TT>(pd.b + (size_t)k * pd.L * P, t, bc);
@@ -767,7 +790,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     // per group: u[2][L*P], b[2][L*P], prm[2][NPS], mass[2][4P], scratch, partial sums [2][8], instance index [2]
     static constexpr int oU = 0, oB = oU + 2 * L * P, oPrm = oB + 2 * L * P, oMass = oPrm + 2 * NPS, oScr = oMass + 8 * P,
                          oSum = oScr + scratch, oK = oSum + 16, group_doubles = oK + 2;
-    static constexpr int bar_doubles = 2 * G;  // one mbarrier (8 bytes) per stage and group
+    static constexpr int bar_doubles = 2 * G + 2;  // one mbarrier (8 bytes) per stage and group + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
 
@@ -797,35 +820,39 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
     int* list_out = pd.list[parity ^ 1];
     const int stride = gridDim.x * G;
     int j = blockIdx.x * G + g;
-    if (blockIdx.x * G >= n_in) return;  // whole CTA has nothing to do
+    if (blockIdx.x * G >= n_in) {  // whole CTA has nothing to do
+        if (t == 0) group_done(pd, slot, gridDim.x * G);
+        return;
+    }
 
-    // mesh weights -> shared memory, once per CTA
+    // mesh weights -> shared memory, once per CTA, by the bulk-copy engine (waited for right before first use)
     MeshDev mesh = pd.mesh;
-    if constexpr (SYM0) {
-        for (int i = threadIdx.x; i < L; i += blockDim.x) mesh_sm[LY::oGw + i] = pd.mesh.gw[i];
-        mesh.gw = mesh_sm + LY::oGw;
-    } else {
-        const double* src = reinterpret_cast<const double*>(pd.mesh.awbw);  // awbw[2L] and gwwf[2L] are contiguous
-        for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) mesh_sm[LY::oAB + i] = src[i];
+    uint64_t* mesh_bar = bars + 2 * G;
+    if constexpr (SYM0) mesh.gw = mesh_sm + LY::oGw;
+    else {
         mesh.awbw = reinterpret_cast<const double2*>(mesh_sm + LY::oAB);
         mesh.gwwf = reinterpret_cast<const double2*>(mesh_sm + LY::oAB + 2 * L);
     }
-    if constexpr (Fn::c_unit) {
-        for (int i = threadIdx.x; i < L; i += blockDim.x) mesh_sm[LY::oIvol + i] = pd.mesh.ivol[i];
-        mesh.ivol = mesh_sm + LY::oIvol;
-    }
-    if constexpr (LY::kFrac) {
-        const double* src = reinterpret_cast<const double*>(pd.mesh.frac);
-        for (int i = threadIdx.x; i < 2 * L; i += blockDim.x) mesh_sm[LY::oFrac + i] = src[i];
-        mesh.frac = reinterpret_cast<const double2*>(mesh_sm + LY::oFrac);
-    }
+    if constexpr (Fn::c_unit) mesh.ivol = mesh_sm + LY::oIvol;
+    if constexpr (LY::kFrac) mesh.frac = reinterpret_cast<const double2*>(mesh_sm + LY::oFrac);
+    if (threadIdx.x == 0) mbar_init(mesh_bar, 1);
     if (t == 0) {
         mbar_init(bar + 0, 1);
         mbar_init(bar + 1, 1);
+    }
+    if (threadIdx.x == 0 || t == 0) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
+        mbar_expect_tx(mesh_bar, (uint32_t)(LY::mesh_doubles * sizeof(double)));
+        if constexpr (SYM0) bulk_g2s(mesh_sm + LY::oGw, pd.mesh.gw, LB, mesh_bar);
+        else bulk_g2s(mesh_sm + LY::oAB, pd.mesh.awbw, 4 * LB, mesh_bar);  // awbw[2L] and gwwf[2L] are contiguous
+        if constexpr (Fn::c_unit) bulk_g2s(mesh_sm + LY::oIvol, pd.mesh.ivol, LB, mesh_bar);
+        if constexpr (LY::kFrac) bulk_g2s(mesh_sm + LY::oFrac, pd.mesh.frac, 2 * LB, mesh_bar);
+    }
 
     constexpr uint32_t kBytes = (uint32_t)(L * P * sizeof(double));
     constexpr uint32_t kPrmBytes = (uint32_t)(NPS * sizeof(double)), kMassBytes = (uint32_t)(4 * P * sizeof(double));
@@ -846,6 +873,7 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
     if (t == 0 && k_next >= 0) issue(k_next, 0);
     if constexpr (TT == 32) __syncwarp();
     else __syncthreads();  // kslot[0] visible
+    mbar_wait(mesh_bar, 0);
 
     int pend_pos = -1, pend_k = 0;  // deferred list write of the previous instance (thread t == 0)
     int it = 0;
@@ -907,7 +935,10 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
             pend_k = (int)k;
         }
     }
-    if (t == 0 && pend_pos >= 0) list_out[pend_pos] = pend_k;
+    if (t == 0) {
+        if (pend_pos >= 0) list_out[pend_pos] = pend_k;
+        group_done(pd, slot, gridDim.x * G);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
