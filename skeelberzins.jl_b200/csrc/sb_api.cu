@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/skeelberzins_b200.h"
+#include "sb_longmesh.cuh"
 #include "sb_registry.h"
 
 using namespace sb;
@@ -45,34 +46,36 @@ constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
 
 long long g_launches = 0;  // kernels launched by this library (all contexts; not thread-safe by design)
 
-// reference layout [B][Nx][W] <-> device layout [B][R][T][W]   (W doubles per node)
-// identity != 0: padding nodes receive the W = P*P identity block (used for Jd)
+// reference layout [B][Nx][W] <-> device layout [B][tile][R][T][W]   (W doubles per node, tiles of Lt = R*T nodes,
+// L = ntiles*Lt padded nodes per instance).  identity != 0: padding nodes receive the W = P*P identity block (Jd)
 __global__ void k_to_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
-                                   int T, int W, int identity_P) {
-    const size_t L = (size_t)R * T;
+                                   int T, int L, int W, int identity_P) {
+    const int Lt = R * T;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*L*W device elements
     if (idx >= (size_t)B * L * W) return;
     const int w = (int)(idx % W);
     const size_t ns = idx / W;
     const int64_t k = ns / L;
     const int s = (int)(ns - (size_t)k * L);
-    const int r = s / T, t = s - r * T;
-    const int i = t * R + r;
+    const int tile = s / Lt, sl = s - tile * Lt;
+    const int r = sl / T, t = sl - r * T;
+    const int i = tile * Lt + t * R + r;
     double pad = 0.0;
     if (identity_P > 0 && (w / identity_P) == (w % identity_P)) pad = 1.0;
     dst[idx] = (i < Nx) ? src[((size_t)k * Nx + i) * W + w] : pad;
 }
 
 __global__ void k_from_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
-                                     int T, int W) {
+                                     int T, int L, int W) {
+    const int Lt = R * T;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*Nx*W reference elements
     if (idx >= (size_t)B * Nx * W) return;
     const int w = (int)(idx % W);
     const size_t ni = idx / W;
     const int64_t k = ni / Nx;
     const int i = (int)(ni - (size_t)k * Nx);
-    const int r = i % R, t = i / R;
-    dst[idx] = src[(((size_t)k * R + r) * T + t) * W + w];
+    const int tile = i / Lt, il = i - tile * Lt;
+    dst[idx] = src[((size_t)k * L + (size_t)tile * Lt + (size_t)(il % R) * T + il / R) * W + w];
 }
 
 const FunctorEntry* registry() {
@@ -131,6 +134,11 @@ struct sb_problem {
     ProbDev pd;
     int P, dec, sym0, warp, design, design_pending;  // dec: index into kDecomp
     int* d_list = nullptr;          // 2*B compacted active lists (fused_tma design)
+    // long-mesh path (K6): levels of the recursive partition
+    bool longmesh = false;
+    std::vector<LevelDev> lv;
+    int top_R = 1;
+    double *d_lm = nullptr, *d_partial = nullptr;
     int p_grid = 0;                 // persistent grid of the fused_tma kernel (0: not configured yet)
     size_t p_smem = 0;
     std::vector<double> xmesh, xi, zeta;
@@ -193,7 +201,7 @@ int to_device(sb_problem* pb, const double* src_ref_dev, double* dst, int W, int
     const size_t n = (size_t)pb->pd.B * pb->pd.L * W;
     const int bs = 256;
     k_to_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src_ref_dev, dst, pb->pd.B, pb->pd.Nx, pb->pd.R,
-                                                                               pb->pd.T, W, identity_P);
+                                                                               pb->pd.T, pb->pd.L, W, identity_P);
     ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
@@ -203,7 +211,7 @@ int from_device(sb_problem* pb, const double* src, double* dst_ref_dev, int W) {
     const size_t n = (size_t)pb->pd.B * pb->pd.Nx * W;
     const int bs = 256;
     k_from_device_layout<<<(unsigned)((n + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(src, dst_ref_dev, pb->pd.B, pb->pd.Nx, pb->pd.R,
-                                                                                 pb->pd.T, W);
+                                                                                 pb->pd.T, pb->pd.L, W);
     ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
@@ -258,6 +266,85 @@ int pick_decomposition(int Nx, int P) {
         if (best < 0 || cost < best_cost) { best = d; best_cost = cost; }
     }
     return best;
+}
+
+// ---- long-mesh path (K6, sb_longmesh.cuh) -------------------------------------------------------
+constexpr int kLongLt = kLongR * kLongTT;
+constexpr int kLongTopRows = 16 * kLongTT;  // the top level is solved by one CTA of kLongTT threads, <= 16 rows each
+
+int longmesh_setup(sb_problem* pb) {
+    const int64_t B = pb->pd.B;
+    std::vector<LevelDev> lv;
+    size_t total = 0;  // doubles
+    int n = pb->pd.Nx;
+    for (int l = 0;; ++l) {
+        LevelDev L;
+        memset(&L, 0, sizeof L);
+        L.n = n;
+        L.ntiles = (n + kLongLt - 1) / kLongLt;
+        L.stride = (size_t)L.ntiles * kLongLt;
+        const bool top = (l > 0 && n <= kLongTopRows);
+        L.cstride = top ? 0 : (size_t)L.ntiles * kLongTT;
+        lv.push_back(L);
+        if (l > 0) total += 4 * L.stride * B;      // a, c, d, x
+        total += 10 * L.cstride * B;               // chunk summaries
+        if (top) break;
+        n = (int)L.cstride;
+        if (l > 12) return fail(SB_ERR_UNSUPPORTED, "long-mesh recursion too deep");
+    }
+    CU(cudaMalloc((void**)&pb->d_lm, total * sizeof(double)));
+    CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));   // padding rows of every level stay (0, 1, 0 | 0)
+    double* p = pb->d_lm;
+    for (size_t l = 0; l < lv.size(); ++l) {
+        if (l > 0) { lv[l].a = p; p += lv[l].stride * B; lv[l].c = p; p += lv[l].stride * B; lv[l].d = p; p += lv[l].stride * B;
+                     lv[l].x = p; p += lv[l].stride * B; }
+        if (lv[l].cstride) { lv[l].chunk = p; p += 10 * lv[l].cstride * B; }
+    }
+    CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * pb->pd.ntiles * sizeof(double)));
+    pb->lv = lv;
+    const int ntop = lv.back().n;
+    pb->top_R = 1;
+    while (pb->top_R * kLongTT < ntop) pb->top_R *= 2;
+    return SB_OK;
+}
+
+template <int RT>
+void launch_top(sb_problem* pb, const LevelDev& top) {
+    const size_t smem = (size_t)(2 * 3 + 1) * kLongTT * sizeof(double);
+    k6_top<RT, kLongTT><<<(unsigned)pb->pd.B, kLongTT, smem, pb->ctx->stream>>>(top, pb->d_active);
+}
+
+// one Newton iteration of the long-mesh path; publishes the active count like the batched kernels
+int longmesh_iteration(sb_problem* pb, double tol, int slot) {
+    cudaStream_t st = pb->ctx->stream;
+    const unsigned B = (unsigned)pb->pd.B;
+    std::vector<LevelDev>& lv = pb->lv;
+    const int top = (int)lv.size() - 1;
+    pb->fe->long_chunk[pb->sym0]<<<dim3(lv[0].ntiles, B), kLongTT, 0, st>>>(pb->pd, pb->t_next, pb->inv_tau, lv[0]);
+    ++g_launches;
+    for (int l = 0; l < top; ++l) {
+        if (l > 0) { k6_chunk_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], pb->d_active); ++g_launches; }
+        k6_form<kLongR, kLongTT><<<dim3((unsigned)((lv[l].cstride + 255) / 256), B), 256, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
+        ++g_launches;
+    }
+    switch (pb->top_R) {
+        case 1: launch_top<1>(pb, lv[top]); break;
+        case 2: launch_top<2>(pb, lv[top]); break;
+        case 4: launch_top<4>(pb, lv[top]); break;
+        case 8: launch_top<8>(pb, lv[top]); break;
+        default: launch_top<16>(pb, lv[top]); break;
+    }
+    ++g_launches;
+    for (int l = top - 1; l >= 1; --l) {
+        k6_back_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
+        ++g_launches;
+    }
+    pb->fe->long_back[pb->sym0]<<<dim3(lv[0].ntiles, B), kLongTT, 0, st>>>(pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial);
+    k6_commit<0><<<dim3((unsigned)((pb->pd.L + 255) / 256), B), 256, 0, st>>>(pb->pd, pb->d_active);
+    k6_finalize<0><<<1, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
+    g_launches += 3;
+    CU(cudaGetLastError());
+    return SB_OK;
 }
 
 }  // namespace
@@ -364,17 +451,26 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     sb_problem* pb = new sb_problem;
     pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
     pb->dec = pick_decomposition(Nx, pb->P);
+    if (getenv("SB_FORCE_LONGMESH") && pb->P == 1) pb->dec = -1;   // testing: long-mesh path on short meshes
+    int R, T, ntiles = 1;
     if (pb->dec < 0) {
-        delete pb;
-        return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) of this build", Nx,
-                    kMaxBlockT * (fe->npde == 1 ? 16 : 8));
+        if (pb->P != 1) {
+            delete pb;
+            return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) for npde = %d; the long-mesh "
+                        "path handles scalar PDEs only", Nx, kMaxBlockT * 8, fe->npde);
+        }
+        pb->longmesh = true;
+        R = kLongR; T = kLongTT;
+        ntiles = (Nx + R * T - 1) / (R * T);
+        for (int d = 0; d < kNumDecomp; ++d) if (kDecomp[d].R == R && kDecomp[d].TT == T) pb->dec = d;
+    } else {
+        R = kDecomp[pb->dec].R; T = kDecomp[pb->dec].TT;
     }
-    const int R = kDecomp[pb->dec].R, T = kDecomp[pb->dec].TT;
     pb->warp = (T == 32);
     pb->sym0 = (m == 0);
     ProbDev& pd = pb->pd;
     memset(&pd, 0, sizeof pd);
-    pd.Nx = Nx; pd.R = R; pd.T = T; pd.L = R * T; pd.m = m; pd.nprm = fe->nparams; pd.nprm_s = (fe->nparams + 1) / 2 * 2; pd.iter_no = 0; pd.B = B;
+    pd.Nx = Nx; pd.R = R; pd.T = T; pd.Lt = R * T; pd.ntiles = ntiles; pd.L = ntiles * R * T; pd.m = m; pd.nprm = fe->nparams; pd.nprm_s = (fe->nparams + 1) / 2 * 2; pd.iter_no = 0; pd.B = B;
     pd.singular = (m >= 1) && (xmesh[0] == 0);  // src/utils.jl:616
     pb->xmesh.assign(xmesh, xmesh + Nx);
 
@@ -403,7 +499,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     double *h_xi = &mesh[0], *h_awbw = &mesh[L], *h_gwwf = &mesh[3 * L], *h_frac = &mesh[5 * L], *h_gw = &mesh[7 * L],
            *h_ivol = &mesh[8 * L];
     for (int i = 0; i < Nx; ++i) {
-        const size_t s = (size_t)(i % R) * T + i / R;
+        const size_t s = (size_t)(i / (R * T)) * (R * T) + (size_t)((i % (R * T)) % R) * T + (i % (R * T)) / R;
         double fR = 0.0, fL = 0.0;
         if (i < NI) {
             const double xl = xmesh[i], xr = xmesh[i + 1], q = pb->xi[i];
@@ -480,6 +576,10 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.list[0] = pb->d_list; pd.list[1] = pb->d_list + B;
     pd.done_count = pb->d_count + kSlots; pd.host_count = d_hcount;
     pb->last_active = B;
+    if (pb->longmesh) {
+        int rc2 = longmesh_setup(pb);
+        if (rc2 != SB_OK) { sb_problem_destroy(pb); return rc2; }
+    }
     *out = pb;
     return SB_OK;
 }
@@ -490,7 +590,7 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
     cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
-    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list);
+    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list); cudaFree(pb->d_lm); cudaFree(pb->d_partial);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     delete pb;
@@ -597,8 +697,12 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     }
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    AssembleKernel kern = pb->fe->assemble_val[pb->dec][pb->sym0];
-    kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
+    if (pb->longmesh) {
+        pb->fe->long_assemble_val[pb->sym0]<<<dim3(pd.ntiles, (unsigned)pd.B), kLongTT, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
+    } else {
+        AssembleKernel kern = pb->fe->assemble_val[pb->dec][pb->sym0];
+        kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
+    }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     int rc = SB_OK;
@@ -705,7 +809,10 @@ int sb_residual_jacobian(sb_problem* pb) {
     launch_geometry(pb, grid, block, smem);
     const int ps = (int)(pb->launched % kSlots);
     if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
-    pb->fe->assemble_jac[pb->dec][pb->sym0]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+    if (pb->longmesh)
+        pb->fe->long_assemble_jac[pb->sym0]<<<dim3(pb->pd.ntiles, (unsigned)pb->pd.B), kLongTT, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+    else
+        pb->fe->assemble_jac[pb->dec][pb->sym0]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
     ++g_launches;
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evM[ps], pb->ctx->stream));
@@ -715,6 +822,8 @@ int sb_residual_jacobian(sb_problem* pb) {
 int sb_solve_update_norm(sb_problem* pb, double tol) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     if (!pb->d_J) return fail(SB_ERR_INVALID, "sb_solve_update_norm called before sb_residual_jacobian");
+    if (pb->longmesh)
+        return fail(SB_ERR_UNSUPPORTED, "the long-mesh path solves from on-the-fly assembly only: use sb_newton_iteration");
     CU(cudaSetDevice(pb->ctx->device));
     int slot;
     int rc = prepare_slot(pb, &slot);
@@ -730,6 +839,17 @@ int sb_solve_update_norm(sb_problem* pb, double tol) {
 
 int sb_newton_iteration(sb_problem* pb, double tol) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
+    if (pb->longmesh) {
+        CU(cudaSetDevice(pb->ctx->device));
+        int slot;
+        int rc = prepare_slot(pb, &slot);
+        if (rc) return rc;
+        if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
+        rc = longmesh_iteration(pb, tol, slot);
+        if (rc) return rc;
+        if (pb->prof) { CU(cudaEventRecord(pb->evM[slot], pb->ctx->stream)); CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream)); }
+        return finish_slot(pb, slot);
+    }
     if (pb->design == SB_DESIGN_SPLIT) {
         int rc = sb_residual_jacobian(pb);
         if (rc) return rc;
@@ -954,6 +1074,7 @@ int sb_debug_download_system(sb_problem* pb, double* F, double* Jl, double* Jd, 
 
 int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const double* Ju, const double* F, double* x) {
     if (!pb || !Jl || !Jd || !Ju || !F || !x) return fail(SB_ERR_INVALID, "NULL argument");
+    if (pb->longmesh) return fail(SB_ERR_UNSUPPORTED, "sb_debug_solve is not available on the long-mesh path");
     CU(cudaSetDevice(pb->ctx->device));
     int rc = ensure_jacobian(pb);
     if (rc) return rc;

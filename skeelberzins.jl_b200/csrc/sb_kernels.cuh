@@ -42,7 +42,8 @@ template <bool GLOB> SB_D double ldw(const double* p, int i) { if constexpr (GLO
 template <bool GLOB> SB_D double2 ldw(const double2* p, int i) { if constexpr (GLOB) return __ldg(p + i); else return p[i]; }
 
 struct ProbDev {
-    int Nx, R, T, L;       // L = R*T padded nodes
+    int Nx, R, T, L;       // L = padded nodes per instance = ntiles * R*T (ntiles = 1 on the batched path)
+    int Lt, ntiles;        // tile length R*T and number of tiles of an instance (long-mesh path: ntiles > 1)
     int m, singular, nprm;
     int nprm_s;            // stride of the per-instance parameter block (even, so every block is 16-byte aligned)
     int iter_no;           // Newton iteration number inside the current step (same for every active instance)
@@ -166,12 +167,9 @@ struct ChunkThomas {
     // shared memory needed by finish<TT>() in doubles
     template <int TT> static constexpr int smem_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
 
-    // solve; x[r] = unknowns of the thread's rows.  t = thread index inside the system.
-    template <int TT>
-    SB_D void finish(Vec<P> (&x)[R], double* sm, int t) {
-        // representation of the first row: x_first = y0 - v0*x_prevsep - w0*x_sep
-        // and of the last interior row:     x_last  = yL - vL*x_prevsep - wL*x_sep
-        Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
+    // representation of the chunk's first row: x_first = y0 - v0*x_prevsep - w0*x_sep
+    // and of its last interior row:             x_last  = yL - vL*x_prevsep - wL*x_sep
+    SB_D void summary(Vec<P>& y0, Mat<P>& v0, Mat<P>& w0, Vec<P>& yL, Mat<P>& vL, Mat<P>& wL) const {
         if constexpr (R == 1) {
             y0 = vec_zero<P>(); v0 = mat_zero<P>(); w0 = neg(mat_identity<P>());
             yL = vec_zero<P>(); vL = neg(mat_identity<P>()); wL = mat_zero<P>();
@@ -185,6 +183,31 @@ struct ChunkThomas {
                 w0 = neg(mul(ct[r], w0));
             }
         }
+    }
+    // reduced row of the chunk's separator, normalised to unit diagonal, given the first-row representation
+    // (v0n, w0n, y0n) of the next chunk
+    static SB_D void reduced_row(const Mat<P>& As_, const Mat<P>& Bs_, const Mat<P>& Cs_, const Vec<P>& ds_, const Vec<P>& yL,
+                                 const Mat<P>& vL, const Mat<P>& wL, const Mat<P>& v0n, const Mat<P>& w0n, const Vec<P>& y0n,
+                                 Mat<P>& an, Mat<P>& cn, Vec<P>& dn) {
+        const Mat<P> ar = neg(mul(As_, vL));
+        const Mat<P> br = sub_mul(sub_mul(Bs_, As_, wL), Cs_, v0n);
+        const Mat<P> cr = neg(mul(Cs_, w0n));
+        const Vec<P> dr = sub_mul(sub_mul(ds_, As_, yL), Cs_, y0n);
+        const Mat<P> binv = inverse_fast(br);
+        an = mul(binv, ar); cn = mul(binv, cr); dn = mul(binv, dr);
+    }
+    // unknowns of the chunk's rows from its own (xs) and the previous (xp) separator unknowns
+    SB_D void back(Vec<P> (&x)[R], const Vec<P>& xp, const Vec<P>& xs) const {
+        x[R - 1] = xs;
+#pragma unroll
+        for (int r = R - 2; r >= 0; --r) x[r] = sub_mul(sub_mul(dt[r], vt[r], xp), ct[r], x[r + 1]);
+    }
+
+    // solve; x[r] = unknowns of the thread's rows.  t = thread index inside the system.
+    template <int TT>
+    SB_D void finish(Vec<P> (&x)[R], double* sm, int t) {
+        Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
+        summary(y0, v0, w0, yL, vL, wL);
         // (v0, w0, y0) of thread t+1
         double mine[NW], nb[NW];
         pack(mine, v0, w0, y0);
@@ -203,14 +226,8 @@ struct ChunkThomas {
         }
         Mat<P> v0n, w0n; Vec<P> y0n;
         unpack(nb, v0n, w0n, y0n);
-        // reduced row of this thread's separator, normalised to unit diagonal
-        const Mat<P> ar = neg(mul(As, vL));
-        const Mat<P> br = sub_mul(sub_mul(Bs, As, wL), Cs, v0n);
-        const Mat<P> cr = neg(mul(Cs, w0n));
-        const Vec<P> dr = sub_mul(sub_mul(ds, As, yL), Cs, y0n);
-        const Mat<P> binv = inverse_fast(br);
-        Mat<P> an = mul(binv, ar), cn = mul(binv, cr);
-        Vec<P> dn = mul(binv, dr);
+        Mat<P> an, cn; Vec<P> dn;
+        reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
 
         Vec<P> xs, xp;  // this thread's and the previous thread's separator unknowns
         if constexpr (TT == 32) {
@@ -274,9 +291,7 @@ struct ChunkThomas {
                 xp.a[i] = (t > 0) ? xsm[i * TT + t - 1] : 0.0;
             }
         }
-        x[R - 1] = xs;
-#pragma unroll
-        for (int r = R - 2; r >= 0; --r) x[r] = sub_mul(sub_mul(dt[r], vt[r], xp), ct[r], x[r + 1]);
+        back(x, xp, xs);
     }
 };
 
@@ -341,18 +356,16 @@ struct RowOut { Mat<P> A, Bm, C; Vec<P> d; };
 // side = 1: node Nx-1 with I = interval Nx-2.  ui/bi: u and b at the boundary node.
 // JAC: out = (Jl, Jd, Ju, F); !JAC: out.d = du.
 template <class Fn, bool JAC, int ND, bool GFRAC = true>
-SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* ub, const double* mass, int side, double tt,
-                       double inv_tau, const double* prm, const IntervalRes<Fn::npde, ND>& I, const double* ui,
-                       const double* bi, int slot, RowOut<Fn::npde>& out) {
+SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* u0p, const double* uNp, const double* mass,
+                       int side, double tt, double inv_tau, const double* prm, const IntervalRes<Fn::npde, ND>& I,
+                       const double* ui, const double* bi, int slot, RowOut<Fn::npde>& out) {
     constexpr int P = Fn::npde;
     constexpr int PO = JAC ? P : 0;
-    const int R = pd.R, T = pd.T, Nx = pd.Nx;
-    const int s0 = 0, sN = ((Nx - 1) % R) * T + (Nx - 1) / R;
     Dual<PO> ul_[P], ur_[P], pl[P], pr[P];
     double ql[P], qr[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        ul_[p] = Dual<PO>(ub[(size_t)s0 * P + p]); ur_[p] = Dual<PO>(ub[(size_t)sN * P + p]);
+        ul_[p] = Dual<PO>(u0p[p]); ur_[p] = Dual<PO>(uNp[p]);
         if constexpr (JAC) { ul_[p].d[p] = 1.0; ur_[p].d[p] = 1.0; }
     }
     Fn::template bc<Dual<PO>>(pd.x0, ul_, pd.xN, ur_, tt, prm, pl, ql, pr, qr);  // src/assembler.jl:26/29
@@ -464,12 +477,17 @@ template <class Fn, int R, int TT, bool SYM0, bool JAC, bool GLOB = true, class 
 // shared memory); mass: its 3*P mass flags; prm: its functor parameters.
 SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* ub, const double* bb, const double* mass,
                          int t, double tt, double inv_tau, const double* prm, const double (&uc)[R][Fn::npde],
-                         const double (&bc)[R][Fn::npde], Sink& sink) {
+                         const double (&bc)[R][Fn::npde], Sink& sink, int i_base = 0, const double* u0p = nullptr,
+                         const double* uNp = nullptr) {
+    // Long meshes are stored as tiles of R*TT nodes: i_base = global index of the tile's first node, ub/bb/mesh
+    // point at the tile, the neighbouring tiles are adjacent in memory (slot -1 and slot R*TT), and u0p/uNp point
+    // at the first / last mesh node of the instance.  Batched path: one tile, i_base = 0.
     constexpr int P = Fn::npde;
     constexpr int ND = JAC ? 2 * P : 0;
     constexpr int PO = JAC ? P : 0;
     const int Nx = pd.Nx;
-    const int i0 = t * R;
+    const int i0 = i_base + t * R;
+    if (!u0p) { u0p = ub; uNp = ub + (size_t)(((Nx - 1) % R) * TT + (Nx - 1) / R) * P; }
     double mI[P];  // interior mass flags * inv_tau
 #pragma unroll
     for (int p = 0; p < P; ++p) mI[p] = inv_tau * mass[P + p];
@@ -480,25 +498,26 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
     rowN.A = mat_zero<P>(); rowN.Bm = mat_identity<P>(); rowN.C = mat_zero<P>(); rowN.d = vec_zero<P>();
     if (Nx - 1 >= i0 && Nx - 1 < i0 + R) {
         const int rN = Nx - 1 - i0;
-        const int sN = rN * TT + t, sM = ((Nx - 2) % R) * TT + (Nx - 2) / R;
+        const int sN = rN * TT + t;
+        const int sM = (rN >= 1) ? (rN - 1) * TT + t : ((t > 0) ? (R - 1) * TT + t - 1 : -1);
         double uM[P], uN[P], bN[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            uM[p] = ub[(size_t)sM * P + p]; uN[p] = ub[(size_t)sN * P + p];
+            uM[p] = ub[(ptrdiff_t)sM * P + p]; uN[p] = ub[(size_t)sN * P + p];
             bN[p] = JAC ? bb[(size_t)sN * P + p] : 0.0;
         }
         IntervalRes<P, ND> IN;
         eval_interval<Fn, ND, SYM0, GLOB>(mesh, sM, uM, uN, tt, prm, IN);
-        boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, ub, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
+        boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
     }
 
     double un[P];  // first node of the next chunk
     IntervalRes<P, ND> Lr, Rr;
     if (i0 >= 1 && i0 - 1 <= Nx - 2) {
         double ul[P];
-        const int slot = (R - 1) * TT + t - 1;
+        const int slot = (t > 0) ? (R - 1) * TT + t - 1 : -1;  // t == 0: last node of the previous tile
 #pragma unroll
-        for (int p = 0; p < P; ++p) ul[p] = ub[(size_t)slot * P + p];
+        for (int p = 0; p < P; ++p) ul[p] = ub[(ptrdiff_t)slot * P + p];
         eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, ul, uc[0], tt, prm, Lr);
     } else {
 #pragma unroll
@@ -507,7 +526,8 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
     }
     Rr = Lr;
 #pragma unroll
-    for (int p = 0; p < P; ++p) un[p] = (t + 1 < TT) ? ub[(size_t)(t + 1) * P + p] : 0.0;
+    for (int p = 0; p < P; ++p)  // t == TT-1: first node of the next tile (if the mesh goes on)
+        un[p] = (t + 1 < TT) ? ub[(size_t)(t + 1) * P + p] : ((i0 + R <= Nx - 1) ? ub[(size_t)R * TT * P + p] : 0.0);
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -560,11 +580,11 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
                 row.d.a[j] = du;
             }
         }
-        if (r == 0 && i0 == 0) {  // left boundary node: only thread 0, only this unrolled copy
+        if (r == 0 && i0 == 0) {  // left boundary node: only thread 0 (of tile 0), only this unrolled copy
             double b0[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) b0[p] = JAC ? bc[0][p] : 0.0;
-            boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, ub, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
+            boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
         }
         if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
             if (i == Nx - 1) row = rowN;
@@ -957,7 +977,8 @@ __global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary
     const double* ub = pd.u + (size_t)k * pd.L * P;
     const double* prm = pd.prm + (size_t)k * pd.nprm_s;
     const int R = pd.R, T = pd.T, Nx = pd.Nx;
-    auto slot_of = [&](int i) { return (i % R) * T + i / R; };
+    const int Lt = pd.Lt;
+    auto slot_of = [&](int i) { const int tile = i / Lt, il = i - tile * Lt; return tile * Lt + (il % R) * T + il / R; };
     double u0[P], u1[P], uN[P];
     for (int p = 0; p < P; ++p) {
         u0[p] = ub[(size_t)slot_of(0) * P + p];
@@ -985,8 +1006,9 @@ __global__ void k_begin_step(ProbDev pd) {
     if (idx >= total) return;
     const int64_t k = idx / pd.L;
     const int s = (int)(idx - (size_t)k * pd.L);
-    const int r = s / pd.T, t = s - r * pd.T;
-    const int i = t * pd.R + r;
+    const int tile = s / pd.Lt, sl = s - tile * pd.Lt;
+    const int r = sl / pd.T, t = sl - r * pd.T;
+    const int i = tile * pd.Lt + t * pd.R + r;
     if (s == 0) { pd.active[k] = 1; pd.iters[k] = 0; }
     const double* mass = pd.mass + (size_t)k * 4 * P;
     const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);

@@ -4,7 +4,7 @@
 #pragma once
 #include <utility>
 
-#include "sb_kernels.cuh"
+#include "sb_longmesh.cuh"
 
 namespace sb {
 
@@ -25,6 +25,8 @@ typedef void (*FusedKernel)(ProbDev, double, double, double, int);
 typedef void (*FusedPKernel)(ProbDev, double, double, double, int, int, int);
 typedef void (*SolveKernel)(ProbDev, double, int, int);
 typedef void (*MassKernel)(ProbDev, double, double*, int);
+typedef void (*LongChunkKernel)(ProbDev, double, double, LevelDev);
+typedef void (*LongBackKernel)(ProbDev, double, double, LevelDev, double*);
 
 struct FunctorEntry {
     const char* name;
@@ -35,6 +37,10 @@ struct FunctorEntry {
     FusedPKernel fused_p[kNumDecomp][2];      // persistent TMA-prefetch variant
     size_t fused_p_smem[kNumDecomp][2];       // its dynamic shared memory (bytes)
     MassKernel mass;
+    // long-mesh path (scalar PDEs): [SYM0]
+    LongChunkKernel long_chunk[2];
+    LongBackKernel long_back[2];
+    AssembleKernel long_assemble_jac[2], long_assemble_val[2];
 };
 
 template <class Fn, int D>
@@ -68,6 +74,16 @@ FunctorEntry make_entry(const char* name) {
     e.name = name; e.npde = Fn::npde; e.nparams = Fn::nparams;
     fill_all<Fn>(e, std::make_integer_sequence<int, kNumDecomp>{});
     e.mass = k_mass_flags<Fn>;
+    if constexpr (Fn::npde == 1) {
+        e.long_chunk[0] = k6_chunk_asm<Fn, kLongR, kLongTT, false>; e.long_chunk[1] = k6_chunk_asm<Fn, kLongR, kLongTT, true>;
+        e.long_back[0] = k6_back_asm<Fn, kLongR, kLongTT, false>; e.long_back[1] = k6_back_asm<Fn, kLongR, kLongTT, true>;
+        e.long_assemble_jac[0] = k6_assemble<Fn, kLongR, kLongTT, false, true>;
+        e.long_assemble_jac[1] = k6_assemble<Fn, kLongR, kLongTT, true, true>;
+        e.long_assemble_val[0] = k6_assemble<Fn, kLongR, kLongTT, false, false>;
+        e.long_assemble_val[1] = k6_assemble<Fn, kLongR, kLongTT, true, false>;
+    } else {
+        for (int s = 0; s < 2; ++s) { e.long_chunk[s] = nullptr; e.long_back[s] = nullptr; e.long_assemble_jac[s] = nullptr; e.long_assemble_val[s] = nullptr; }
+    }
     return e;
 }
 

@@ -242,3 +242,80 @@ def test_frozen_instances_and_c_loop(ctx, oracle):
     fk = sb.Functor(c.functor, c.params[k:k + 1])
     s = sb.pdepe(c.m, fk, c.icfun, fk, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, squeeze=False, save="last")
     assert np.array_equal(s.u[-1][0], a.u[-1][k])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K6: long-mesh path (recursive partition over tiles; sb_longmesh.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Nx", [21, 2049, 5000, 70001])
+def test_longmesh_stationary_vs_oracle(ctx, oracle, monkeypatch, Nx):
+    """Example105 (stationary nonlinear diffusion) through the long-mesh kernels at sizes that exercise one, two and
+    three levels of the recursion (forced onto the long path also where a single CTA would do)."""
+    monkeypatch.setenv("SB_FORCE_LONGMESH", "1")
+    c = ex.example105(Nx)
+    fn = sb.Functor(c.functor, c.params)
+    u, hist = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, ctx=ctx, hist=True)
+    r = oracle.pdepe_stationary(c.functor, c.m, c.xmesh, c.params, c.initial(), hist=True)
+    assert len(hist) == r["iters"][0] == 7
+    assert _relerr(u, r["u"][0, :, 0]) < RTOL
+    x = c.xmesh
+    assert np.abs(u - np.sqrt(0.01 + x * (1 - x) / 2)).max() < 1e-12
+
+
+@pytest.mark.parametrize("cfg,Nx,nsteps", [("2", 6000, 3), ("3a", 5000, 4), ("3b", 4500, 4)])
+def test_longmesh_transient_vs_oracle(ctx, oracle, monkeypatch, cfg, Nx, nsteps):
+    """Transient steps (m = 0, 1, 2; Neumann and time-dependent Dirichlet data) on meshes beyond the single-CTA range,
+    three instances with different parameters and iteration counts."""
+    c = ex.baseline_case(cfg, B=3, Nx=Nx)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:nsteps + 1]
+    fn = sb.Functor(c.functor, c.params)
+    sol, hist, dev = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, hist=True, squeeze=False,
+                              save="last", return_device=True)
+    assert dev.layout()["T"] == 256 and dev.info()["Nx"] == Nx
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None)
+    err = np.abs(sol.u[-1] - r["u"][:, :, 0]).max(axis=1) / np.abs(r["u"][:, :, 0]).max(axis=1)
+    assert err.max() < RTOL
+    its = np.array([[len(h[k]) for h in hist] for k in range(c.B)])
+    assert np.array_equal(its, r["iters"])
+
+
+def test_longmesh_assemble_entrywise(ctx, oracle):
+    """assemble! and the Jacobian rows of a long mesh (tiles with neighbours in other tiles) against the oracle."""
+    rng = np.random.default_rng(7)
+    Nx, B = 9000, 2
+    for fid, m in ((ex.GENERIC_SCALAR, 0), (ex.GENERIC_SCALAR, 2), (ex.NONLIN_DIFF, 0)):
+        x = _mesh(m, m > 0, Nx, rng)
+        prm = _rand_params(fid, B, rng)
+        u = 0.5 + rng.random((B, Nx, 1))
+        dev = sb.DeviceProblem(ctx, m, x, sb.Functor(fid, prm), design="split")
+        assert _relerr(dev.assemble(u, 0.3), oracle.assemble(fid, m, x, prm, u, 0.3)) < 1e-12
+        dev.upload(u)
+        dev.mass_flags(0.1)
+        M = oracle.mass(fid, m, x, prm, u, 0.1)
+        assert np.array_equal(dev.mass(), M)
+        dev.begin_step(0.3, 100.0)
+        dev.residual_jacobian()
+        F, Jl, Jd, Ju = dev.debug_system()
+        b = M * u
+        Fo, Jlo, Jdo, Juo = oracle.residual_jacobian(fid, m, x, prm, b, b, 1e-2, M, 0.3)
+        scale = np.abs(Jdo).max()
+        assert np.abs(F - Fo).max() <= 1e-12 * max(np.abs(Fo).max(), 1.0)
+        for A, Ao in ((Jl, Jlo), (Jd, Jdo), (Ju, Juo)):
+            assert np.abs(A - Ao).max() <= 1e-12 * scale
+        dev.close()
+
+
+def test_cfg5_full_size_stationary(ctx, oracle):
+    """BASELINE config 5: Example105 on 2^22 mesh points, one instance.  Newton iteration count identical to the
+    oracle (7), solution within 1e-10 relative of the oracle and of the exact solution sqrt(0.01 + x(1-x)/2)."""
+    c = ex.baseline_case("5")
+    assert c.xmesh.size == 2 ** 22
+    fn = sb.Functor(c.functor, c.params)
+    u, hist = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, ctx=ctx, hist=True)
+    r = oracle.pdepe_stationary(c.functor, c.m, c.xmesh, c.params, c.initial(), hist=True)
+    assert r["iters"][0] == 7
+    assert len(hist) == 7
+    assert _relerr(u, r["u"][0, :, 0]) < RTOL
+    x = c.xmesh
+    assert np.abs(u - np.sqrt(0.01 + x * (1 - x) / 2)).max() < 1e-10
