@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="2", help="BASELINE config: 2 (default), 3a, 3b, 4")
+    ap.add_argument("--config", default="2", help="BASELINE config: 2 (default), 3a, 3b, 4, 5")
     ap.add_argument("--design", default=os.environ.get("SB_DESIGN", "fused_tma"), choices=["fused", "fused_tma", "split"])
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's B)")
     ap.add_argument("--nx", type=int, default=0)
@@ -66,6 +66,8 @@ def make_case(args, world):
 
 def time_grid_of(case, args):
     import skeelberzins_jl_b200 as sb
+    if case.tspan is None:          # stationary problem: one Newton solve with tau = Inf at t = 1 (src/pdepe.jl:180)
+        return np.array([1.0, 1.0]), np.inf
     tg, tau = sb.time_grid(case.tspan, case.tstep)
     if args.time_steps:
         tg = tg[:args.time_steps + 1]
@@ -150,7 +152,10 @@ def cpu_baseline(args, case_full, Nx, tg, tau, sample, nthreads=0):
     u0 = np.asarray(case_full.icfun(case_full.xmesh), dtype=np.float64).reshape(1, Nx, case_full.npde)
     u0 = np.broadcast_to(u0, (idx.size, Nx, case_full.npde))
     t0 = time.perf_counter()
-    r = sb_oracle.pdepe_transient(case_full.functor, case_full.m, case_full.xmesh, prm, u0, tg, tau, nthreads=nthreads)
+    if case_full.tspan is None:
+        r = sb_oracle.pdepe_stationary(case_full.functor, case_full.m, case_full.xmesh, prm, u0, nthreads=nthreads)
+    else:
+        r = sb_oracle.pdepe_transient(case_full.functor, case_full.m, case_full.xmesh, prm, u0, tg, tau, nthreads=nthreads)
     dt = time.perf_counter() - t0
     units = float(r["iters"].sum()) * Nx
     return units / dt, dt, int(idx.size), sb_oracle.num_threads(), r
@@ -228,12 +233,14 @@ def run_ours(args):
     tol, maxit = 1e-10, 100
     nsteps = tg.size - 1
 
+    stationary = case.tspan is None
+
     def solve_resident():
         dev.rollback()
-        dev.mass_flags(tg[0])
+        dev.mass_flags(tg[0], stationary=stationary)
         for i in range(nsteps):
             tau_i = tau if tau is not None else tg[i + 1] - tg[i]
-            dev.begin_step(tg[i + 1], 1.0 / tau_i)
+            dev.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
             if args.python_loop:
                 sb.api._newton_loop(dev, tol, maxit)
             else:
@@ -275,6 +282,9 @@ def run_ours(args):
 
     def solve_e2e():
         f2 = sb.Functor(case.functor, prm)
+        if stationary:
+            return sb.pdepe(case.m, f2, u0, f2, case.xmesh, ctx=ctx, design=args.design, squeeze=False,
+                            c_loop=not args.python_loop)
         sol = sb.pdepe(case.m, f2, u0, f2, case.xmesh, tspan_arg, ctx=ctx, design=args.design, tstep=tstep_arg,
                        save="last", squeeze=False, c_loop=not args.python_loop)
         return sol.u[-1]
@@ -295,11 +305,11 @@ def run_ours(args):
 
     # ---- roofline: profiled solve, CUDA events around every Newton-iteration launch -------------------
     dev.rollback()
-    dev.mass_flags(tg[0])
+    dev.mass_flags(tg[0], stationary=stationary)
     dev.profile_begin()
     for i in range(nsteps):
         tau_i = tau if tau is not None else tg[i + 1] - tg[i]
-        dev.begin_step(tg[i + 1], 1.0 / tau_i)
+        dev.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
         dev.newton_solve(tol, maxit)
     prof = dev.profile_end()
     bpu = algorithmic_bytes_per_unit(args.design, P)

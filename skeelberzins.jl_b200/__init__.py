@@ -6,7 +6,7 @@ library ``libskeelberzins_b200.so`` (include/skeelberzins_b200.h).  All compute 
 hand-written sm_100a CUDA kernels; there is no CPU fallback -- importing the host logic works
 anywhere, but every solve raises if the CUDA library or a GPU is missing.
 """
-from . import examples, timegrid  # noqa: F401
+from . import examples, sharding, timegrid  # noqa: F401
 from .api import (ConvergenceFailed, Context, DeviceProblem, DiffEqArray, Functor, Params,  # noqa: F401
                   ProblemDefinition, SBError, SkeelBerzinsDiscretization, assemble_, default_context,
                   functor_info, kernel_launches, mass_matrix, newton, newton_stat, pdepe, pinned_empty, problem_init)
