@@ -1,0 +1,217 @@
+# SkeelBerzinsB200.jl -- Julia host shim over libskeelberzins_b200.so (C ABI: include/skeelberzins_b200.h).
+#
+# Drop-in for the internal implicit-Euler / stationary-Newton path of SkeelBerzins.jl, batched over B independent
+# PDE instances.  The Julia side owns the time loop (reference src/pdepe.jl:90-108) and the Newton loop
+# (src/utils.jl:311-336) exactly as the reference does and calls one C entry point per Newton iteration; all the
+# arithmetic runs in hand-written sm_100a CUDA kernels.  No CUDA.jl, no CPU fallback.
+#
+# NOTE: `julia` is not installed in the build image, so this file has never been executed there; the Python host
+# (skeelberzins.jl_b200/api.py) drives the identical sequence of C calls and is what the tests and the bench run.
+#
+# pdefun / bdfun must be registry functors (device-compiled restatements of the example callbacks, see
+# `Functor`): Julia closures cannot run on the GPU.  icfun stays an ordinary Julia function evaluated on the host,
+# as in the reference (src/utils.jl:629-632).
+module SkeelBerzinsB200
+
+export pdepe, Params, ProblemDefinition, SkeelBerzinsDiscretization, Functor, assemble!, mass_matrix
+
+const libsb = get(ENV, "SKEELBERZINS_B200_LIB", "libskeelberzins_b200.so")
+
+# registry ids (enum sb_functor_id)
+const LIN_DIFF, NONLIN_DIFF, LIN_DIFF_CYL, POISSON, STAT_NONLIN, REACT_DIFF = 0, 1, 2, 3, 4, 5
+const LIN_DIFF_SPH, CONV_DIFF, LIN_REACT, GENERIC_SCALAR = 6, 7, 8, 9
+const DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA = 0, 1, 2
+
+struct SBError <: Exception
+    code::Cint
+    msg::String
+end
+
+last_error() = unsafe_string(ccall((:sb_last_error, libsb), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : throw(SBError(rc, last_error()))
+
+"""Registry coefficient functor (pdefun + bdfun) with per-instance parameters, `params[nparams, B]`."""
+struct Functor
+    id::Int
+    params::Matrix{Float64}     # column k = parameters of instance k  (C side: instance-major, contiguous)
+end
+Functor(id::Integer, p::AbstractVector) = Functor(Int(id), reshape(collect(Float64, p), :, 1))
+batch(f::Functor) = size(f.params, 2)
+
+function functor_info(id::Integer)
+    npde = Ref{Cint}(0); nprm = Ref{Cint}(0); name = Ref{Cstring}(C_NULL)
+    check(ccall((:sb_functor_info, libsb), Cint, (Cint, Ref{Cint}, Ref{Cint}, Ref{Cstring}), id, npde, nprm, name))
+    Int(npde[]), Int(nprm[]), unsafe_string(name[])
+end
+
+"""Same fields as SkeelBerzins.Params (src/utils.jl:191-238)."""
+Base.@kwdef struct Params
+    solver::Symbol = :euler
+    tstep::Union{Float64, Vector{Float64}} = 1e-2
+    hist::Bool = false
+    sparsity::Symbol = :sparseArrays      # accepted; the Jacobian lives on the device in block-tridiagonal form
+    linsolve::Any = nothing               # accepted; the GPU solver is fixed (partitioned block-Thomas)
+    maxit::Int = 100
+    tol::Float64 = 1e-10
+    data::Bool = false
+    nb_design_var::Int = 0
+end
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    device::Int
+    function Context(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:sb_ctx_create, libsb), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, r))
+        c = new(r[], device)
+        finalizer(x -> ccall((:sb_ctx_destroy, libsb), Cint, (Ptr{Cvoid},), x.h), c)
+        c
+    end
+end
+
+"""Problem record, same field names as SkeelBerzins.ProblemDefinition (src/utils.jl:113-182); `handle` is the
+sb_problem*; the Jacobian (`jac` in the reference) is device scratch rewritten every Newton iteration."""
+mutable struct ProblemDefinition
+    npde::Int
+    Nx::Int
+    xmesh::Vector{Float64}
+    tspan::Tuple{Float64, Float64}
+    singular::Bool
+    m::Int
+    nb_design_var::Int
+    inival::Matrix{Float64}      # [npde*Nx, B], component fastest (src/utils.jl:632)
+    ξ::Vector{Float64}
+    ζ::Vector{Float64}
+    pdefunction::Functor
+    icfunction::Any
+    bdfunction::Functor
+    ctx::Context
+    handle::Ptr{Cvoid}
+end
+const SkeelBerzinsDiscretization = ProblemDefinition
+Base.length(pb::ProblemDefinition) = pb.nb_design_var          # src/utils.jl:665
+
+function problem_init(m, xmesh, tspan, pdefun::Functor, icfun, bdfun, params; ctx = Context(0), design = DESIGN_FUSED_TMA)
+    x = collect(Float64, xmesh)
+    Nx = length(x); B = batch(pdefun)
+    npde, nprm, _ = functor_info(pdefun.id)
+    size(pdefun.params, 1) == nprm || error("functor takes $nprm parameters per instance")
+    params.sparsity in (:sparseArrays, :banded) ||
+        throw("Error: Invalid sparsity pattern selected. Please choose from the available options: :sparseArrays, :banded")
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sb_problem_create, libsb), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
+                ctx.h, m, Nx, B, x, pdefun.id, pdefun.params, nprm, h))
+    check(ccall((:sb_problem_set_design, libsb), Cint, (Ptr{Cvoid}, Cint), h[], design))
+    u0 = npde == 1 ? icfun.(x) : vec(reduce(hcat, icfun.(x)))   # src/utils.jl:632
+    inival = repeat(reshape(collect(Float64, u0), :, 1), 1, B)
+    ξ = zeros(Nx - 1); ζ = zeros(Nx - 1)
+    check(ccall((:sb_problem_quadrature, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], ξ, ζ))
+    sing = Ref{Cint}(0)
+    check(ccall((:sb_problem_info, libsb), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Int64}, Ref{Cint}),
+                h[], C_NULL, C_NULL, C_NULL, sing))
+    pb = ProblemDefinition(npde, Nx, x, (Float64(tspan[1]), Float64(tspan[2])), sing[] != 0, m, params.nb_design_var,
+                           inival, ξ, ζ, pdefun, icfun, pdefun, ctx, h[])
+    finalizer(p -> ccall((:sb_problem_destroy, libsb), Cint, (Ptr{Cvoid},), p.handle), pb)
+    Nx, npde, inival, pb
+end
+
+upload!(pb, u::AbstractArray{Float64}) = check(ccall((:sb_state_upload, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}), pb.handle, u))
+function download(pb)
+    u = Matrix{Float64}(undef, pb.npde * pb.Nx, batch(pb.pdefunction))
+    check(ccall((:sb_state_download, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}), pb.handle, u))
+    u
+end
+
+"""mass_matrix(pb) (src/assembler.jl:138-174): diagonal per instance and the DAE flag."""
+function mass_matrix(pb::ProblemDefinition)
+    upload!(pb, pb.inival)
+    check(ccall((:sb_mass_flags, libsb), Cint, (Ptr{Cvoid}, Cdouble, Cint), pb.handle, pb.tspan[1], 0))
+    M = similar(pb.inival)
+    check(ccall((:sb_mass_download, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}), pb.handle, M))
+    M, any(==(0.0), M)
+end
+
+"""assemble!(du, u, pb, t) (src/assembler.jl:19-125), on `[npde*Nx, B]` arrays."""
+function assemble!(du, u, pb::ProblemDefinition, t)
+    check(ccall((:sb_assemble, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cdouble, Ptr{Float64}), pb.handle, u, t, du))
+    du
+end
+
+"""newton (src/utils.jl:303-337) on the device-resident state: b = M .* u_n (src/pdepe.jl:94), unP1 = copy(b),
+then the Newton loop, host-owned; `depth` iterations stay enqueued behind the one being waited for."""
+function newton(pb::ProblemDefinition, tau, timeStep; tol = 1.0e-10, maxit = 100, depth = 2)
+    check(ccall((:sb_begin_step, libsb), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), pb.handle, timeStep, isinf(tau) ? 0.0 : 1 / tau))
+    launched = 0; done = 0
+    nact = Ref{Int64}(0)
+    while true
+        while launched < maxit && launched - done < depth
+            check(ccall((:sb_newton_iteration, libsb), Cint, (Ptr{Cvoid}, Cdouble), pb.handle, tol))
+            launched += 1
+        end
+        check(ccall((:sb_wait_iteration, libsb), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), pb.handle, done, nact))
+        done += 1
+        nact[] == 0 && return launched
+        done >= maxit && throw("convergence failed")            # src/utils.jl:336
+    end
+end
+
+function history(pb, maxit)
+    B = batch(pb.pdefunction)
+    h = Matrix{Float64}(undef, maxit, B)
+    check(ccall((:sb_get_history, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), pb.handle, h, maxit))
+    it = Vector{Int32}(undef, B)
+    check(ccall((:sb_get_step_iters, libsb), Cint, (Ptr{Cvoid}, Ptr{Int32}), pb.handle, it))
+    [h[1:it[k], k] for k in 1:B]
+end
+
+_merge(params, kwargs) = Params(; (f => get(kwargs, f, getfield(params, f)) for f in fieldnames(Params))...)
+
+"""Transient pdepe (src/pdepe.jl:42-128) for the batch.  Returns `(u = Vector of [npde*Nx, B] states, t = grid)`
+and, as in the reference, `pb` / `storage` when `data` / `hist` are set."""
+function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params(), ctx = Context(0), kwargs...)
+    params = _merge(params, kwargs)
+    @assert m == 0 || m == 1 || m == 2 "Parameter m invalid"
+    @assert m == 0 || m > 0 && xmesh[1] ≥ 0 "Non-conforming mesh"
+    @assert params.tstep ≠ Inf "Adjust time step or try the alternative method for solving elliptic problems"
+    Nx, npde, inival, pb = problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params; ctx = ctx)
+    params.solver == :DiffEq && return pb
+    params.hist && check(ccall((:sb_enable_history, libsb), Cint, (Ptr{Cvoid}, Cint), pb.handle, params.maxit))
+    flag_tstep = params.tstep isa Real
+    timeSteps, tstep = flag_tstep ? (collect(tspan[1]:(params.tstep):tspan[2]), params.tstep) :
+                                    (params.tstep, diff(params.tstep))          # src/pdepe.jl:82-85
+    upload!(pb, inival)
+    check(ccall((:sb_mass_flags, libsb), Cint, (Ptr{Cvoid}, Cdouble, Cint), pb.handle, timeSteps[1], 0))
+    results = [copy(inival)]
+    storage = []
+    for i in eachindex(timeSteps[1:(end - 1)])                                     # src/pdepe.jl:90
+        newton(pb, flag_tstep ? tstep : tstep[i], timeSteps[i + 1]; tol = params.tol, maxit = params.maxit)
+        params.hist && push!(storage, history(pb, params.maxit))
+        push!(results, download(pb))
+    end
+    sol = (u = results, t = timeSteps)
+    params.hist && params.data && return sol, pb, storage
+    params.hist && return sol, storage
+    params.data && return sol, pb
+    sol
+end
+
+"""Stationary pdepe (src/pdepe.jl:156-192): one Newton solve with tau = Inf at t = 1."""
+function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh; params = Params(; tstep = Inf), ctx = Context(0), kwargs...)
+    params = _merge(params, merge(Dict{Symbol, Any}(:tstep => Inf), Dict{Symbol, Any}(kwargs)))
+    @assert params.solver == :euler "Elliptic problems can only be solved using the Euler method"
+    @assert params.tstep == Inf "Time step should be set to Inf to obtain the stationary solution"
+    Nx, npde, inival, pb = problem_init(m, xmesh, (0, 1), pdefun, icfun, bdfun, params; ctx = ctx)
+    params.hist && check(ccall((:sb_enable_history, libsb), Cint, (Ptr{Cvoid}, Cint), pb.handle, params.maxit))
+    upload!(pb, inival)
+    check(ccall((:sb_mass_flags, libsb), Cint, (Ptr{Cvoid}, Cdouble, Cint), pb.handle, 1.0, 1))
+    newton(pb, Inf, 1.0; tol = params.tol, maxit = params.maxit)                   # src/pdepe.jl:180
+    u = download(pb)
+    hist = params.hist ? history(pb, params.maxit) : nothing
+    params.hist && params.data && return u, pb, hist
+    params.hist && return u, hist
+    params.data && return u, pb
+    u
+end
+
+end # module
