@@ -142,9 +142,18 @@ def hbm_peak():
         return 6650.0, "fallback"
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(args, case_full, Nx, tg, tau, sample, nthreads=0):
-    """CPU oracle (port of the reference algorithm) on a bounded sample of the same sweep."""
+    """CPU oracle (port of the reference algorithm) on a bounded sample of the same sweep, on all host threads
+    (set explicitly: torchrun exports OMP_NUM_THREADS=1)."""
     from oracle import sb_oracle
+    nthreads = nthreads or host_threads()
     from skeelberzins_jl_b200 import examples as ex
     B = case_full.B
     idx = np.unique(np.linspace(0, B - 1, min(sample, B)).astype(np.int64))
@@ -158,7 +167,7 @@ def cpu_baseline(args, case_full, Nx, tg, tau, sample, nthreads=0):
         r = sb_oracle.pdepe_transient(case_full.functor, case_full.m, case_full.xmesh, prm, u0, tg, tau, nthreads=nthreads)
     dt = time.perf_counter() - t0
     units = float(r["iters"].sum()) * Nx
-    return units / dt, dt, int(idx.size), sb_oracle.num_threads(), r
+    return units / dt, dt, int(idx.size), nthreads, r
 
 
 def run_reference(args):
@@ -183,7 +192,7 @@ def run_reference(args):
         if time.perf_counter() - t_start > 150:
             break
     value = float(np.mean(vals))
-    cores = sb_oracle.num_threads()
+    cores = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
