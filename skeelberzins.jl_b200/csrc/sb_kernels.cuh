@@ -533,7 +533,9 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
     for (int r = 0; r < R; ++r) {
         const int i = i0 + r;
         const int slot = r * TT + t;
-        if (i <= Nx - 2) eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr);
+        // evaluated for every row: for i > Nx-2 the slot is padding (zeros) and the result is never used
+        eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr);
+        const double wR = SYM0 ? 1.0 : Rr.wf, wL = SYM0 ? 1.0 : Lr.wf;  // m == 0: unit flux weights, folded away
 
         // interior node, src/assembler.jl:60-95 (computed for every row; boundary / padding rows are replaced below)
         double frR = 0.0, frL = 0.0;
@@ -543,7 +545,7 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
         RowOut<P> row;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-            double num = Rr.wf * Rr.f[j].v - Lr.wf * Lr.f[j].v;
+            double num = wR * Rr.f[j].v - wL * Lr.f[j].v;
             if constexpr (!Fn::s_zero) num += frR * Rr.s[j].v + frL * Lr.s[j].v;
             bool hc = true;
             double id;
@@ -557,9 +559,9 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
                 row.d.a[j] = (mI[j] * uc[r][j] - du) - inv_tau * bc[r][j];  // src/utils.jl:251-256, :314
 #pragma unroll
                 for (int q = 0; q < P; ++q) {
-                    double nm = -(Lr.wf * Lr.f[j].d[q]);
-                    double nc = Rr.wf * Rr.f[j].d[q] - Lr.wf * Lr.f[j].d[PO + q];
-                    double np = Rr.wf * Rr.f[j].d[PO + q];
+                    double nm = -(wL * Lr.f[j].d[q]);
+                    double nc = wR * Rr.f[j].d[q] - wL * Lr.f[j].d[PO + q];
+                    double np = wR * Rr.f[j].d[PO + q];
                     if constexpr (!Fn::s_zero) {
                         nm += frL * Lr.s[j].d[q];
                         nc += frR * Rr.s[j].d[q] + frL * Lr.s[j].d[PO + q];
