@@ -47,6 +47,7 @@ template <int N> inline Dual<N> operator*(const Dual<N>& a, double b) { Dual<N> 
 template <int N> inline Dual<N> operator*(double a, const Dual<N>& b) { return b * a; }
 template <int N> inline Dual<N> operator/(const Dual<N>& a, double b) { Dual<N> r; r.v = a.v / b; for (int k = 0; k < N; ++k) r.d[k] = a.d[k] / b; return r; }
 template <int N> inline Dual<N> operator/(double a, const Dual<N>& b) { return Dual<N>(a) / b; }
+template <int N> inline Dual<N> exp(const Dual<N>& a) { Dual<N> r; r.v = std::exp(a.v); for (int k = 0; k < N; ++k) r.d[k] = a.d[k] * r.v; return r; }
 inline double value(double x) { return x; }
 template <int N> inline double value(const Dual<N>& x) { return x.v; }
 
@@ -56,15 +57,17 @@ template <int N> inline double value(const Dual<N>& x) { return x.v; }
 // --------------------------------------------------------------------------------------------
 enum {
     LIN_DIFF = 0, NONLIN_DIFF = 1, LIN_DIFF_CYL = 2, POISSON = 3, STAT_NONLIN = 4, REACT_DIFF = 5,
-    LIN_DIFF_SPH = 6, CONV_DIFF = 7, LIN_REACT = 8, GENERIC_SCALAR = 9, NUM_FUNCTORS = 10
+    LIN_DIFF_SPH = 6, CONV_DIFF = 7, LIN_REACT = 8, GENERIC_SCALAR = 9,
+    EXP_DIFF = 10,  // not in the product registry: checker for run-time compiled user functors (tests/test_gpu_plugin.py)
+    NUM_FUNCTORS = 11
 };
-static const int k_npde[NUM_FUNCTORS] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 1};
-static const int k_nprm[NUM_FUNCTORS] = {1, 1, 3, 3, 3, 3, 1, 3, 2, 19};
+static const int k_npde[NUM_FUNCTORS] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1};
+static const int k_nprm[NUM_FUNCTORS] = {1, 1, 3, 3, 3, 3, 1, 3, 2, 19, 3};
 
 // pdefun(x,t,u,dudx) -> (c,f,s)     docs/src/solvers.md:9-24
 template <class T>
 static void pdefun(int id, const double* p, double x, double t, const T* u, const T* ux, T* c, T* f, T* s) {
-    (void)x; (void)t;
+    (void)t;
     switch (id) {
     case LIN_DIFF:      // examples/Example101_LinearDiffusion.jl:21-27
     case LIN_DIFF_CYL:  // examples/Example103_LinearDiffusionCylindrical.jl:35-41
@@ -89,6 +92,8 @@ static void pdefun(int id, const double* p, double x, double t, const T* u, cons
         c[0] = p[0] + p[1] * u[0];
         f[0] = (p[2] + p[3] * u[0]) * ux[0];
         s[0] = p[4] + p[5] * u[0] + p[6] * ux[0]; break;
+    case EXP_DIFF:      // c = 1, f = p0*exp(u)*ux, s = -p1*u^2 + x
+        c[0] = T(1.0); f[0] = p[0] * exp(u[0]) * ux[0]; s[0] = -(p[1] * u[0] * u[0]) + x; break;
     }
 }
 
@@ -120,6 +125,8 @@ static void bdfun(int id, const double* p, double xl, const T* ul, double xr, co
     case GENERIC_SCALAR:
         pl[0] = p[7] * ul[0] - (p[8] + p[9] * t + p[10] * std::exp(-p[11] * t)); ql[0] = T(p[12]);
         pr[0] = p[13] * ur[0] - (p[14] + p[15] * t + p[16] * std::exp(-p[17] * t)); qr[0] = T(p[18]); break;
+    case EXP_DIFF:      // left Dirichlet u = p2*(1+t), right homogeneous Neumann
+        pl[0] = ul[0] - p[2] * (1.0 + t); ql[0] = T(0.0); pr[0] = T(0.0); qr[0] = T(1.0); break;
     }
 }
 

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libskeelberzins_b200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH", os.path.join(HERE, "libskeelberzins_b200.so"))  # SB_LIB_PATH: tuning builds
 
 SB_OK = 0
 SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_UNSUPPORTED, SB_ERR_CONVERGENCE, SB_ERR_PLUGIN = -1, -2, -3, -4, -5

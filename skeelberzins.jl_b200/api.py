@@ -83,6 +83,27 @@ def kernel_launches():
     return n.value
 
 
+def register_user_functor(cuda_source, struct_name, npde, nparams):
+    """Plugin slot (sb_register_user_functor): CUDA C++ source of a functor struct
+
+        struct <struct_name> {
+            static constexpr int npde = ..., nparams = ...;
+            static constexpr bool c_unit = ..., s_zero = ...;    // c == 1 identically / s == 0 identically
+            template <class S> static __device__ void pde(double x, double t, const S* u, const S* ux,
+                                                          const double* prm, S* c, S* f, S* s);
+            template <class S> static __device__ void bc(double xl, const S* ul, double xr, const S* ur, double t,
+                                                         const double* prm, S* pl, double* ql, S* pr, double* qr);
+        };
+
+    i.e. the reference's pdefun / bdfun written generically in the scalar type S (double or dual number).  The
+    kernels are compiled with NVRTC for sm_100a when a problem that uses the functor is created.  Returns the
+    functor id to pass to ``Functor``."""
+    fid = ctypes.c_int()
+    _lib.check(_lib.load().sb_register_user_functor(None, cuda_source.encode(), struct_name.encode(), int(npde),
+                                                    int(nparams), ctypes.byref(fid)))
+    return fid.value
+
+
 class _PinnedPool:
     """Page-locked host buffers for results.  A buffer goes back to the pool when the numpy array that wraps
     it (and every view of it) has been garbage-collected, so repeated solves re-use the same pinned pages."""

@@ -12,11 +12,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libskeelberzins_b200.so")
+# tuning builds: SB_EXTRA_NVCC_FLAGS="-DSB_TMA_STAGES=2" SB_LIB_SUFFIX=_s2 python build.py  -> libskeelberzins_b200_s2.so
+_SUFFIX = os.environ.get("SB_LIB_SUFFIX", "")
+OBJ = os.path.join(HERE, "build" + _SUFFIX)
+LIB = os.path.join(HERE, "libskeelberzins_b200%s.so" % _SUFFIX)
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
+NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH + os.environ.get("SB_EXTRA_NVCC_FLAGS", "").split()
 
 FUNCTORS = [
     ("FnLinDiff", "entry_lin_diff", "LIN_DIFF"),
@@ -80,7 +82,8 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1))) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):
             logs.append(out)
-    link = [nvcc, "-shared", "-o", LIB] + ARCH + [j[0] for j in jobs] + ["-lcudart"]
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    link = [nvcc, "-shared", "-o", LIB] + ARCH + [j[0] for j in jobs] + ["-lcudart", "-lnvrtc", "-ldl", "-Xlinker", "-rpath=" + cuda_lib]
     logs.append(_run(link))
     with open(stamp, "w") as f:
         f.write(digest)

@@ -5,6 +5,8 @@
 // interpolation weights (src/utils.jl:18-48), choice of the thread decomposition (R rows per thread,
 // T threads per system), device allocation, layout transforms, the Newton software pipeline.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
 
 #include <algorithm>
 #include <cmath>
@@ -45,6 +47,32 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
 
 long long g_launches = 0;  // kernels launched by this library (all contexts; not thread-safe by design)
+
+// Kernel handles of one problem: host function pointers of the statically compiled registry kernels, or
+// cudaKernel_t handles of kernels compiled at run time (NVRTC) for a user functor.  Both launch through
+// cudaLaunchKernel.
+struct KernelSet {
+    const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr;
+    const void *long_chunk = nullptr, *long_back = nullptr, *long_assemble_jac = nullptr, *long_assemble_val = nullptr;
+    size_t fused_p_smem = 0;
+    cudaLibrary_t lib = nullptr;  // owner of the run-time compiled kernels (user functors)
+};
+
+template <class... Args>
+cudaError_t launch_any(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    void* p[] = {(void*)&args...};
+    ++g_launches;
+    return cudaLaunchKernel(func, grid, block, p, smem, st);
+}
+
+struct UserFunctor {
+    std::string source, name;
+    int npde, nparams;
+};
+std::vector<UserFunctor>& user_functors() {
+    static std::vector<UserFunctor> v;
+    return v;
+}
 
 // reference layout [B][Nx][W] <-> device layout [B][tile][R][T][W]   (W doubles per node, tiles of Lt = R*T nodes,
 // L = ntiles*Lt padded nodes per instance).  identity != 0: padding nodes receive the W = P*P identity block (Jd)
@@ -130,7 +158,9 @@ struct sb_ctx {
 
 struct sb_problem {
     sb_ctx* ctx;
-    const FunctorEntry* fe;
+    const FunctorEntry* fe;  // registry entry (nullptr for user functors)
+    KernelSet ks;
+    int nparams = 0;
     ProbDev pd;
     int P, dec, sym0, warp, design, design_pending;  // dec: index into kDecomp
     int* d_list = nullptr;          // 2*B compacted active lists (fused_tma design)
@@ -268,6 +298,95 @@ int pick_decomposition(int Nx, int P) {
     return best;
 }
 
+// ---- user functor plugin (NVRTC) ------------------------------------------------------------------
+#ifndef SB_TMA_STAGES
+#define SB_TMA_STAGES 1
+#endif
+#ifndef SB_PERSISTENT_WARPS_PER_SM
+#define SB_PERSISTENT_WARPS_PER_SM 20
+#endif
+
+std::string csrc_dir() {
+    if (const char* e = getenv("SB_CSRC_DIR")) return e;
+    Dl_info info;
+    if (dladdr((const void*)&sb_version, &info) && info.dli_fname) {
+        std::string so = info.dli_fname;
+        const size_t slash = so.find_last_of('/');
+        return (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/csrc";
+    }
+    return "csrc";
+}
+
+// Compile the kernels this problem needs (its decomposition, its coordinate symmetry) for a user functor and load them.
+int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
+    const int R = pb->pd.R, TT = pb->pd.T;
+    const char* sym = pb->sym0 ? "true" : "false";
+    char buf[256];
+    std::string src = "#include \"sb_longmesh.cuh\"\nusing namespace sb;\n" + uf.source + "\n";
+    snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_fused_p_smem = sb::FusedPLayout<%s, %d, %d, %s>::bytes;\n",
+             uf.name.c_str(), R, TT, sym);
+    src += buf;
+    snprintf(buf, sizeof buf, "static_assert(%s::npde == %d && %s::nparams == %d, \"npde/nparams differ from the registration\");\n",
+             uf.name.c_str(), uf.npde, uf.name.c_str(), uf.nparams);
+    src += buf;
+    std::vector<std::string> names;
+    auto name = [&](const char* fmt) { snprintf(buf, sizeof buf, fmt, uf.name.c_str(), R, TT, sym); names.push_back(buf); };
+    snprintf(buf, sizeof buf, "sb::k_mass_flags<%s>", uf.name.c_str()); names.push_back(buf);
+    name("sb::k_assemble<%s, %d, %d, %s, true>");
+    name("sb::k_assemble<%s, %d, %d, %s, false>");
+    name("sb::k_newton_fused<%s, %d, %d, %s>");
+    name("sb::k_newton_fused_p<%s, %d, %d, %s>");
+    if (pb->longmesh) {
+        name("sb::k6_chunk_asm<%s, %d, %d, %s>");
+        name("sb::k6_back_asm<%s, %d, %d, %s>");
+        name("sb::k6_assemble<%s, %d, %d, %s, true>");
+        name("sb::k6_assemble<%s, %d, %d, %s, false>");
+    }
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "sb_user_functor.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(SB_ERR_PLUGIN, "nvrtcCreateProgram failed");
+    for (const std::string& n : names) nvrtcAddNameExpression(prog, n.c_str());
+    const std::string inc = "-I" + csrc_dir();
+    char d1[64], d2[64];
+    snprintf(d1, sizeof d1, "-DSB_TMA_STAGES=%d", (int)SB_TMA_STAGES);
+    snprintf(d2, sizeof d2, "-DSB_PERSISTENT_WARPS_PER_SM=%d", (int)SB_PERSISTENT_WARPS_PER_SM);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), d1, d2};
+    const nvrtcResult r = nvrtcCompileProgram(prog, 6, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        nvrtcGetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        return fail(SB_ERR_PLUGIN, "NVRTC compilation of functor %s failed: %s\n%.700s", uf.name.c_str(), nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t cs = 0;
+    nvrtcGetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    KernelSet& ks = pb->ks;
+    cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { nvrtcDestroyProgram(&prog); return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e)); }
+    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p,
+                            &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
+    for (size_t i = 0; i < names.size(); ++i) {
+        const char* low = nullptr;
+        nvrtcGetLoweredName(prog, names[i].c_str(), &low);
+        cudaKernel_t kern;
+        e = cudaLibraryGetKernel(&kern, ks.lib, low);
+        if (e != cudaSuccess) { nvrtcDestroyProgram(&prog); return fail(SB_ERR_PLUGIN, "cudaLibraryGetKernel(%s): %s", names[i].c_str(), cudaGetErrorString(e)); }
+        *slots[i] = (const void*)kern;
+    }
+    nvrtcDestroyProgram(&prog);
+    void* dptr = nullptr; size_t bytes = 0;
+    e = cudaLibraryGetGlobal(&dptr, &bytes, ks.lib, "sb_user_fused_p_smem");
+    unsigned long long smem = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "reading the shared-memory size of the compiled kernel: %s", cudaGetErrorString(e));
+    ks.fused_p_smem = (size_t)smem;
+    return SB_OK;
+}
+
 // ---- long-mesh path (K6, sb_longmesh.cuh) -------------------------------------------------------
 constexpr int kLongLt = kLongR * kLongTT;
 constexpr int kLongTopRows = 16 * kLongTT;  // the top level is solved by one CTA of kLongTT threads, <= 16 rows each
@@ -320,8 +439,7 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
     const unsigned B = (unsigned)pb->pd.B;
     std::vector<LevelDev>& lv = pb->lv;
     const int top = (int)lv.size() - 1;
-    pb->fe->long_chunk[pb->sym0]<<<dim3(lv[0].ntiles, B), kLongTT, 0, st>>>(pb->pd, pb->t_next, pb->inv_tau, lv[0]);
-    ++g_launches;
+    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongTT), 0, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
     for (int l = 0; l < top; ++l) {
         if (l > 0) { k6_chunk_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], pb->d_active); ++g_launches; }
         k6_form<kLongR, kLongTT><<<dim3((unsigned)((lv[l].cstride + 255) / 256), B), 256, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
@@ -339,10 +457,10 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         k6_back_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
         ++g_launches;
     }
-    pb->fe->long_back[pb->sym0]<<<dim3(lv[0].ntiles, B), kLongTT, 0, st>>>(pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial);
+    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongTT), 0, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
     k6_commit<0><<<dim3((unsigned)((pb->pd.L + 255) / 256), B), 256, 0, st>>>(pb->pd, pb->d_active);
     k6_finalize<0><<<1, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
-    g_launches += 3;
+    g_launches += 2;
     CU(cudaGetLastError());
     return SB_OK;
 }
@@ -419,6 +537,13 @@ int sb_ctx_synchronize(sb_ctx* ctx) {
 }
 
 int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name) {
+    if (functor_id >= SB_USER_FUNCTOR_BASE && functor_id < SB_USER_FUNCTOR_BASE + (int)user_functors().size()) {
+        const UserFunctor& u = user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+        if (npde) *npde = u.npde;
+        if (nparams) *nparams = u.nparams;
+        if (name) *name = u.name.c_str();
+        return SB_OK;
+    }
     if (functor_id < 0 || functor_id >= SB_NUM_BUILTIN_FUNCTORS) return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
     const FunctorEntry& e = registry()[functor_id];
     if (npde) *npde = e.npde;
@@ -427,8 +552,17 @@ int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name) 
     return SB_OK;
 }
 
-int sb_register_user_functor(sb_ctx*, const char*, const char*, int, int, int*) {
-    return fail(SB_ERR_UNSUPPORTED, "user functor plugin slot (NVRTC) is not built in this version");
+int sb_register_user_functor(sb_ctx* ctx, const char* cuda_source, const char* struct_name, int npde, int nparams,
+                             int* functor_id) {
+    (void)ctx;
+    if (!cuda_source || !struct_name || !functor_id) return fail(SB_ERR_INVALID, "NULL argument");
+    if (npde < 1 || npde > SB_MAX_NPDE) return fail(SB_ERR_UNSUPPORTED, "npde = %d: kernels are compiled for npde <= %d", npde, SB_MAX_NPDE);
+    if (nparams < 1) return fail(SB_ERR_INVALID, "a functor needs at least one per-instance parameter");
+    UserFunctor uf;
+    uf.source = cuda_source; uf.name = struct_name; uf.npde = npde; uf.nparams = nparams;
+    user_functors().push_back(uf);
+    *functor_id = SB_USER_FUNCTOR_BASE + (int)user_functors().size() - 1;
+    return SB_OK;   // kernels are compiled when a problem is created (they depend on the mesh decomposition)
 }
 
 int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh, int functor_id, const double* params,
@@ -441,15 +575,26 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (B < 1) return fail(SB_ERR_INVALID, "B = %lld: need at least one instance", (long long)B);
     for (int i = 0; i + 1 < Nx; ++i)
         if (!(xmesh[i + 1] > xmesh[i])) return fail(SB_ERR_INVALID, "xmesh must be strictly increasing (at index %d)", i);
-    if (functor_id < 0 || functor_id >= SB_NUM_BUILTIN_FUNCTORS) return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
-    const FunctorEntry* fe = &registry()[functor_id];
-    if (nparams != fe->nparams)
-        return fail(SB_ERR_INVALID, "functor %s takes %d parameters per instance, got %d", fe->name, fe->nparams, nparams);
-    if (fe->nparams > 0 && !params) return fail(SB_ERR_INVALID, "params is NULL");
+    const FunctorEntry* fe = nullptr;
+    const UserFunctor* uf = nullptr;
+    int f_npde, f_nparams;
+    const char* f_name;
+    if (functor_id >= 0 && functor_id < SB_NUM_BUILTIN_FUNCTORS) {
+        fe = &registry()[functor_id];
+        f_npde = fe->npde; f_nparams = fe->nparams; f_name = fe->name;
+    } else if (functor_id >= SB_USER_FUNCTOR_BASE && functor_id < SB_USER_FUNCTOR_BASE + (int)user_functors().size()) {
+        uf = &user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+        f_npde = uf->npde; f_nparams = uf->nparams; f_name = uf->name.c_str();
+    } else {
+        return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
+    }
+    if (nparams != f_nparams)
+        return fail(SB_ERR_INVALID, "functor %s takes %d parameters per instance, got %d", f_name, f_nparams, nparams);
+    if (f_nparams > 0 && !params) return fail(SB_ERR_INVALID, "params is NULL");
     CU(cudaSetDevice(ctx->device));
 
     sb_problem* pb = new sb_problem;
-    pb->ctx = ctx; pb->fe = fe; pb->P = fe->npde; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
+    pb->ctx = ctx; pb->fe = fe; pb->P = f_npde; pb->nparams = f_nparams; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
     pb->dec = pick_decomposition(Nx, pb->P);
     if (getenv("SB_FORCE_LONGMESH") && pb->P == 1) pb->dec = -1;   // testing: long-mesh path on short meshes
     int R, T, ntiles = 1;
@@ -457,7 +602,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         if (pb->P != 1) {
             delete pb;
             return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) for npde = %d; the long-mesh "
-                        "path handles scalar PDEs only", Nx, kMaxBlockT * 8, fe->npde);
+                        "path handles scalar PDEs only", Nx, kMaxBlockT * 8, f_npde);
         }
         pb->longmesh = true;
         R = kLongR; T = kLongTT;
@@ -470,7 +615,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pb->sym0 = (m == 0);
     ProbDev& pd = pb->pd;
     memset(&pd, 0, sizeof pd);
-    pd.Nx = Nx; pd.R = R; pd.T = T; pd.Lt = R * T; pd.ntiles = ntiles; pd.L = ntiles * R * T; pd.m = m; pd.nprm = fe->nparams; pd.nprm_s = (fe->nparams + 1) / 2 * 2; pd.iter_no = 0; pd.B = B;
+    pd.Nx = Nx; pd.R = R; pd.T = T; pd.Lt = R * T; pd.ntiles = ntiles; pd.L = ntiles * R * T; pd.m = m; pd.nprm = f_nparams; pd.nprm_s = (f_nparams + 1) / 2 * 2; pd.iter_no = 0; pd.B = B;
     pd.singular = (m >= 1) && (xmesh[0] == 0);  // src/utils.jl:616
     pb->xmesh.assign(xmesh, xmesh + Nx);
 
@@ -522,7 +667,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     const size_t n = (size_t)B * L * pb->P;
 #define TRY(x) do { if (rc == SB_OK) rc = (x); } while (0)
     TRY(dev_alloc(&pb->d_mesh, 9 * L));
-    TRY(dev_alloc(&pb->d_prm, (size_t)B * pd.nprm_s));
+    TRY(dev_alloc(&pb->d_prm, (size_t)B * std::max(pd.nprm_s, 2)));
     TRY(dev_alloc(&pb->d_u, n));
     TRY(dev_alloc(&pb->d_b, n));
     TRY(dev_alloc(&pb->d_F, n));
@@ -544,9 +689,9 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     for (int i = 0; i < kSlots; ++i) pb->h_count[i] = 0;
     cudaStream_t st = ctx->stream;
     e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && fe->nparams > 0)
-        e = cudaMemcpy2DAsync(pb->d_prm, pd.nprm_s * sizeof(double), params, fe->nparams * sizeof(double),
-                              fe->nparams * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && f_nparams > 0)
+        e = cudaMemcpy2DAsync(pb->d_prm, pd.nprm_s * sizeof(double), params, f_nparams * sizeof(double),
+                              f_nparams * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_u, 0, n * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_b, 0, n * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_F, 0, n * sizeof(double), st);
@@ -576,6 +721,22 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.list[0] = pb->d_list; pd.list[1] = pb->d_list + B;
     pd.done_count = pb->d_count + kSlots; pd.host_count = d_hcount;
     pb->last_active = B;
+    if (fe) {
+        KernelSet& ks = pb->ks;
+        ks.mass = (const void*)fe->mass;
+        ks.assemble_jac = (const void*)fe->assemble_jac[pb->dec][pb->sym0];
+        ks.assemble_val = (const void*)fe->assemble_val[pb->dec][pb->sym0];
+        ks.fused = (const void*)fe->fused[pb->dec][pb->sym0];
+        ks.fused_p = (const void*)fe->fused_p[pb->dec][pb->sym0];
+        ks.fused_p_smem = fe->fused_p_smem[pb->dec][pb->sym0];
+        ks.long_chunk = (const void*)fe->long_chunk[pb->sym0];
+        ks.long_back = (const void*)fe->long_back[pb->sym0];
+        ks.long_assemble_jac = (const void*)fe->long_assemble_jac[pb->sym0];
+        ks.long_assemble_val = (const void*)fe->long_assemble_val[pb->sym0];
+    } else {
+        int rcu = compile_user_kernels(pb, *uf);
+        if (rcu != SB_OK) { sb_problem_destroy(pb); return rcu; }
+    }
     if (pb->longmesh) {
         int rc2 = longmesh_setup(pb);
         if (rc2 != SB_OK) { sb_problem_destroy(pb); return rc2; }
@@ -593,6 +754,7 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list); cudaFree(pb->d_lm); cudaFree(pb->d_partial);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
+    if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
     delete pb;
     return SB_OK;
 }
@@ -632,11 +794,11 @@ int sb_problem_set_design(sb_problem* pb, int design) {
 
 int sb_problem_set_params(sb_problem* pb, const double* params_host) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
-    if (pb->fe->nparams == 0) return SB_OK;
+    if (pb->nparams == 0) return SB_OK;
     if (!params_host) return fail(SB_ERR_INVALID, "params is NULL");
     CU(cudaSetDevice(pb->ctx->device));
-    CU(cudaMemcpy2DAsync(pb->d_prm, pb->pd.nprm_s * sizeof(double), params_host, pb->fe->nparams * sizeof(double),
-                         pb->fe->nparams * sizeof(double), (size_t)pb->pd.B, cudaMemcpyHostToDevice, pb->ctx->stream));
+    CU(cudaMemcpy2DAsync(pb->d_prm, pb->pd.nprm_s * sizeof(double), params_host, pb->nparams * sizeof(double),
+                         pb->nparams * sizeof(double), (size_t)pb->pd.B, cudaMemcpyHostToDevice, pb->ctx->stream));
     CU(cudaStreamSynchronize(pb->ctx->stream));
     return SB_OK;
 }
@@ -662,8 +824,7 @@ int sb_mass_flags(sb_problem* pb, double t0, int stationary) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
     const int bs = 128;
-    pb->fe->mass<<<(unsigned)((pb->pd.B + bs - 1) / bs), bs, 0, pb->ctx->stream>>>(pb->pd, t0, pb->d_mass, stationary);
-    ++g_launches;
+    CU(launch_any(pb->ks.mass, dim3((unsigned)((pb->pd.B + bs - 1) / bs)), dim3(bs), 0, pb->ctx->stream, pb->pd, t0, pb->d_mass, stationary));
     CU(cudaGetLastError());
     pb->mass_ready = true;
     return SB_OK;
@@ -697,14 +858,10 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     }
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    if (pb->longmesh) {
-        pb->fe->long_assemble_val[pb->sym0]<<<dim3(pd.ntiles, (unsigned)pd.B), kLongTT, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
-    } else {
-        AssembleKernel kern = pb->fe->assemble_val[pb->dec][pb->sym0];
-        kern<<<grid, block, 0, pb->ctx->stream>>>(pd, t, 0.0, 1);
-    }
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (pb->longmesh) e = launch_any(pb->ks.long_assemble_val, dim3(pd.ntiles, (unsigned)pd.B), dim3(kLongTT), 0, pb->ctx->stream, pd, t, 0.0, 1);
+    else e = launch_any(pb->ks.assemble_val, grid, block, 0, pb->ctx->stream, pd, t, 0.0, 1);
+    if (e == cudaSuccess) e = cudaGetLastError();
     int rc = SB_OK;
     if (e != cudaSuccess) rc = fail(SB_ERR_CUDA, "k_assemble launch: %s", cudaGetErrorString(e));
     if (rc == SB_OK) rc = download_nodes(pb, pb->d_F, du_host, pb->P);
@@ -810,10 +967,9 @@ int sb_residual_jacobian(sb_problem* pb) {
     const int ps = (int)(pb->launched % kSlots);
     if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
     if (pb->longmesh)
-        pb->fe->long_assemble_jac[pb->sym0]<<<dim3(pb->pd.ntiles, (unsigned)pb->pd.B), kLongTT, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
+        CU(launch_any(pb->ks.long_assemble_jac, dim3(pb->pd.ntiles, (unsigned)pb->pd.B), dim3(kLongTT), 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
     else
-        pb->fe->assemble_jac[pb->dec][pb->sym0]<<<grid, block, 0, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, 0);
-    ++g_launches;
+        CU(launch_any(pb->ks.assemble_jac, grid, block, 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evM[ps], pb->ctx->stream));
     return SB_OK;
@@ -862,12 +1018,12 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     if (pb->design == SB_DESIGN_FUSED_TMA) {
-        FusedPKernel kern = pb->fe->fused_p[pb->dec][pb->sym0];
+        const void* kern = pb->ks.fused_p;
         if (pb->p_grid == 0) {  // one-time configuration: opt in to the shared memory, size the persistent grid
-            pb->p_smem = pb->fe->fused_p_smem[pb->dec][pb->sym0];
-            CU(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->p_smem));
+            pb->p_smem = pb->ks.fused_p_smem;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->p_smem));
             int occ = 0, sms = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)kern, (int)block.x, pb->p_smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)block.x, pb->p_smem));
             CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pb->ctx->device));
             if (occ < 1) return fail(SB_ERR_UNSUPPORTED, "fused_tma kernel does not fit on an SM (%zu bytes of shared memory)", pb->p_smem);
             if (const char* e = getenv("SB_PERSISTENT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < occ) occ = v; }
@@ -876,15 +1032,13 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         const int prev_slot = (pb->launched == 0) ? -1 : (int)((pb->launched - 1) % kSlots);
         const int parity = (int)(pb->launched & 1);
         if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
-        kern<<<pb->p_grid, block, pb->p_smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity);
-        ++g_launches;
+        CU(launch_any(kern, dim3(pb->p_grid), block, pb->p_smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity));
         CU(cudaGetLastError());
         if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
         return finish_slot(pb, slot);
     }
     if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
-    pb->fe->fused[pb->dec][pb->sym0]<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, pb->t_next, pb->inv_tau, tol, slot);
-    ++g_launches;
+    CU(launch_any(pb->ks.fused, grid, block, smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot));
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
     return finish_slot(pb, slot);

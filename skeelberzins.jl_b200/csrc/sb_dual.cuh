@@ -5,7 +5,16 @@
 // seeds are the two end values of a mesh interval (2*npde partials), see sb_assemble.cuh.
 // Dual<0> degenerates to a plain double and is used by the residual-only kernel (assemble!).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#else  // NVRTC (user-functor plugin): no system headers
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+typedef long ptrdiff_t;
+#endif
 
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_D __device__ __forceinline__

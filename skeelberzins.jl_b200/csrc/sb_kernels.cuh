@@ -15,8 +15,6 @@
 //   k_newton_fused<Fn,R,TT,SYM0>  K3+K4+K7 in one kernel: J and F never leave the SM
 //   k_begin_step, k_mass_flags
 #pragma once
-#include <stdint.h>
-
 #include "sb_dual.cuh"
 #include "sb_functors.cuh"
 
@@ -165,7 +163,7 @@ struct ChunkThomas {
     }
 
     // shared memory needed by finish<TT>() in doubles
-    template <int TT> static constexpr int smem_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
+    template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
 
     // representation of the chunk's first row: x_first = y0 - v0*x_prevsep - w0*x_sep
     // and of its last interior row:             x_last  = yL - vL*x_prevsep - wL*x_sep
@@ -204,8 +202,15 @@ struct ChunkThomas {
     }
 
     // solve; x[r] = unknowns of the thread's rows.  t = thread index inside the system.
+    struct NoHook { SB_D void operator()() const {} };
+
     template <int TT>
-    SB_D void finish(Vec<P> (&x)[R], double* sm, int t) {
+    SB_D void finish(Vec<P> (&x)[R], double* sm, int t) { finish<TT>(x, sm, t, NoHook()); }
+
+    // hook(): called by every thread right after the first synchronisation point of the system's thread group
+    // (all threads have then finished reading their inputs), e.g. to start the prefetch of the next instance
+    template <int TT, class Hook>
+    SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
         summary(y0, v0, w0, yL, vL, wL);
         // (v0, w0, y0) of thread t+1
@@ -217,10 +222,12 @@ struct ChunkThomas {
                 const double v = __shfl_down_sync(0xffffffffu, mine[w], 1);
                 nb[w] = (t < 31) ? v : 0.0;
             }
+            hook();
         } else {
 #pragma unroll
             for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
             __syncthreads();
+            hook();
 #pragma unroll
             for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
         }
@@ -801,40 +808,48 @@ SB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+#ifndef SB_TMA_STAGES
+#define SB_TMA_STAGES 1   // 1: the next instance is prefetched into the same buffers as soon as every thread of the
+#endif                    //    group has consumed the current one (less smem -> more CTAs/SM); 2: double buffering
+#ifndef SB_PERSISTENT_WARPS_PER_SM
+#define SB_PERSISTENT_WARPS_PER_SM 20
+#endif
+
 template <class Fn, int R, int TT, bool SYM0>
 struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
-    static constexpr int P = Fn::npde, L = R * TT, G = (TT == 32) ? kWarpBlockThreads / 32 : 1;
+    static constexpr int P = Fn::npde, L = R * TT, G = (TT == 32) ? kWarpBlockThreads / 32 : 1, S = SB_TMA_STAGES;
     static constexpr int NPS = (Fn::nparams + 1) / 2 * 2;  // parameter block stride (even)
     static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
     static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
     static constexpr int oGw = 0, oAB = oGw + nGw, oIvol = oAB + nAB, oFrac = oIvol + nIvol, mesh_doubles = oFrac + nFrac;
     static constexpr int scratch = ChunkThomas<P, R>::template smem_doubles<TT>();
-    // per group: u[2][L*P], b[2][L*P], prm[2][NPS], mass[2][4P], scratch, partial sums [2][8], instance index [2]
-    static constexpr int oU = 0, oB = oU + 2 * L * P, oPrm = oB + 2 * L * P, oMass = oPrm + 2 * NPS, oScr = oMass + 8 * P,
+    // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], instance index [2]
+    static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
                          oSum = oScr + scratch, oK = oSum + 16, group_doubles = oK + 2;
-    static constexpr int bar_doubles = 2 * G + 2;  // one mbarrier (8 bytes) per stage and group + one for the mesh weights
+    static constexpr int bar_doubles = 2 * G + 2;  // mbarriers (8 bytes): S per group (2 reserved) + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
 
-#define SB_LAUNCH_BOUNDS_P(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), 512 / ((TT) == 32 ? kWarpBlockThreads : (TT)))
+#define SB_LAUNCH_BOUNDS_P(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), \
+    (32 * SB_PERSISTENT_WARPS_PER_SM) / ((TT) == 32 ? kWarpBlockThreads : (TT)) > 0 ? (32 * SB_PERSISTENT_WARPS_PER_SM) / ((TT) == 32 ? kWarpBlockThreads : (TT)) : 1)
 template <class Fn, int R, int TT, bool SYM0>
 __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
                                                           int prev_slot, int parity) {
     using LY = FusedPLayout<Fn, R, TT, SYM0>;
-    constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS;
+    constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS, S = LY::S;
     extern __shared__ __align__(16) double smp[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smp);
     double* mesh_sm = smp + LY::bar_doubles;
     const int g = (TT == 32) ? (threadIdx.x >> 5) : 0;
     const int t = (TT == 32) ? (threadIdx.x & 31) : threadIdx.x;
     double* grp = mesh_sm + LY::mesh_doubles + (size_t)g * LY::group_doubles;
-    double* ubuf = grp + LY::oU;      // [2][L*P]
-    double* bbuf = grp + LY::oB;      // [2][L*P]
-    double* pbuf = grp + LY::oPrm;    // [2][NPS]
-    double* mbuf = grp + LY::oMass;   // [2][4P]
+    double* ubuf = grp + LY::oU;      // [S][L*P]
+    double* bbuf = grp + LY::oB;      // [S][L*P]
+    double* pbuf = grp + LY::oPrm;    // [S][NPS]
+    double* mbuf = grp + LY::oMass;   // [S][4P]
     double* scratch = grp + LY::oScr;
     double* sums = grp + LY::oSum;    // [2][8]
-    long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index of each stage
+    long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index per stage / parity
     uint64_t* bar = bars + 2 * g;
 
     const int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
@@ -878,21 +893,22 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
 
     constexpr uint32_t kBytes = (uint32_t)(L * P * sizeof(double));
     constexpr uint32_t kPrmBytes = (uint32_t)(NPS * sizeof(double)), kMassBytes = (uint32_t)(4 * P * sizeof(double));
-    // thread t == 0 of the group is the producer: it knows the instance indices two stages ahead
+    // thread t == 0 of the group is the producer: it knows the instance indices two steps ahead
     long long k_next = -1, k_next2 = -1;
     if (t == 0) {
         if (j < n_in) k_next = list_in ? list_in[j] : j;
         if (j + stride < n_in) k_next2 = list_in ? list_in[j + stride] : j + stride;
     }
-    auto issue = [&](long long kk, int stage) {
-        kslot[stage] = kk;
+    // fetch instance kk into buffer `stage`; its index is published in kslot[seq & 1] (seq = position in this group's sequence)
+    auto issue = [&](long long kk, int stage, int seq) {
+        kslot[seq & 1] = kk;
         mbar_expect_tx(bar + stage, 2 * kBytes + kPrmBytes + kMassBytes);
         bulk_g2s(ubuf + (size_t)stage * L * P, pd.u + (size_t)kk * L * P, kBytes, bar + stage);
         bulk_g2s(bbuf + (size_t)stage * L * P, pd.b + (size_t)kk * L * P, kBytes, bar + stage);
         bulk_g2s(pbuf + stage * NPS, pd.prm + (size_t)kk * NPS, kPrmBytes, bar + stage);
         bulk_g2s(mbuf + stage * 4 * P, pd.mass + (size_t)kk * 4 * P, kMassBytes, bar + stage);
     };
-    if (t == 0 && k_next >= 0) issue(k_next, 0);
+    if (t == 0 && k_next >= 0) issue(k_next, 0, 0);
     if constexpr (TT == 32) __syncwarp();
     else __syncthreads();  // kslot[0] visible
     mbar_wait(mesh_bar, 0);
@@ -900,21 +916,25 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
     int pend_pos = -1, pend_k = 0;  // deferred list write of the previous instance (thread t == 0)
     int it = 0;
     for (; j < n_in; j += stride, ++it) {
-        const int stage = it & 1;
-        if (t == 0) {
-            // refill the other stage (released by the barrier inside the previous iteration's reduction)
-            if (k_next2 >= 0) issue(k_next2, stage ^ 1);
-            k_next = k_next2;
-            const int j3 = j + 2 * stride;
-            k_next2 = (j3 < n_in) ? (list_in ? (long long)list_in[j3] : (long long)j3) : -1;
-            if (pend_pos >= 0) { list_out[pend_pos] = pend_k; pend_pos = -1; }
-        }
+        const int stage = (S == 2) ? (it & 1) : 0;
+        // the producer refills: S == 2 -> the other stage, now (released by the previous iteration's reduction barrier);
+        //                       S == 1 -> the same buffers, as soon as the whole group has consumed them (hook below)
+        auto prefetch = [&]() {
+            if (t == 0) {
+                if (k_next2 >= 0) issue(k_next2, (S == 2) ? (stage ^ 1) : 0, it + 1);
+                k_next = k_next2;
+                const int j3 = j + 2 * stride;
+                k_next2 = (j3 < n_in) ? (list_in ? (long long)list_in[j3] : (long long)j3) : -1;
+            }
+        };
+        if constexpr (S == 2) prefetch();
+        if (t == 0 && pend_pos >= 0) { list_out[pend_pos] = pend_k; pend_pos = -1; }
         const double* us = ubuf + (size_t)stage * L * P;
         const double* bs = bbuf + (size_t)stage * L * P;
         const double* prm = pbuf + stage * NPS;
         const double* mass = mbuf + stage * 4 * P;
-        mbar_wait(bar + stage, (it >> 1) & 1);
-        const int64_t k = kslot[stage];
+        mbar_wait(bar + stage, (S == 2) ? ((it >> 1) & 1) : (it & 1));
+        const int64_t k = kslot[it & 1];
 
         double uc[R][P], bc[R][P];
 #pragma unroll
@@ -924,7 +944,12 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
         ChunkThomas<P, R> th;
         assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, us, bs, mass, t, tt, inv_tau, prm, uc, bc, th);
         Vec<P> h[R];
-        th.template finish<TT>(h, scratch, t);
+        if constexpr (S == 2) {
+            th.template finish<TT>(h, scratch, t);
+        } else {
+            if constexpr (TT == 32) __syncwarp();  // every lane is done with the staged inputs
+            th.template finish<TT>(h, scratch, t, prefetch);
+        }
 
         // update, ||h||^2 of the system; the barrier of this reduction also releases the stage and the scratch
         double* ug = pd.u + (size_t)k * L * P;
