@@ -185,6 +185,10 @@ struct sb_problem {
     long launched = 0, confirmed = 0;
     int64_t last_active = 0;
     bool mass_ready = false;
+    // begin_step fusion (fused_tma): b = M.*u_{n+1} is written by the converging iteration of the previous step
+    bool b_ready = false;        // b already holds M.*u for the next step
+    bool lazy_pending = false;   // the current step started without k_begin_step and no iteration has run yet
+    int step_design = -1;
     double* d_ckpt = nullptr;  // sb_state_checkpoint copy of u (device layout)
     // profiling (sb_profile_begin/end): timed events around every Newton-iteration launch
     bool prof = false, prof_ev_ok = false;
@@ -194,6 +198,11 @@ struct sb_problem {
     double prof_ms_assemble = 0.0, prof_ms_solve = 0.0;
     int64_t prof_launches = 0, prof_noop = 0, prof_inst_iters = 0;
 };
+
+extern "C" {
+static int materialize_begin(sb_problem* pb);
+static int run_begin_step_kernel(sb_problem* pb);
+}
 
 namespace {
 
@@ -806,6 +815,7 @@ int sb_problem_set_params(sb_problem* pb, const double* params_host) {
 int sb_state_upload(sb_problem* pb, const double* u_host) {
     if (!pb || !u_host) return fail(SB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(pb->ctx->device));
+    pb->b_ready = false; pb->lazy_pending = false; pb->pd.lazy_b = 0;
     int rc = upload_nodes(pb, u_host, pb->d_u, pb->P, 0);
     if (rc) return rc;
     CU(cudaMemsetAsync(pb->d_total, 0, pb->pd.B * sizeof(long long), pb->ctx->stream));
@@ -817,12 +827,15 @@ int sb_state_upload(sb_problem* pb, const double* u_host) {
 int sb_state_download(sb_problem* pb, double* u_host) {
     if (!pb || !u_host) return fail(SB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(pb->ctx->device));
+    { int rc = materialize_begin(pb); if (rc) return rc; }
     return download_nodes(pb, pb->d_u, u_host, pb->P);
 }
 
 int sb_mass_flags(sb_problem* pb, double t0, int stationary) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
+    pb->b_ready = false;
+    { int rc = materialize_begin(pb); if (rc) return rc; }
     const int bs = 128;
     CU(launch_any(pb->ks.mass, dim3((unsigned)((pb->pd.B + bs - 1) / bs)), dim3(bs), 0, pb->ctx->stream, pb->pd, t0, pb->d_mass, stationary));
     CU(cudaGetLastError());
@@ -848,6 +861,7 @@ int sb_mass_download(sb_problem* pb, double* mass_host) {
 int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host) {
     if (!pb || !du_host) return fail(SB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(pb->ctx->device));
+    if (!u_host) { int rc0 = materialize_begin(pb); if (rc0) return rc0; }
     ProbDev pd = pb->pd;
     double* d_uin = nullptr;
     if (u_host) {
@@ -867,6 +881,26 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     if (rc == SB_OK) rc = download_nodes(pb, pb->d_F, du_host, pb->P);
     if (d_uin) cudaFree(d_uin);
     return rc;
+}
+
+static int run_begin_step_kernel(sb_problem* pb) {
+    const size_t total = (size_t)pb->pd.B * pb->pd.L;
+    const int bs = 256;
+    cudaStream_t st = pb->ctx->stream;
+    if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    else k_begin_step<2><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SB_OK;
+}
+
+// a step that started lazily (no k_begin_step) is about to be observed or continued by something other than the
+// fused_tma kernel: run the kernel now (u still holds the true u_n, so the result is the same)
+static int materialize_begin(sb_problem* pb) {
+    if (!pb->lazy_pending) return SB_OK;
+    pb->lazy_pending = false;
+    pb->pd.lazy_b = 0;
+    return run_begin_step_kernel(pb);
 }
 
 // profiling: fold the timed events of iterations [prof_harvested, launched) of the current step into the totals
@@ -903,12 +937,17 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     pb->design = pb->design_pending;
     cudaStream_t st = pb->ctx->stream;
     CU(cudaMemsetAsync(pb->d_count, 0, 2 * kSlots * sizeof(unsigned int), st));
-    const size_t total = (size_t)pb->pd.B * pb->pd.L;
-    const int bs = 256;
-    if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
-    else k_begin_step<2><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
-    ++g_launches;
-    CU(cudaGetLastError());
+    const bool lazy = pb->b_ready && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh && !getenv("SB_NO_LAZY_BEGIN");
+    pb->b_ready = false;
+    pb->lazy_pending = false;
+    pb->pd.lazy_b = 0;
+    if (lazy) {
+        pb->lazy_pending = true;   // the first fused_tma iteration takes b as the iterate and resets the per-step flags
+        pb->pd.lazy_b = 1;
+    } else {
+        int rc = run_begin_step_kernel(pb);
+        if (rc) return rc;
+    }
     pb->launched = 0; pb->confirmed = 0; pb->last_active = pb->pd.B;
     return SB_OK;
 }
@@ -931,6 +970,7 @@ static int wait_slot(sb_problem* pb, int s, unsigned int* value) {
         }
     }
     *value = v;
+    if (v == 0 && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh) pb->b_ready = true;  // every instance wrote its next b
     return SB_OK;
 }
 
@@ -962,6 +1002,7 @@ int sb_residual_jacobian(sb_problem* pb) {
     CU(cudaSetDevice(pb->ctx->device));
     int rc = ensure_jacobian(pb);
     if (rc) return rc;
+    if ((rc = materialize_begin(pb))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     const int ps = (int)(pb->launched % kSlots);
@@ -1034,6 +1075,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
         CU(launch_any(kern, dim3(pb->p_grid), block, pb->p_smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity));
         CU(cudaGetLastError());
+        pb->lazy_pending = false;   // pd.lazy_b stays set for this step: only iter_no == 0 reads b as the iterate
         if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
         return finish_slot(pb, slot);
     }
@@ -1058,6 +1100,7 @@ int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active) {
         while (pb->confirmed < pb->launched) {
             const unsigned int v = *((volatile unsigned int*)pb->h_count + (pb->confirmed % kSlots));
             if (v == kPending) break;
+            if (v == 0 && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh) pb->b_ready = true;
             pb->last_active = v;
             pb->confirmed++;
         }
@@ -1143,6 +1186,7 @@ int sb_state_checkpoint(sb_problem* pb) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
     const size_t bytes = node_elems(pb) * sizeof(double);
+    { int rc = materialize_begin(pb); if (rc) return rc; }
     if (!pb->d_ckpt) CU(cudaMalloc((void**)&pb->d_ckpt, bytes));
     CU(cudaMemcpyAsync(pb->d_ckpt, pb->d_u, bytes, cudaMemcpyDeviceToDevice, pb->ctx->stream));
     return SB_OK;
@@ -1153,6 +1197,7 @@ int sb_state_rollback(sb_problem* pb) {
     if (!pb->d_ckpt) return fail(SB_ERR_INVALID, "no checkpoint taken");
     CU(cudaSetDevice(pb->ctx->device));
     cudaStream_t st = pb->ctx->stream;
+    pb->b_ready = false; pb->lazy_pending = false; pb->pd.lazy_b = 0;
     CU(cudaMemcpyAsync(pb->d_u, pb->d_ckpt, node_elems(pb) * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(cudaMemsetAsync(pb->d_total, 0, pb->pd.B * sizeof(long long), st));
     CU(cudaMemsetAsync(pb->d_status, 0, pb->pd.B * sizeof(int), st));

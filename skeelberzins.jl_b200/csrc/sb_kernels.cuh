@@ -45,6 +45,7 @@ struct ProbDev {
     int m, singular, nprm;
     int nprm_s;            // stride of the per-instance parameter block (even, so every block is 16-byte aligned)
     int iter_no;           // Newton iteration number inside the current step (same for every active instance)
+    int lazy_b;            // fused_tma: this step started without k_begin_step: at iter_no == 0 the iterate is b itself
     int64_t B;
     double x0, xN, x0m, xNm, xi0;  // first/last mesh point, x^m of both, first quadrature point
     MeshDev mesh;
@@ -825,7 +826,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr int scratch = ChunkThomas<P, R>::template smem_doubles<TT>();
     // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], instance index [2]
     static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
-                         oSum = oScr + scratch, oK = oSum + 16, group_doubles = oK + 2;
+                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 2 * 4 * P, group_doubles = oK + 2;
     static constexpr int bar_doubles = 2 * G + 2;  // mbarriers (8 bytes): S per group (2 reserved) + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
@@ -849,6 +850,7 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
     double* mbuf = grp + LY::oMass;   // [S][4P]
     double* scratch = grp + LY::oScr;
     double* sums = grp + LY::oSum;    // [2][8]
+    double* keep = grp + LY::oKeep;   // [2][4P] mass flags of the instance in flight (the stage may be refilled early)
     long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index per stage / parity
     uint64_t* bar = bars + 2 * g;
 
@@ -900,10 +902,12 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
         if (j + stride < n_in) k_next2 = list_in ? list_in[j + stride] : j + stride;
     }
     // fetch instance kk into buffer `stage`; its index is published in kslot[seq & 1] (seq = position in this group's sequence)
+    // first iteration of a step that skipped k_begin_step: the Newton iterate is b = M.*u_n itself (src/utils.jl:309)
+    const bool from_b = pd.lazy_b && pd.iter_no == 0;
     auto issue = [&](long long kk, int stage, int seq) {
         kslot[seq & 1] = kk;
-        mbar_expect_tx(bar + stage, 2 * kBytes + kPrmBytes + kMassBytes);
-        bulk_g2s(ubuf + (size_t)stage * L * P, pd.u + (size_t)kk * L * P, kBytes, bar + stage);
+        mbar_expect_tx(bar + stage, (from_b ? 1 : 2) * kBytes + kPrmBytes + kMassBytes);
+        if (!from_b) bulk_g2s(ubuf + (size_t)stage * L * P, pd.u + (size_t)kk * L * P, kBytes, bar + stage);
         bulk_g2s(bbuf + (size_t)stage * L * P, pd.b + (size_t)kk * L * P, kBytes, bar + stage);
         bulk_g2s(pbuf + stage * NPS, pd.prm + (size_t)kk * NPS, kPrmBytes, bar + stage);
         bulk_g2s(mbuf + stage * 4 * P, pd.mass + (size_t)kk * 4 * P, kMassBytes, bar + stage);
@@ -929,12 +933,14 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
         };
         if constexpr (S == 2) prefetch();
         if (t == 0 && pend_pos >= 0) { list_out[pend_pos] = pend_k; pend_pos = -1; }
-        const double* us = ubuf + (size_t)stage * L * P;
         const double* bs = bbuf + (size_t)stage * L * P;
+        const double* us = from_b ? bs : ubuf + (size_t)stage * L * P;
         const double* prm = pbuf + stage * NPS;
         const double* mass = mbuf + stage * 4 * P;
         mbar_wait(bar + stage, (S == 2) ? ((it >> 1) & 1) : (it & 1));
         const int64_t k = kslot[it & 1];
+        double* kp = keep + (it & 1) * 4 * P;
+        if (t < 3 * P) kp[t] = mass[t];
 
         double uc[R][P], bc[R][P];
 #pragma unroll
@@ -966,18 +972,32 @@ __global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, d
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
-        if constexpr (TT > 32) {
+        if constexpr (TT > 32) {  // every thread forms the same total (same order as thread 0) -> all know the outcome
             double* sl = sums + (it & 1) * 8;
             if ((t & 31) == 0) sl[t >> 5] = ss;
             __syncthreads();
-            if (t == 0) {
+            ss = sl[0];
 #pragma unroll
-                for (int w = 1; w < TT / 32; ++w) ss += sl[w];
-            }
+            for (int w = 1; w < TT / 32; ++w) ss += sl[w];
         } else {
-            __syncwarp();
+            ss = __shfl_sync(0xffffffffu, ss, 0);
+        }
+        if (::sqrt(ss) < tol) {
+            // converged: this is u_{n+1}.  Write b = M .* u_{n+1} for the next time step right away (src/pdepe.jl:94),
+            // which then needs no separate pass over the state.
+            double* bg = pd.b + (size_t)k * L * P;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = t * R + r;
+                if (i < pd.Nx) {
+                    const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) bg[(size_t)(r * TT + t) * P + p] = kp[cls * P + p] * (uc[r][p] - h[r].a[p]);
+                }
+            }
         }
         if (t == 0) {
+            if (from_b) pd.active[k] = 1;
             pend_pos = finalize_system(pd, k, ss, tol, slot);
             pend_k = (int)k;
         }

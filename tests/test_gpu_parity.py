@@ -319,3 +319,34 @@ def test_cfg5_full_size_stationary(ctx, oracle):
     assert _relerr(u, r["u"][0, :, 0]) < RTOL
     x = c.xmesh
     assert np.abs(u - np.sqrt(0.01 + x * (1 - x) / 2)).max() < 1e-10
+
+
+def test_begin_step_fusion_is_transparent(ctx, oracle):
+    """fused_tma writes b = M.*u_{n+1} in the converging iteration and skips the begin-step pass of the next time
+    step.  Observing the state in between, or switching the design, must give what the reference sequence gives."""
+    c = ex.example103(300)                       # Dirichlet data on the right: M has a zero, so b != u
+    B = 5
+    prm = np.tile(c.params, (B, 1)) * (1 + 0.1 * np.arange(B))[:, None]
+    fn = sb.Functor(c.functor, prm)
+    tg, tau = sb.time_grid(c.tspan, c.tstep)
+    u0 = np.broadcast_to(np.asarray(c.icfun(c.xmesh)).reshape(1, -1, 1), (B, c.xmesh.size, 1))
+    M = oracle.mass(c.functor, c.m, c.xmesh, prm, u0, tg[0])
+
+    def run(designs, peek):
+        dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn, design=designs[0])
+        dev.upload(u0)
+        dev.mass_flags(tg[0])
+        for i, d in enumerate(designs):
+            dev.set_design(d)
+            dev.begin_step(tg[i + 1], 1.0 / tau)
+            if peek and i > 0:
+                assert np.array_equal(dev.download(), M * prev)   # u <- b = M.*u_n (src/utils.jl:309), materialised on demand
+            dev.newton_solve(1e-10, 100)
+            prev = dev.download().copy()
+        return prev
+
+    ref = oracle.pdepe_transient(c.functor, c.m, c.xmesh, prm, u0, tg[:5], tau)["u"]
+    for designs, peek in ((["fused_tma"] * 4, False), (["fused_tma"] * 4, True), (["fused_tma", "split", "fused_tma", "fused"], False),
+                          (["split", "fused_tma", "fused_tma", "split"], True)):
+        got = run(designs, peek)
+        assert _relerr(got, ref) < RTOL, designs
