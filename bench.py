@@ -298,9 +298,10 @@ def run_ours(args):
                        save="last", squeeze=False, c_loop=not args.python_loop)
         return sol.u[-1]
 
-    last = solve_e2e()                                         # warm-up (allocator, page-ins)
+    for _ in range(2):
+        last = solve_e2e()                                     # warm-up (allocator, page-ins, pinned pools)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(1, min(args.steps, 4))
+    n_e2e = max(1, min(args.steps, 8))
     barrier()
     f0.record(stream)
     for _ in range(n_e2e):
@@ -346,7 +347,7 @@ def run_ours(args):
         "noop_launches_profiled": prof["noop_launches"],
         "algorithmic_bytes_per_unit": bpu[dom], "units_per_launch_avg": prof["instance_iterations"] * Nx / n_launch,
         "kernel_ms_per_step": {k: v for k, v in kern.items()},
-        "kernel_share_of_step": sum(kern.values()) / (ms / args.steps),
+        "kernel_share_of_step": min(1.0, sum(kern.values()) / (ms / args.steps)),
         "lockstep_efficiency": prof["instance_iterations"] / float(n_launch * Bp),
     }
 

@@ -280,7 +280,7 @@ int download_nodes(sb_problem* pb, const double* src, double* host, int W) {
 // decomposition that covers the mesh with R <= Rpref rows per thread, else the CTA-per-system one with
 // the preferred R and the fewest threads.  SB_ROWS_PER_THREAD / SB_THREADS_PER_SYSTEM override (tuning).
 int pick_decomposition(int Nx, int P) {
-    const int Rpref = (P == 1) ? 8 : 4;
+    const int Rpref = 8;  // measured: (8, 32) beats (4, 64) for npde = 2 at Nx = 256; (8, 128) is best for npde = 1 at Nx = 1024
     int want_R = 0, want_T = 0;
     if (const char* e = getenv("SB_ROWS_PER_THREAD")) want_R = atoi(e);
     if (const char* e = getenv("SB_THREADS_PER_SYSTEM")) want_T = atoi(e);

@@ -831,10 +831,16 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
 
-#define SB_LAUNCH_BOUNDS_P(TT) __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), \
-    (32 * SB_PERSISTENT_WARPS_PER_SM) / ((TT) == 32 ? kWarpBlockThreads : (TT)) > 0 ? (32 * SB_PERSISTENT_WARPS_PER_SM) / ((TT) == 32 ? kWarpBlockThreads : (TT)) : 1)
+// resident warps per SM the persistent kernel is compiled for (register cap): scalar PDEs keep ~100 registers per
+// thread; 2x2 block arithmetic needs about twice that, so it is given half the warps instead of spilling
+constexpr int persistent_min_blocks(int TT, int P) {
+    const int threads = (TT == 32) ? kWarpBlockThreads : TT;
+    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_PER_SM / 2;
+    return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;
+}
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void SB_LAUNCH_BOUNDS_P(TT) k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
+__global__ void __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), persistent_min_blocks(TT, Fn::npde))
+k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
                                                           int prev_slot, int parity) {
     using LY = FusedPLayout<Fn, R, TT, SYM0>;
     constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS, S = LY::S;
