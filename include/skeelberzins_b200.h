@@ -168,6 +168,13 @@ int sb_mass_download(sb_problem* pb, double* mass_host);
  * copies in, runs the residual-only kernel, copies out.  u_host==NULL: use the resident state.   */
 int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host);
 
+/* pdeval(m, xmesh, u_approx, x_eval, pb) (src/utils.jl:396-438; the same evaluation serves interpolate_sol_space,
+ * :460-559): value and x-derivative of the solution at nq points shared by the batch, by the interpolation the
+ * discretisation itself uses (src/utils.jl:18-48).  u_host: states in reference layout, or NULL for the resident
+ * state.  Outputs [B][nq][npde].  A point outside the mesh -> SB_ERR_INVALID, "Evaluation point oustide of the
+ * spatial discretization." (the reference's message, :413).                                                      */
+int sb_pdeval(sb_problem* pb, const double* u_host, int nq, const double* xq_host, double* u_out, double* dudx_out);
+
 /* time step n -> n+1 (src/pdepe.jl:94, src/utils.jl:309): b = M.*u_n ; u <- b ; all instances
  * active ; per-step iteration counters cleared.  inv_tau = 1/tau (0 for the stationary solve).   */
 int sb_begin_step(sb_problem* pb, double t_next, double inv_tau);

@@ -533,6 +533,33 @@ int sbo_block_tridiag_solve(int P, int Nx, int64_t B, const double* Jl, const do
     return rc;
 }
 
+// pdeval(m, xmesh, u_approx, x_eval, pb), src/utils.jl:396-438, for B instances and nq evaluation points:
+// uo/dxo[B][nq][P].  Returns -3 for a point outside the mesh ("Evaluation point oustide of the spatial discretization.").
+int sbo_pdeval(int functor, int m, int Nx, const double* xmesh, int64_t B, const double* u, int nq, const double* xq,
+               double* uo, double* dxo) {
+    if (functor < 0 || functor >= NUM_FUNCTORS) return -1;
+    const int P = k_npde[functor];
+    Problem pb; problem_init(pb, m, Nx, xmesh, functor, nullptr);
+    for (int64_t k = 0; k < B; ++k)
+        for (int q = 0; q < nq; ++q) {
+            const double pt = xq[q];
+            int il;
+            if (pt == xmesh[0] || std::fabs(pt - xmesh[0]) <= 1.0e-10 * std::fabs(xmesh[1] - xmesh[0])) {   // :403 isapprox(...; atol)
+                il = 0;
+            } else {
+                const int idx = (int)(std::lower_bound(xmesh, xmesh + Nx, pt) - xmesh) + 1;               // :410 searchsortedfirst (1-based)
+                if (idx == 1 || idx > Nx) return -3;                                                        // :412-414
+                il = idx - 2;                                                                                // interval [idx-1, idx] (1-based)
+            }
+            for (int j = 0; j < P; ++j) {
+                double U, Ux;
+                interpolation(pb, xmesh[il], u[((size_t)k * Nx + il) * P + j], xmesh[il + 1], u[((size_t)k * Nx + il + 1) * P + j], pt, U, Ux);
+                uo[((size_t)k * nq + q) * P + j] = U; dxo[((size_t)k * nq + q) * P + j] = Ux;
+            }
+        }
+    return 0;
+}
+
 // Batched transient solve: the reference pdepe (src/pdepe.jl:42-128) looped over B instances (OpenMP over instances).
 // u[B][n] in: initial values, out: final states.  iters[B][nt-1], hist[B][nt-1][hist_cap] (nullable),
 // snapshots[B][nt][n] (nullable).  status[B]: 0 ok, -1 convergence failed, -2 singular Jacobian.

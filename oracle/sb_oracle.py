@@ -169,3 +169,32 @@ def pdepe_stationary(fid, m, xmesh, prm, u0, tol=1e-10, maxit=100, hist=False, n
     if hist:
         out["hist"] = H
     return out
+
+
+def pdeval(fid, m, xmesh, u, x_eval):
+    """pdeval (src/utils.jl:396-438) per instance: returns (u[B,nq,P], dudx[B,nq,P])."""
+    npde, nprm = functor_info(fid)
+    x = _c(xmesh)
+    u = _c(u).reshape(-1, x.size, npde)
+    xq = np.atleast_1d(_c(x_eval))
+    uo = np.empty((u.shape[0], xq.size, npde))
+    dxo = np.empty_like(uo)
+    rc = lib().sbo_pdeval(int(fid), int(m), x.size, _d(x), ctypes.c_int64(u.shape[0]), _d(u), xq.size, _d(xq), _d(uo), _d(dxo))
+    if rc == -3:
+        raise ValueError("Evaluation point oustide of the spatial discretization.")
+    assert rc == 0
+    return uo, dxo
+
+
+def interpolate_sol_time(ts, us, t):
+    """interpolate_sol_time(u_approx, t), src/utils.jl:575-595 (us: sequence of snapshots, ts: their times)."""
+    ts = np.asarray(ts, dtype=np.float64)
+    if t == ts[0] or abs(t - ts[0]) <= 1.0e-10 * abs(ts[1] - ts[0]):
+        return np.asarray(us[0])
+    idx = int(np.searchsorted(ts, t, side="left")) + 1                  # searchsortedfirst, 1-based
+    if idx == 1 or idx > len(us):
+        raise ValueError("The chosen time is not within the interval.")
+    dt = ts[idx - 1] - ts[idx - 2]
+    x1 = (ts[idx - 1] - t) / dt
+    x0 = (t - ts[idx - 2]) / dt
+    return x1 * np.asarray(us[idx - 2]) + x0 * np.asarray(us[idx - 1])

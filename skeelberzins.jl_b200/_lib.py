@@ -47,6 +47,7 @@ SIGNATURES = {
     "sb_mass_flags": (_c.c_int, [_vp, _c.c_double, _c.c_int]),
     "sb_mass_download": (_c.c_int, [_vp, _vp]),
     "sb_assemble": (_c.c_int, [_vp, _vp, _c.c_double, _vp]),
+    "sb_pdeval": (_c.c_int, [_vp, _vp, _c.c_int, _vp, _vp, _vp]),
     "sb_begin_step": (_c.c_int, [_vp, _c.c_double, _c.c_double]),
     "sb_residual_jacobian": (_c.c_int, [_vp]),
     "sb_solve_update_norm": (_c.c_int, [_vp, _c.c_double]),

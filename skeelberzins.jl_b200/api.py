@@ -342,6 +342,18 @@ class DeviceProblem:
         _lib.check(self.lib.sb_total_active_iterations(self._h, ctypes.byref(n)))
         return n.value
 
+    def pdeval(self, u, x_eval):
+        """(u, dudx)[B, nq, npde] at the points x_eval; u: states [B, Nx, npde] in reference layout or None (resident state)."""
+        xq = np.atleast_1d(np.ascontiguousarray(x_eval, dtype=np.float64))
+        uu = None if u is None else self._nodes(u)
+        uo = np.empty((self.B, xq.size, self.npde))
+        dxo = np.empty_like(uo)
+        rc = self.lib.sb_pdeval(self._h, _lib.ptr(uu), xq.size, _lib.ptr(xq), _lib.ptr(uo), _lib.ptr(dxo))
+        if rc == _lib.SB_ERR_INVALID and "oustide" in self.lib.sb_last_error().decode():
+            raise ValueError("Evaluation point oustide of the spatial discretization.")   # src/utils.jl:413 (sic)
+        _lib.check(rc)
+        return uo, dxo
+
     def debug_system(self):
         P = self.npde
         F = np.empty((self.B, self.Nx, P))
@@ -430,16 +442,84 @@ SkeelBerzinsDiscretization = ProblemDefinition  # name used by the north_star fo
 class DiffEqArray:
     """Result container of the transient solve (RecursiveArrayTools.DiffEqArray, src/pdepe.jl:110):
     `u[k]` is the state at `t[k]`: [B, Nx] for npde == 1, [B, npde, Nx] otherwise (squeezed to the
-    reference's Vector[Nx] / Matrix(npde, Nx) when the batch axis was not requested)."""
+    reference's Vector[Nx] / Matrix(npde, Nx) when the batch axis was not requested).
+    `sol(t)` interpolates linearly in time (src/utils.jl:597); `sol(x_eval, t, pb)` in time and space (:561)."""
 
     def __init__(self, u, t):
         self.u, self.t = u, np.asarray(t)
+
+    def __call__(self, *args, val=True, deriv=True):
+        if len(args) == 1:
+            return interpolate_sol_time(self, args[0])
+        x_eval, t, pb = args
+        return interpolate_sol_space(self, x_eval, t, pb, val=val, deriv=deriv)
 
     def __len__(self):
         return len(self.u)
 
     def __getitem__(self, k):
         return self.u[k]
+
+
+def _to_reference_layout(u_approx, pb):
+    """states as pdepe returns them ([Nx] | [B, Nx] | [npde, Nx] | [B, npde, Nx] | flat) -> [B, Nx, npde]"""
+    B, Nx, P = pb.device.B, pb.Nx, pb.npde
+    a = np.asarray(u_approx, dtype=np.float64)
+    if a.size != B * Nx * P:
+        raise ValueError("u_approx has %d values, expected %d" % (a.size, B * Nx * P))
+    if P == 1 or a.ndim <= 1 or a.shape[-1] == Nx * P:
+        return np.ascontiguousarray(a.reshape(B, Nx, P))          # component fastest already (or scalar PDE)
+    return np.ascontiguousarray(np.transpose(a.reshape(B, P, Nx), (0, 2, 1)))
+
+
+def _shape_eval(a, pb, scalar_x):
+    """[B, nq, npde] -> drop the axes the caller did not ask for (reference: scalars for a scalar x_eval)"""
+    if pb.npde == 1:
+        a = a[:, :, 0]
+    if scalar_x:
+        a = a[:, 0]
+    return a[0] if pb.device.B == 1 else a
+
+
+def pdeval(m, xmesh, u_approx, x_eval, pb):
+    """pdeval(m, xmesh, u_approx, x_eval, pb) (src/utils.jl:396-438): (u, dudx) at x_eval, evaluated on the GPU with
+    the interpolation of the discretisation.  Batched: one result row per instance."""
+    if m != pb.m:
+        raise ValueError("The symmetry argument is different from the one used to solve the PDE problem.")   # :398
+    scalar_x = np.isscalar(x_eval)
+    uo, dxo = pb.device.pdeval(_to_reference_layout(u_approx, pb), x_eval)
+    return _shape_eval(uo, pb, scalar_x), _shape_eval(dxo, pb, scalar_x)
+
+
+def interpolate_sol_time(u_approx, t):
+    """interpolate_sol_time(u_approx, t) (src/utils.jl:575-595): linear interpolation between stored time steps."""
+    ts = u_approx.t
+    if t == ts[0] or abs(t - ts[0]) <= 1.0e-10 * abs(ts[1] - ts[0]):
+        return u_approx.u[0]
+    idx = int(np.searchsorted(ts, t, side="left")) + 1            # searchsortedfirst (1-based)
+    if idx == 1 or idx > len(u_approx):
+        raise ValueError("The chosen time is not within the interval.")          # :583
+    dt = ts[idx - 1] - ts[idx - 2]
+    x1 = (ts[idx - 1] - t) / dt
+    x0 = (t - ts[idx - 2]) / dt
+    return x1 * np.asarray(u_approx.u[idx - 2]) + x0 * np.asarray(u_approx.u[idx - 1])
+
+
+def interpolate_sol_space(u_approx, x_eval, times, pb, val=True, deriv=True):
+    """interpolate_sol_space(u_approx, x_eval, times, pb; val, deriv) (src/utils.jl:460-559)."""
+    scalar_t = np.isscalar(times)
+    us, dus = [], []
+    for t in np.atleast_1d(times):
+        u, du = pdeval(pb.m, pb.xmesh, interpolate_sol_time(u_approx, t), x_eval, pb)
+        us.append(u)
+        dus.append(du)
+    if scalar_t:
+        us, dus = us[0], dus[0]
+    if val and not deriv:
+        return us
+    if deriv and not val:
+        return dus
+    return us, dus
 
 
 def _merge_params(params, kwargs, stationary):

@@ -106,6 +106,40 @@ __global__ void k_from_device_layout(const double* __restrict__ src, double* __r
     dst[idx] = src[((size_t)k * L + (size_t)tile * Lt + (size_t)(il % R) * T + il / R) * W + w];
 }
 
+// pdeval / interpolate_sol_space (src/utils.jl:396-438, :460-559): one thread per (instance, evaluation point);
+// bisection on the shared mesh, then the interpolation of src/utils.jl:18-48 at the point itself
+__global__ void k_pdeval(const double* __restrict__ u, const double* __restrict__ x, int Nx, int R, int T, int L, int P,
+                         int m, int singular, int64_t B, int nq, const double* __restrict__ xq, double* __restrict__ uo,
+                         double* __restrict__ dxo) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * nq) return;
+    const int64_t k = idx / nq;
+    const int q = (int)(idx - (size_t)k * nq);
+    const double pt = xq[q];
+    int il;
+    if (pt == x[0] || fabs(pt - x[0]) <= 1.0e-10 * fabs(x[1] - x[0])) {
+        il = 0;
+    } else {
+        int lo = 0, hi = Nx;             // first index with x[i] >= pt (searchsortedfirst)
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] < pt) lo = mid + 1; else hi = mid; }
+        il = lo - 1;                     // the host has checked 1 <= lo <= Nx-1
+    }
+    const int Lt = R * T;
+    auto slot = [&](int i) { const int tile = i / Lt, r = i - tile * Lt; return (size_t)tile * Lt + (size_t)(r % R) * T + r / R; };
+    const double xl = x[il], xr = x[il + 1];
+    double aw, bw, gw;                   // U = aw*ul + bw*ur, Ux = gw*(ur - ul)
+    if (singular) { const double h = xr * xr - xl * xl, th = (pt * pt - xl * xl) / h; aw = 1 - th; bw = th; gw = (2 * pt) / h; }
+    else if (m == 0) { const double h = xr - xl; aw = (xr - pt) / h; bw = (pt - xl) / h; gw = 1.0 / h; }
+    else if (m == 1) { const double lg = log(xr / xl), th = log(pt / xl) / lg; aw = 1 - th; bw = th; gw = 1.0 / (pt * lg); }
+    else { const double h = xr - xl, th = (xr * (pt - xl)) / (pt * h); aw = 1 - th; bw = th; gw = (xr * xl) / (pt * pt * h); }
+    const double* ub = u + (size_t)k * L * P;
+    for (int j = 0; j < P; ++j) {
+        const double ul = ub[slot(il) * P + j], ur = ub[slot(il + 1) * P + j];
+        uo[idx * P + j] = aw * ul + bw * ur;
+        dxo[idx * P + j] = gw * (ur - ul);
+    }
+}
+
 const FunctorEntry* registry() {
     static FunctorEntry table[SB_NUM_BUILTIN_FUNCTORS];
     static bool init = false;
@@ -926,6 +960,48 @@ static int prof_harvest(sb_problem* pb) {
         pb->prof_prev_active = pb->h_count[s];
     }
     pb->prof_harvested = pb->launched;
+    return SB_OK;
+}
+
+int sb_pdeval(sb_problem* pb, const double* u_host, int nq, const double* xq_host, double* u_out, double* dudx_out) {
+    if (!pb || !xq_host || !u_out || !dudx_out || nq < 1) return fail(SB_ERR_INVALID, "NULL argument or nq < 1");
+    CU(cudaSetDevice(pb->ctx->device));
+    const int Nx = pb->pd.Nx, P = pb->P;
+    const std::vector<double>& x = pb->xmesh;
+    for (int q = 0; q < nq; ++q) {       // src/utils.jl:403-414
+        const double pt = xq_host[q];
+        if (pt == x[0] || std::fabs(pt - x[0]) <= 1.0e-10 * std::fabs(x[1] - x[0])) continue;
+        const long idx = (std::lower_bound(x.begin(), x.end(), pt) - x.begin()) + 1;
+        if (idx == 1 || idx > Nx) return fail(SB_ERR_INVALID, "Evaluation point oustide of the spatial discretization.");
+    }
+    int rc = SB_OK;
+    double* d_uin = nullptr;
+    const double* d_u = pb->d_u;
+    if (u_host) {
+        CU(cudaMalloc((void**)&d_uin, node_elems(pb) * sizeof(double)));
+        rc = upload_nodes(pb, u_host, d_uin, P, 0);
+        if (rc) { cudaFree(d_uin); return rc; }
+        d_u = d_uin;
+    } else if ((rc = materialize_begin(pb))) return rc;
+    double *d_x = nullptr, *d_q = nullptr, *d_o = nullptr;
+    const size_t no = (size_t)pb->pd.B * nq * P;
+    cudaError_t e = cudaMalloc((void**)&d_x, (size_t)(Nx + nq) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, 2 * no * sizeof(double));
+    cudaStream_t st = pb->ctx->stream;
+    if (e == cudaSuccess) { d_q = d_x + Nx; e = cudaMemcpyAsync(d_x, x.data(), Nx * sizeof(double), cudaMemcpyHostToDevice, st); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, xq_host, nq * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const size_t n = (size_t)pb->pd.B * nq;
+        k_pdeval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_u, d_x, Nx, pb->pd.R, pb->pd.T, pb->pd.L, P, pb->pd.m, pb->pd.singular,
+                                                             pb->pd.B, nq, d_q, d_o, d_o + no);
+        ++g_launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u_out, d_o, no * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dudx_out, d_o + no, no * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_x); cudaFree(d_o); cudaFree(d_uin);
+    if (e != cudaSuccess) return fail(SB_ERR_CUDA, "sb_pdeval: %s", cudaGetErrorString(e));
     return SB_OK;
 }
 
