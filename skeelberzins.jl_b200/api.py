@@ -522,6 +522,39 @@ def interpolate_sol_space(u_approx, x_eval, times, pb, val=True, deriv=True):
     return us, dus
 
 
+class ODEFunction:
+    """DifferentialEquations.jl-facing operator (src/diffEq.jl:18-27): f(du, u, p, t) = assemble!(du, u, pb, t) on the
+    GPU, the diagonal mass matrix when the problem is a DAE, and the block-tridiagonal Jacobian prototype.
+    Vectors are flat [B, Nx*npde] (component fastest), like pb.inival."""
+
+    def __init__(self, pb):
+        self.pb = pb
+        M, flag_dae = mass_matrix(pb)
+        self.mass_matrix = M if flag_dae else None               # src/diffEq.jl:21-26
+        self.jac_prototype = jac_prototype(pb.Nx, pb.npde)
+
+    def __call__(self, du, u, p, t):
+        return assemble_(du, u, self.pb, t)
+
+
+def jac_prototype(Nx, npde):
+    """All-ones block-tridiagonal sparsity prototype (get_sparsity_pattern, src/utils.jl:725-759) as scipy CSC."""
+    import scipy.sparse as sp
+    blk = np.ones((npde, npde))
+    return sp.kron(sp.diags([np.ones(Nx - 1), np.ones(Nx), np.ones(Nx - 1)], [-1, 0, 1]), blk, format="csc")
+
+
+def ODEProblem(pb):
+    """ODEProblem(pb) (src/diffEq.jl:40-43): (ODEFunction, u0, tspan) for an external ODE/DAE integrator."""
+    return ODEFunction(pb), pb.inival.copy(), pb.tspan
+
+
+def reshape_solution(sol_u, pb):
+    """reshape(sol, pb) (src/diffEq.jl:54-57): flat states -> [..., npde, Nx]."""
+    a = np.asarray(sol_u)
+    return np.transpose(a.reshape(a.shape[:-1] + (pb.Nx, pb.npde)), tuple(range(a.ndim - 1)) + (a.ndim, a.ndim - 1))
+
+
 def _merge_params(params, kwargs, stationary):
     # src/pdepe.jl:44-52 / :158-166 -- kwargs override the fields of params
     names = ("solver", "tstep", "hist", "sparsity", "linsolve", "maxit", "tol", "data", "nb_design_var")
@@ -616,7 +649,7 @@ newton_stat = newton  # src/utils.jl:344-378: same loop, residual without mass m
 
 
 def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused_tma", save="all",
-          squeeze=None, c_loop=False, return_device=False, **kwargs):
+          squeeze=None, c_loop=False, return_device=False, alias_compat=False, **kwargs):
     """Batched pdepe.  With `tspan`: transient solve by implicit Euler (src/pdepe.jl:42-128); without:
     stationary solve by one Newton solve with tau = Inf, t = 1 (src/pdepe.jl:156-192).
 
@@ -625,7 +658,8 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     squeeze (drop the batch axis; default: when the functor has a single instance).
     Returns what the reference returns: sol | (sol, pb) | (sol, storage) | (sol, pb, storage); stationary:
     u | (u, hist) | (u, pb) | (u, pb, hist).  Unlike the reference stored states are the
-    true states, not the in-place masked aliases.
+    true states, not the in-place masked aliases; alias_compat=True reproduces the reference's stored values
+    (every sol.u[k] but the last -- and, for npde > 1, the first -- multiplied by the mass flags, src/pdepe.jl:87-107).
     """
     stationary = tspan is None
     params = _merge_params(params or Params(tstep=np.inf if stationary else 1e-2), kwargs, stationary)
@@ -698,6 +732,10 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
         results.append(shape(dev.download()))
         sol = DiffEqArray(results, timeSteps[-1:])
     else:
+        if alias_compat:
+            Mm = shape(dev.mass())
+            first = 1 if npde > 1 else 0
+            results = [r if (k < first or k == len(results) - 1) else Mm * r for k, r in enumerate(results)]
         sol = DiffEqArray(results, timeSteps)
     out = [sol]
     if params.data:

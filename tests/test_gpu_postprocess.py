@@ -80,3 +80,37 @@ def test_sol_time_interpolation_and_system(ctx, oracle):
     assert np.abs(u - ro[0]).max() < 1e-14 and np.abs(du - rdx[0]).max() < 1e-12
     only_val = sol(xq, tq, pb, deriv=False)
     assert np.array_equal(only_val, u)
+
+
+def test_diffeq_operator_and_alias_compat(ctx, oracle):
+    """the ODEFunction/ODEProblem adapter (src/diffEq.jl:18-57) and the reference's stored-value quirk."""
+    c = ex.example103(60)
+    fn = sb.Functor(c.functor, c.params)
+    pb = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=ctx, solver="DiffEq")     # returns pb, src/pdepe.jl:123-126
+    f, u0, tspan = sb.ODEProblem(pb)
+    assert tspan == (0.0, 1.0) and u0.shape == (1, 60)
+    du = np.empty_like(u0)
+    f(du, u0, None, 0.25)
+    ref = oracle.assemble(c.functor, c.m, c.xmesh, c.params, u0.reshape(1, 60, 1), 0.25)
+    assert np.abs(du.reshape(-1) - ref.reshape(-1)).max() < 1e-12 * np.abs(ref).max()
+    assert f.mass_matrix is not None and f.mass_matrix[0, -1] == 0 and f.mass_matrix[0, 0] == 1     # Dirichlet right end
+    J = f.jac_prototype
+    assert J.shape == (60, 60) and J.nnz == 3 * 60 - 2                                              # src/utils.jl:725-759
+    assert sb.jac_prototype(21, 2).nnz == 4 * (3 * 21 - 2)
+    assert sb.reshape_solution(np.arange(12.0).reshape(1, 12), type("P", (), {"Nx": 6, "npde": 2})).shape == (1, 2, 6)
+    true = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=ctx)
+    ali = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=ctx, alias_compat=True)
+    assert np.array_equal(true.u[-1], ali.u[-1])
+    assert ali.u[5][-1] == 0.0 and true.u[5][-1] != 0.0 and np.array_equal(ali.u[5][:-1], true.u[5][:-1])
+
+
+def test_nonuniform_vector_tstep(ctx, oracle):
+    """Params.tstep as a vector is the time grid itself, tau_i = diff (src/pdepe.jl:85,92)."""
+    c = ex.baseline_case("2", B=6, Nx=200)
+    grid = np.array([0.001, 0.0011, 0.0013, 0.0018, 0.002, 0.0027])
+    fn = sb.Functor(c.functor, c.params)
+    sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (grid[0], grid[-1]), ctx=ctx, tstep=grid, squeeze=False)
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), grid, None, snapshots=True)
+    assert len(sol) == grid.size
+    for k in range(grid.size):
+        assert np.abs(sol.u[k] - r["snapshots"][:, k, :, 0]).max() < 1e-10 * np.abs(r["snapshots"]).max()
