@@ -346,7 +346,7 @@ int pick_decomposition(int Nx, int P) {
 #define SB_TMA_STAGES 1
 #endif
 #ifndef SB_PERSISTENT_WARPS_PER_SM
-#define SB_PERSISTENT_WARPS_PER_SM 20
+#define SB_PERSISTENT_WARPS_PER_SM 16
 #endif
 
 std::string csrc_dir() {

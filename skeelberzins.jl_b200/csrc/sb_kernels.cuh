@@ -813,7 +813,7 @@ SB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
 #define SB_TMA_STAGES 1   // 1: the next instance is prefetched into the same buffers as soon as every thread of the
 #endif                    //    group has consumed the current one (less smem -> more CTAs/SM); 2: double buffering
 #ifndef SB_PERSISTENT_WARPS_PER_SM
-#define SB_PERSISTENT_WARPS_PER_SM 20
+#define SB_PERSISTENT_WARPS_PER_SM 16
 #endif
 
 template <class Fn, int R, int TT, bool SYM0>
