@@ -128,6 +128,10 @@ int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name);
 int sb_register_user_functor(sb_ctx* ctx, const char* cuda_source, const char* struct_name,
                              int npde, int nparams, int* functor_id);
 
+/* NVRTC-only dry run (needs no GPU): compile the kernels a problem with Nx mesh points and coordinate symmetry m would
+ * need for a registered user functor; SB_ERR_PLUGIN + the compiler log on failure, size of the CUBIN on success.  */
+int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_bytes);
+
 /* ---- problem (replaces problem_init, src/utils.jl:609-663, for a batch of B instances) -------
  * m          coordinate symmetry 0/1/2 (asserts of src/pdepe.jl:55-57 apply)
  * xmesh_host Nx mesh points shared by the batch

@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_ctx_synchronize": (_c.c_int, [_vp]),
     "sb_functor_info": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_char_p)]),
     "sb_register_user_functor": (_c.c_int, [_vp, _c.c_char_p, _c.c_char_p, _c.c_int, _c.c_int, _c.POINTER(_c.c_int)]),
+    "sb_user_functor_compile_check": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.POINTER(_c.c_size_t)]),
     "sb_problem_create": (_c.c_int, [_vp, _c.c_int, _c.c_int, _c.c_int64, _vp, _c.c_int, _vp, _c.c_int, _c.POINTER(_vp)]),
     "sb_problem_destroy": (_c.c_int, [_vp]),
     "sb_problem_info": (_c.c_int, [_vp, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int)]),

@@ -104,6 +104,13 @@ def register_user_functor(cuda_source, struct_name, npde, nparams):
     return fid.value
 
 
+def user_functor_compile_check(functor_id, Nx, m=0):
+    """NVRTC dry run of a registered user functor for a problem shape (no GPU needed); returns the CUBIN size."""
+    n = ctypes.c_size_t()
+    _lib.check(_lib.load().sb_user_functor_compile_check(int(functor_id), int(Nx), int(m), ctypes.byref(n)))
+    return n.value
+
+
 class _PinnedPool:
     """Page-locked host buffers for results.  A buffer goes back to the pool when the numpy array that wraps
     it (and every view of it) has been garbage-collected, so repeated solves re-use the same pinned pages."""

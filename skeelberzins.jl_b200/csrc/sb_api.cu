@@ -360,10 +360,11 @@ std::string csrc_dir() {
     return "csrc";
 }
 
-// Compile the kernels this problem needs (its decomposition, its coordinate symmetry) for a user functor and load them.
-int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
-    const int R = pb->pd.R, TT = pb->pd.T;
-    const char* sym = pb->sym0 ? "true" : "false";
+// NVRTC stage (needs no GPU): source of the user functor -> CUBIN of the kernels of one problem shape
+// (decomposition R x TT, coordinate symmetry, long mesh or not) + their lowered names
+int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool longmesh, std::vector<char>& cubin,
+                       std::vector<std::string>& lowered) {
+    const char* sym = sym0 ? "true" : "false";
     char buf[256];
     std::string src = "#include \"sb_longmesh.cuh\"\nusing namespace sb;\n" + uf.source + "\n";
     snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_fused_p_smem = sb::FusedPLayout<%s, %d, %d, %s>::bytes;\n",
@@ -379,7 +380,7 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     name("sb::k_assemble<%s, %d, %d, %s, false>");
     name("sb::k_newton_fused<%s, %d, %d, %s>");
     name("sb::k_newton_fused_p<%s, %d, %d, %s>");
-    if (pb->longmesh) {
+    if (longmesh) {
         name("sb::k6_chunk_asm<%s, %d, %d, %s>");
         name("sb::k6_back_asm<%s, %d, %d, %s>");
         name("sb::k6_assemble<%s, %d, %d, %s, true>");
@@ -405,22 +406,35 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     }
     size_t cs = 0;
     nvrtcGetCUBINSize(prog, &cs);
-    std::vector<char> cubin(cs);
+    cubin.resize(cs);
     nvrtcGetCUBIN(prog, cubin.data());
-    KernelSet& ks = pb->ks;
-    cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e != cudaSuccess) { nvrtcDestroyProgram(&prog); return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e)); }
-    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p,
-                            &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
+    lowered.clear();
     for (size_t i = 0; i < names.size(); ++i) {
         const char* low = nullptr;
         nvrtcGetLoweredName(prog, names[i].c_str(), &low);
-        cudaKernel_t kern;
-        e = cudaLibraryGetKernel(&kern, ks.lib, low);
-        if (e != cudaSuccess) { nvrtcDestroyProgram(&prog); return fail(SB_ERR_PLUGIN, "cudaLibraryGetKernel(%s): %s", names[i].c_str(), cudaGetErrorString(e)); }
-        *slots[i] = (const void*)kern;
+        lowered.push_back(low ? low : "");
     }
     nvrtcDestroyProgram(&prog);
+    return SB_OK;
+}
+
+// Compile the kernels this problem needs (its decomposition, its coordinate symmetry) for a user functor and load them.
+int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    int rc = nvrtc_user_kernels(uf, pb->pd.R, pb->pd.T, pb->sym0 != 0, pb->longmesh, cubin, lowered);
+    if (rc != SB_OK) return rc;
+    KernelSet& ks = pb->ks;
+    cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
+    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p,
+                            &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
+    for (size_t i = 0; i < lowered.size(); ++i) {
+        cudaKernel_t kern;
+        e = cudaLibraryGetKernel(&kern, ks.lib, lowered[i].c_str());
+        if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "cudaLibraryGetKernel(%s): %s", lowered[i].c_str(), cudaGetErrorString(e));
+        *slots[i] = (const void*)kern;
+    }
     void* dptr = nullptr; size_t bytes = 0;
     e = cudaLibraryGetGlobal(&dptr, &bytes, ks.lib, "sb_user_fused_p_smem");
     unsigned long long smem = 0;
@@ -577,6 +591,24 @@ int sb_ctx_synchronize(sb_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+}
+
+int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_bytes) {
+    if (functor_id < SB_USER_FUNCTOR_BASE || functor_id >= SB_USER_FUNCTOR_BASE + (int)user_functors().size())
+        return fail(SB_ERR_INVALID, "functor id %d is not a registered user functor", functor_id);
+    const UserFunctor& uf = user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+    int dec = pick_decomposition(Nx, uf.npde);
+    bool longmesh = false;
+    int R, TT;
+    if (dec < 0) {
+        if (uf.npde != 1) return fail(SB_ERR_UNSUPPORTED, "Nx = %d: long meshes need npde = 1", Nx);
+        longmesh = true; R = kLongR; TT = kLongTT;
+    } else { R = kDecomp[dec].R; TT = kDecomp[dec].TT; }
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    int rc = nvrtc_user_kernels(uf, R, TT, m == 0, longmesh, cubin, lowered);
+    if (rc == SB_OK && cubin_bytes) *cubin_bytes = cubin.size();
+    return rc;
 }
 
 int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name) {

@@ -833,7 +833,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
 
 // resident warps per SM the persistent kernel is compiled for (register cap): scalar PDEs keep ~100 registers per
 // thread; 2x2 block arithmetic needs about twice that, so it is given half the warps instead of spilling
-constexpr int persistent_min_blocks(int TT, int P) {
+__host__ __device__ constexpr int persistent_min_blocks(int TT, int P) {
     const int threads = (TT == 32) ? kWarpBlockThreads : TT;
     const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_PER_SM / 2;
     return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;

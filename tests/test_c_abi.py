@@ -80,3 +80,30 @@ def test_time_grid_matches_julia_ranges():
     assert g.size == 81 and g[-1] == 0.8
     grid, tau = sb.time_grid((0, 1), np.array([0.0, 0.1, 0.3, 1.0]))
     assert tau is None and grid.tolist() == [0.0, 0.1, 0.3, 1.0]
+
+
+USER_SRC = r"""
+struct CpuCheckFn {
+    static constexpr int npde = 1, nparams = 2;
+    static constexpr bool c_unit = false, s_zero = false;
+    template <class S> static __device__ void pde(double x, double t, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
+        c[0] = 1.0 + p[1] * u[0] * u[0]; f[0] = p[0] * sqrt(1.0 + u[0] * u[0]) * ux[0]; s[0] = log(2.0 + u[0] * u[0]) - x * t;
+    }
+    template <class S> static __device__ void bc(double, const S* ul, double, const S* ur, double t, const double* p,
+                                                 S* pl, double* ql, S* pr, double* qr) {
+        pl[0] = ul[0] - t; ql[0] = 0.0; pr[0] = ur[0] * ur[0] - 1.0; qr[0] = 1.0;
+    }
+};
+"""
+
+
+@pytest.mark.parametrize("Nx,m", [(21, 0), (256, 1), (1024, 0), (1024, 2), (100000, 0)])
+def test_user_functor_plugin_compiles_without_gpu(built_lib, Nx, m):
+    """The NVRTC stage of the plugin slot runs on the CPU box: the kernel headers must stay NVRTC-clean for every
+    problem shape (warp / CTA / long-mesh decompositions, both symmetry specialisations)."""
+    import skeelberzins_jl_b200 as sb
+    fid = sb.register_user_functor(USER_SRC, "CpuCheckFn", 1, 2)
+    assert sb.user_functor_compile_check(fid, Nx, m) > 10000
+    bad = sb.register_user_functor("struct Nope { int x; };", "Nope", 1, 1)
+    with pytest.raises(sb.SBError, match="NVRTC"):
+        sb.user_functor_compile_check(bad, 64, 0)
