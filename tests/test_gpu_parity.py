@@ -350,3 +350,74 @@ def test_begin_step_fusion_is_transparent(ctx, oracle):
                           (["split", "fused_tma", "fused_tma", "split"], True)):
         got = run(designs, peek)
         assert _relerr(got, ref) < RTOL, designs
+
+
+@pytest.mark.parametrize("Nx", [3, 4, 5, 33])
+def test_tiny_meshes(ctx, oracle, Nx):
+    """Smallest meshes the reference accepts (boundary rows only / one interior row)."""
+    for make in (ex.example104, ex.example105):
+        c = make(Nx)
+        fn = sb.Functor(c.functor, c.params)
+        u, hist = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, ctx=ctx, hist=True)
+        r = oracle.pdepe_stationary(c.functor, c.m, c.xmesh, c.params, c.initial(), hist=True)
+        assert len(hist) == r["iters"][0]
+        assert _relerr(u, r["u"][0, :, 0]) < RTOL
+    c = ex.example101(Nx)
+    fn = sb.Functor(c.functor, c.params)
+    sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (0.0, 0.05), ctx=ctx, tstep=1e-2)
+    tg = sb.julia_range(0.0, 1e-2, 0.05)
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, 1e-2)
+    assert _relerr(sol.u[-1], r["u"][0, :, 0]) < RTOL
+
+
+def test_many_newton_iterations_wrap_the_counter_ring(ctx):
+    """maxit beyond the 128-slot ring of per-iteration counters; tol = 0 can never be met (nm < 0 is false), so the
+    loop runs to maxit and fails like the reference (src/utils.jl:336), for every design."""
+    c = ex.example104(64)
+    fn = sb.Functor(c.functor, np.tile(c.params, (3, 1)))
+    for design in ("fused_tma", "fused", "split"):
+        dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn, design=design)
+        dev.upload(np.tile(c.initial(), (3, 1, 1)))
+        dev.mass_flags(1.0, stationary=True)
+        dev.begin_step(1.0, 0.0)
+        with pytest.raises(sb.ConvergenceFailed):
+            dev.newton_solve(0.0, 300)
+        assert (dev.step_iters() == 300).all() and (dev.total_iters() == 300).all()
+        dev.begin_step(1.0, 0.0)
+        with pytest.raises(sb.ConvergenceFailed):
+            sb.api._newton_loop(dev, 0.0, 150)
+        assert (dev.step_iters() == 150).all()
+        dev.close()
+
+
+def test_nonfinite_instances_are_flagged(ctx):
+    """An instance whose Newton iteration blows up (a = 0 makes the flux vanish with Neumann data: singular Jacobian in
+    the stationary problem) is reported as status 2 and does not disturb its neighbours in the batch."""
+    c = ex.example105(50)
+    prm = np.tile(c.params, (4, 1))
+    prm[2, 0] = 0.0
+    fn = sb.Functor(c.functor, prm)
+    dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn)
+    dev.upload(np.tile(c.initial(), (4, 1, 1)))
+    dev.mass_flags(1.0, stationary=True)
+    dev.begin_step(1.0, 0.0)
+    with pytest.raises(sb.ConvergenceFailed):
+        dev.newton_solve(1e-10, 30)
+    st = dev.status()
+    it = dev.step_iters()
+    assert st[2] == 2 and it[2] == 30
+    assert (st[[0, 1, 3]] == 0).all() and (it[[0, 1, 3]] == 7).all()
+    u = dev.download()
+    x = c.xmesh
+    assert np.abs(u[0, :, 0] - np.sqrt(0.01 + x * (1 - x) / 2)).max() < 1e-12
+
+
+def test_large_batch_of_small_problems(ctx, oracle):
+    c = ex.baseline_case("2", B=20001, Nx=21)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:3]
+    fn = sb.Functor(c.functor, c.params)
+    sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, squeeze=False, save="last")
+    idx = np.array([0, 1, 2, 9999, 20000])
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params[idx], c.initial()[idx], tg, None)
+    assert _relerr(sol.u[-1][idx], r["u"][:, :, 0]) < RTOL
