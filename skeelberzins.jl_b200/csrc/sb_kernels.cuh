@@ -731,21 +731,40 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_solve(ProbDev pd, double tol, int slot, i
         return;
     }
     ChunkThomas<P, R> th;
+    double uc[R][P];
+    if constexpr (P == 1 && R <= 8) {
+        // scalar systems: issue all loads of the chunk (rows and the iterate) before the dependent elimination
+        // chain starts, so the memory latency is paid once per thread instead of once per row
+        double ra[R], rb[R], rc[R], rd[R];
+        const size_t o0 = (size_t)k * pd.L + t;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const size_t o = (size_t)k * pd.L + (size_t)r * TT + t;
-        Mat<P> A, Bm, C; Vec<P> d;
+        for (int r = 0; r < R; ++r) {
+            ra[r] = __ldcs(pd.Jl + o0 + (size_t)r * TT); rb[r] = __ldcs(pd.Jd + o0 + (size_t)r * TT);
+            rc[r] = __ldcs(pd.Ju + o0 + (size_t)r * TT); rd[r] = __ldcs(pd.F + o0 + (size_t)r * TT);
+        }
+        if (update) load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
 #pragma unroll
-        for (int i = 0; i < P * P; ++i) { A.a[i] = pd.Jl[o * P * P + i]; Bm.a[i] = pd.Jd[o * P * P + i]; C.a[i] = pd.Ju[o * P * P + i]; }
+        for (int r = 0; r < R; ++r) {
+            Mat<P> A, Bm, C; Vec<P> d;
+            A.a[0] = ra[r]; Bm.a[0] = rb[r]; C.a[0] = rc[r]; d.a[0] = rd[r];
+            th.row(r, A, Bm, C, d);
+        }
+    } else {
 #pragma unroll
-        for (int i = 0; i < P; ++i) d.a[i] = pd.F[o * P + i];
-        th.row(r, A, Bm, C, d);
+        for (int r = 0; r < R; ++r) {
+            const size_t o = (size_t)k * pd.L + (size_t)r * TT + t;
+            Mat<P> A, Bm, C; Vec<P> d;
+#pragma unroll
+            for (int i = 0; i < P * P; ++i) { A.a[i] = pd.Jl[o * P * P + i]; Bm.a[i] = pd.Jd[o * P * P + i]; C.a[i] = pd.Ju[o * P * P + i]; }
+#pragma unroll
+            for (int i = 0; i < P; ++i) d.a[i] = pd.F[o * P + i];
+            th.row(r, A, Bm, C, d);
+        }
+        if (update) load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
     }
     Vec<P> h[R];
     th.template finish<TT>(h, sm, t);
     if (update) {
-        double uc[R][P];
-        load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
         update_and_test<P, R, TT>(pd, k, t, uc, h, tol, slot, sm);
     } else {  // debug: leave x in F
 #pragma unroll
