@@ -220,6 +220,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION/INFO; stdout carries the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
