@@ -251,6 +251,9 @@ def run_ours(args):
     def solve_resident():
         dev.rollback()
         dev.mass_flags(tg[0], stationary=stationary)
+        if not args.python_loop and not stationary:
+            dev.solve_steps(tg, tau, tol, maxit)
+            return
         for i in range(nsteps):
             tau_i = tau if tau is not None else tg[i + 1] - tg[i]
             dev.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)

@@ -207,6 +207,10 @@ int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active);
  * iters_done (may be NULL) = iterations launched.                                                */
 int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done);
 
+/* convenience: nsteps implicit-Euler steps (the time loop of src/pdepe.jl:90-108 driven from C; no state is
+ * stored in between).  tgrid[nsteps+1] is the time grid; tau > 0: constant time step, else tau_i = diff(tgrid).  */
+int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done);
+
 /* diagnostics (host arrays of length B unless stated)                                            */
 int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iterations this step  */
 int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */

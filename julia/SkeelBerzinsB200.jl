@@ -165,6 +165,25 @@ function history(pb, maxit)
     [h[1:it[k], k] for k in 1:B]
 end
 
+"""pdeval(m, xmesh, u_approx, x_eval, pb) (src/utils.jl:396-438) on the GPU: `(u, dudx)` as `[npde, nq, B]` arrays."""
+function pdeval(m, xmesh, u_approx, x_eval, pb::ProblemDefinition)
+    m == pb.m || error("The symmetry argument is different from the one used to solve the PDE problem.")
+    xq = collect(Float64, x_eval isa Number ? [x_eval] : x_eval)
+    B = batch(pb.pdefunction)
+    u = Array{Float64}(undef, pb.npde, length(xq), B); du = similar(u)
+    check(ccall((:sb_pdeval, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                pb.handle, u_approx, length(xq), xq, u, du))
+    u, du
+end
+
+"""Plugin slot: CUDA C++ source of a functor struct (see include/skeelberzins_b200.h) -> functor id for `Functor`."""
+function register_user_functor(cuda_source::AbstractString, struct_name::AbstractString, npde::Integer, nparams::Integer)
+    id = Ref{Cint}(0)
+    check(ccall((:sb_register_user_functor, libsb), Cint, (Ptr{Cvoid}, Cstring, Cstring, Cint, Cint, Ref{Cint}),
+                C_NULL, cuda_source, struct_name, npde, nparams, id))
+    Int(id[])
+end
+
 _merge(params, kwargs) = Params(; (f => get(kwargs, f, getfield(params, f)) for f in fieldnames(Params))...)
 
 """Transient pdepe (src/pdepe.jl:42-128) for the batch.  Returns `(u = Vector of [npde*Nx, B] states, t = grid)`

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sb_poll_active": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_c.c_int64)]),
     "sb_wait_iteration": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_c.c_int64)]),
     "sb_newton_solve": (_c.c_int, [_vp, _c.c_double, _c.c_int, _c.POINTER(_c.c_int)]),
+    "sb_solve_steps": (_c.c_int, [_vp, _c.c_int, _vp, _c.c_double, _c.c_double, _c.c_int, _c.POINTER(_c.c_int)]),
     "sb_get_step_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_total_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_last_norm": (_c.c_int, [_vp, _vp]),
@@ -81,8 +82,16 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError("%s not built: run `python skeelberzins.jl_b200/build.py` "
-                              "(there is no CPU fallback)" % LIB_PATH)
+            # not a fallback: the only implementation is the CUDA library; build it in-tree if nvcc is here
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("_sb_build", os.path.join(HERE, "build.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.build()
+            except Exception as exc:
+                raise ImportError("%s is not built and building it failed (%s): run `python "
+                                  "skeelberzins.jl_b200/build.py` (there is no CPU fallback)" % (LIB_PATH, exc))
         lib = _c.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

@@ -318,6 +318,17 @@ class DeviceProblem:
         _lib.check(rc)
         return it.value
 
+    def solve_steps(self, tgrid, tau, tol, maxit):
+        """C-side time loop over the grid (no snapshots in between); raises ConvergenceFailed like the reference."""
+        tg = np.ascontiguousarray(tgrid, dtype=np.float64)
+        done = ctypes.c_int()
+        rc = self.lib.sb_solve_steps(self._h, tg.size - 1, _lib.ptr(tg), float(tau) if tau is not None else -1.0,
+                                     float(tol), int(maxit), ctypes.byref(done))
+        if rc == _lib.SB_ERR_CONVERGENCE:
+            raise ConvergenceFailed("convergence failed")
+        _lib.check(rc)
+        return done.value
+
     def _get(self, fn, dtype):
         out = np.empty(self.B, dtype=dtype)
         _lib.check(fn(self._h, _lib.ptr(out)))
@@ -725,7 +736,12 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     dev.mass_flags(timeSteps[0])                               # src/pdepe.jl:78-79
     results = [shape(inival.reshape(B, Nx, npde))] if save == "all" else []
     storage = []
-    for i in range(timeSteps.size - 1):                        # src/pdepe.jl:90
+    if save != "all" and not params.hist and c_loop and timeSteps.size > 1:
+        dev.solve_steps(timeSteps, tau, params.tol, params.maxit)        # same loop, driven from C
+        timeSteps_loop = timeSteps[:1]
+    else:
+        timeSteps_loop = timeSteps
+    for i in range(timeSteps_loop.size - 1):                   # src/pdepe.jl:90
         time_val = timeSteps[i + 1]
         tstep_val = tau if tau is not None else timeSteps[i + 1] - timeSteps[i]
         h = newton(pb, tstep_val, time_val, params.tol, params.maxit, params.hist, c_loop)      # :94-96

@@ -1258,6 +1258,20 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
     return SB_OK;
 }
 
+int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done) {
+    if (!pb || !tgrid || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
+    if (steps_done) *steps_done = 0;
+    for (int i = 0; i < nsteps; ++i) {                                    // src/pdepe.jl:90
+        const double tau_i = (tau > 0) ? tau : tgrid[i + 1] - tgrid[i];  // :92 (scalar tstep | diff of the vector grid)
+        int rc = sb_begin_step(pb, tgrid[i + 1], std::isinf(tau_i) ? 0.0 : 1.0 / tau_i);
+        if (rc) return rc;
+        rc = sb_newton_solve(pb, tol, maxit, nullptr);
+        if (rc) return rc;
+        if (steps_done) *steps_done = i + 1;
+    }
+    return SB_OK;
+}
+
 #define SB_GET(NAME, TYPE, DEVPTR)                                                                       \
     int NAME(sb_problem* pb, TYPE* host) {                                                               \
         if (!pb || !host) return fail(SB_ERR_INVALID, "NULL argument");                                  \
