@@ -188,7 +188,16 @@ struct sb_ctx {
     int device;
     cudaStream_t stream;
     bool own_stream;
+    int refs;   // the creator's reference + one per live problem: a context outlives its problems whatever the order
+                // in which a garbage-collected host language finalises the two handles
 };
+
+static void ctx_unref(sb_ctx* ctx) {
+    if (--ctx->refs > 0) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
 
 struct sb_problem {
     sb_ctx* ctx;
@@ -568,6 +577,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
         return fail(SB_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
     sb_ctx* c = new sb_ctx;
     c->device = device;
+    c->refs = 1;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
         cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -580,9 +590,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
 
 int sb_ctx_destroy(sb_ctx* ctx) {
     if (!ctx) return SB_OK;
-    cudaSetDevice(ctx->device);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    ctx_unref(ctx);   // destroyed once the last problem created on it is gone
     return SB_OK;
 }
 
@@ -669,12 +677,14 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     CU(cudaSetDevice(ctx->device));
 
     sb_problem* pb = new sb_problem;
+    ctx->refs++;
     pb->ctx = ctx; pb->fe = fe; pb->P = f_npde; pb->nparams = f_nparams; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
     pb->dec = pick_decomposition(Nx, pb->P);
     if (getenv("SB_FORCE_LONGMESH") && pb->P == 1) pb->dec = -1;   // testing: long-mesh path on short meshes
     int R, T, ntiles = 1;
     if (pb->dec < 0) {
         if (pb->P != 1) {
+            ctx->refs--;
             delete pb;
             return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) for npde = %d; the long-mesh "
                         "path handles scalar PDEs only", Nx, kMaxBlockT * 8, f_npde);
@@ -830,6 +840,7 @@ int sb_problem_destroy(sb_problem* pb) {
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
+    ctx_unref(pb->ctx);
     delete pb;
     return SB_OK;
 }
