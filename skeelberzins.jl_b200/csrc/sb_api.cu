@@ -54,7 +54,8 @@ long long g_launches = 0;  // kernels launched by this library (all contexts; no
 struct KernelSet {
     const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr;
     const void *long_chunk = nullptr, *long_back = nullptr, *long_assemble_jac = nullptr, *long_assemble_val = nullptr;
-    size_t fused_p_smem = 0;
+    size_t fused_p_smem = 0, long_smem = 0;
+    bool long_configured = false;
     cudaLibrary_t lib = nullptr;  // owner of the run-time compiled kernels (user functors)
 };
 
@@ -379,6 +380,11 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_fused_p_smem = sb::FusedPLayout<%s, %d, %d, %s>::bytes;\n",
              uf.name.c_str(), R, TT, sym);
     src += buf;
+    if (longmesh) {
+        snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_long_smem = sb::LongStage<%s, %d, %d, %s>::bytes;\n",
+                 uf.name.c_str(), R, TT, sym);
+        src += buf;
+    }
     snprintf(buf, sizeof buf, "static_assert(%s::npde == %d && %s::nparams == %d, \"npde/nparams differ from the registration\");\n",
              uf.name.c_str(), uf.npde, uf.name.c_str(), uf.nparams);
     src += buf;
@@ -450,6 +456,12 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "reading the shared-memory size of the compiled kernel: %s", cudaGetErrorString(e));
     ks.fused_p_smem = (size_t)smem;
+    if (pb->longmesh) {
+        e = cudaLibraryGetGlobal(&dptr, &bytes, ks.lib, "sb_user_long_smem");
+        if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "reading the shared-memory size of the compiled long-mesh kernels: %s", cudaGetErrorString(e));
+        ks.long_smem = (size_t)smem;
+    }
     return SB_OK;
 }
 
@@ -485,7 +497,8 @@ int longmesh_setup(sb_problem* pb) {
                      lv[l].x = p; p += lv[l].stride * B; }
         if (lv[l].cstride) { lv[l].chunk = p; p += 10 * lv[l].cstride * B; }
     }
-    CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * pb->pd.ntiles * sizeof(double)));
+    CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
+    lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;
     pb->lv = lv;
     const int ntop = lv.back().n;
     pb->top_R = 1;
@@ -505,7 +518,15 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
     const unsigned B = (unsigned)pb->pd.B;
     std::vector<LevelDev>& lv = pb->lv;
     const int top = (int)lv.size() - 1;
-    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongTT), 0, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
+    const size_t smem = pb->ks.long_smem;
+    if (!pb->ks.long_configured) {  // one-time opt-in to the staged tiles' shared memory
+        if (smem > 48 * 1024) {
+            CU(cudaFuncSetAttribute(pb->ks.long_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(pb->ks.long_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        pb->ks.long_configured = true;
+    }
+    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongTT), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
     for (int l = 0; l < top; ++l) {
         if (l > 0) { k6_chunk_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], pb->d_active); ++g_launches; }
         k6_form<kLongR, kLongTT><<<dim3((unsigned)((lv[l].cstride + 255) / 256), B), 256, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
@@ -523,10 +544,9 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         k6_back_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
         ++g_launches;
     }
-    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongTT), 0, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
-    k6_commit<0><<<dim3((unsigned)((pb->pd.L + 255) / 256), B), 256, 0, st>>>(pb->pd, pb->d_active);
-    k6_finalize<0><<<1, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
-    g_launches += 2;
+    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongTT), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
+    k6_finalize<0><<<B, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
+    ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
 }
@@ -816,6 +836,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         ks.fused_p_smem = fe->fused_p_smem[pb->dec][pb->sym0];
         ks.long_chunk = (const void*)fe->long_chunk[pb->sym0];
         ks.long_back = (const void*)fe->long_back[pb->sym0];
+        ks.long_smem = fe->long_smem[pb->sym0];
         ks.long_assemble_jac = (const void*)fe->long_assemble_jac[pb->sym0];
         ks.long_assemble_val = (const void*)fe->long_assemble_val[pb->sym0];
     } else {

@@ -40,6 +40,7 @@ struct FunctorEntry {
     // long-mesh path (scalar PDEs): [SYM0]
     LongChunkKernel long_chunk[2];
     LongBackKernel long_back[2];
+    size_t long_smem[2];                      // dynamic shared memory of long_chunk / long_back (bytes)
     AssembleKernel long_assemble_jac[2], long_assemble_val[2];
 };
 
@@ -77,12 +78,13 @@ FunctorEntry make_entry(const char* name) {
     if constexpr (Fn::npde == 1) {
         e.long_chunk[0] = k6_chunk_asm<Fn, kLongR, kLongTT, false>; e.long_chunk[1] = k6_chunk_asm<Fn, kLongR, kLongTT, true>;
         e.long_back[0] = k6_back_asm<Fn, kLongR, kLongTT, false>; e.long_back[1] = k6_back_asm<Fn, kLongR, kLongTT, true>;
+        e.long_smem[0] = LongStage<Fn, kLongR, kLongTT, false>::bytes; e.long_smem[1] = LongStage<Fn, kLongR, kLongTT, true>::bytes;
         e.long_assemble_jac[0] = k6_assemble<Fn, kLongR, kLongTT, false, true>;
         e.long_assemble_jac[1] = k6_assemble<Fn, kLongR, kLongTT, true, true>;
         e.long_assemble_val[0] = k6_assemble<Fn, kLongR, kLongTT, false, false>;
         e.long_assemble_val[1] = k6_assemble<Fn, kLongR, kLongTT, true, false>;
     } else {
-        for (int s = 0; s < 2; ++s) { e.long_chunk[s] = nullptr; e.long_back[s] = nullptr; e.long_assemble_jac[s] = nullptr; e.long_assemble_val[s] = nullptr; }
+        for (int s = 0; s < 2; ++s) { e.long_chunk[s] = nullptr; e.long_back[s] = nullptr; e.long_smem[s] = 0; e.long_assemble_jac[s] = nullptr; e.long_assemble_val[s] = nullptr; }
     }
     return e;
 }
