@@ -466,50 +466,55 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
 }
 
 // ---- long-mesh path (K6, sb_longmesh.cuh) -------------------------------------------------------
-constexpr int kLongLt = kLongR * kLongTT;
 constexpr int kLongTopRows = 16 * kLongTT;  // the top level is solved by one CTA of kLongTT threads, <= 16 rows each
 
 int longmesh_setup(sb_problem* pb) {
     const int64_t B = pb->pd.B;
     std::vector<LevelDev> lv;
-    size_t total = 0;  // doubles
     int n = pb->pd.Nx;
     for (int l = 0;; ++l) {
         LevelDev L;
         memset(&L, 0, sizeof L);
         L.n = n;
-        L.ntiles = (n + kLongLt - 1) / kLongLt;
-        L.stride = (size_t)L.ntiles * kLongLt;
         const bool top = (l > 0 && n <= kLongTopRows);
-        L.cstride = top ? 0 : (size_t)L.ntiles * kLongTT;
+        if (top) { L.R = 1; while (L.R * kLongTT < n) L.R *= 2; }
+        else L.R = (l == 0) ? kLongR : kLongRS;
+        const int tt = (l == 0) ? kLongT0 : kLongTT;
+        L.ntiles = (n + L.R * tt - 1) / (L.R * tt);
+        L.stride = (size_t)L.ntiles * L.R * tt;
+        L.nchunks = L.ntiles * tt;                   // every chunk (padding chunks included) is a row of the next level
         lv.push_back(L);
-        if (l > 0) total += 4 * L.stride * B;      // a, c, d, x
-        total += 10 * L.cstride * B;               // chunk summaries
         if (top) break;
-        n = (int)L.cstride;
+        n = L.nchunks;
         if (l > 12) return fail(SB_ERR_UNSUPPORTED, "long-mesh recursion too deep");
     }
+    if (lv[0].ntiles != pb->pd.ntiles) return fail(SB_ERR_INVALID, "long-mesh tiling mismatch");
+    size_t total = 0;  // doubles
+    for (size_t l = 0; l < lv.size(); ++l) {
+        if (l > 0) total += (l + 1 < lv.size() ? 4 : 1) * lv[l].stride * B;   // a, c, d, x (top: x only)
+        if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += 7 * lv[l].up_stride * B; }
+    }
     CU(cudaMalloc((void**)&pb->d_lm, total * sizeof(double)));
-    CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));   // padding rows of every level stay (0, 1, 0 | 0)
+    CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));
     double* p = pb->d_lm;
     for (size_t l = 0; l < lv.size(); ++l) {
-        if (l > 0) { lv[l].a = p; p += lv[l].stride * B; lv[l].c = p; p += lv[l].stride * B; lv[l].d = p; p += lv[l].stride * B;
-                     lv[l].x = p; p += lv[l].stride * B; }
-        if (lv[l].cstride) { lv[l].chunk = p; p += 10 * lv[l].cstride * B; }
+        if (l > 0) {
+            if (l + 1 < lv.size()) { lv[l].a = p; p += lv[l].stride * B; lv[l].c = p; p += lv[l].stride * B; lv[l].d = p; p += lv[l].stride * B; }
+            lv[l].x = p; p += lv[l].stride * B;
+        }
+        if (l + 1 < lv.size()) { lv[l].sum = p; p += 7 * lv[l].up_stride * B; }
     }
     CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
     lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;
     pb->lv = lv;
-    const int ntop = lv.back().n;
-    pb->top_R = 1;
-    while (pb->top_R * kLongTT < ntop) pb->top_R *= 2;
+    pb->top_R = lv.back().R;
     return SB_OK;
 }
 
 template <int RT>
-void launch_top(sb_problem* pb, const LevelDev& top) {
+void launch_top(sb_problem* pb, const LevelDev& top, const LevelDev& below) {
     const size_t smem = (size_t)(2 * 3 + 1) * kLongTT * sizeof(double);
-    k6_top<RT, kLongTT><<<(unsigned)pb->pd.B, kLongTT, smem, pb->ctx->stream>>>(top, pb->d_active);
+    k6_top<RT, kLongTT><<<(unsigned)pb->pd.B, kLongTT, smem, pb->ctx->stream>>>(top, below, pb->d_active);
 }
 
 // one Newton iteration of the long-mesh path; publishes the active count like the batched kernels
@@ -526,25 +531,24 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         }
         pb->ks.long_configured = true;
     }
-    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongTT), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
-    for (int l = 0; l < top; ++l) {
-        if (l > 0) { k6_chunk_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], pb->d_active); ++g_launches; }
-        k6_form<kLongR, kLongTT><<<dim3((unsigned)((lv[l].cstride + 255) / 256), B), 256, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
+    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
+    for (int l = 1; l < top; ++l) {
+        k6_chunk_sys<kLongRS, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l - 1], pb->d_active);
         ++g_launches;
     }
     switch (pb->top_R) {
-        case 1: launch_top<1>(pb, lv[top]); break;
-        case 2: launch_top<2>(pb, lv[top]); break;
-        case 4: launch_top<4>(pb, lv[top]); break;
-        case 8: launch_top<8>(pb, lv[top]); break;
-        default: launch_top<16>(pb, lv[top]); break;
+        case 1: launch_top<1>(pb, lv[top], lv[top - 1]); break;
+        case 2: launch_top<2>(pb, lv[top], lv[top - 1]); break;
+        case 4: launch_top<4>(pb, lv[top], lv[top - 1]); break;
+        case 8: launch_top<8>(pb, lv[top], lv[top - 1]); break;
+        default: launch_top<16>(pb, lv[top], lv[top - 1]); break;
     }
     ++g_launches;
     for (int l = top - 1; l >= 1; --l) {
-        k6_back_sys<kLongR, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
+        k6_back_sys<kLongRS, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
         ++g_launches;
     }
-    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongTT), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
+    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
     k6_finalize<0><<<B, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
     ++g_launches;
     CU(cudaGetLastError());
@@ -630,7 +634,7 @@ int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_b
     int R, TT;
     if (dec < 0) {
         if (uf.npde != 1) return fail(SB_ERR_UNSUPPORTED, "Nx = %d: long meshes need npde = 1", Nx);
-        longmesh = true; R = kLongR; TT = kLongTT;
+        longmesh = true; R = kLongR; TT = kLongT0;
     } else { R = kDecomp[dec].R; TT = kDecomp[dec].TT; }
     std::vector<char> cubin;
     std::vector<std::string> lowered;
@@ -710,7 +714,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
                         "path handles scalar PDEs only", Nx, kMaxBlockT * 8, f_npde);
         }
         pb->longmesh = true;
-        R = kLongR; T = kLongTT;
+        R = kLongR; T = kLongT0;
         ntiles = (Nx + R * T - 1) / (R * T);
         for (int d = 0; d < kNumDecomp; ++d) if (kDecomp[d].R == R && kDecomp[d].TT == T) pb->dec = d;
     } else {
@@ -971,7 +975,7 @@ int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host)
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     cudaError_t e;
-    if (pb->longmesh) e = launch_any(pb->ks.long_assemble_val, dim3(pd.ntiles, (unsigned)pd.B), dim3(kLongTT), 0, pb->ctx->stream, pd, t, 0.0, 1);
+    if (pb->longmesh) e = launch_any(pb->ks.long_assemble_val, dim3(pd.ntiles, (unsigned)pd.B), dim3(kLongT0), 0, pb->ctx->stream, pd, t, 0.0, 1);
     else e = launch_any(pb->ks.assemble_val, grid, block, 0, pb->ctx->stream, pd, t, 0.0, 1);
     if (e == cudaSuccess) e = cudaGetLastError();
     int rc = SB_OK;
@@ -1148,7 +1152,7 @@ int sb_residual_jacobian(sb_problem* pb) {
     const int ps = (int)(pb->launched % kSlots);
     if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
     if (pb->longmesh)
-        CU(launch_any(pb->ks.long_assemble_jac, dim3(pb->pd.ntiles, (unsigned)pb->pd.B), dim3(kLongTT), 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
+        CU(launch_any(pb->ks.long_assemble_jac, dim3(pb->pd.ntiles, (unsigned)pb->pd.B), dim3(kLongT0), 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
     else
         CU(launch_any(pb->ks.assemble_jac, grid, block, 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
     CU(cudaGetLastError());

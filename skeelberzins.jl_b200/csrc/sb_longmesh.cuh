@@ -5,10 +5,10 @@
 // ("SPIKE") solve over levels:
 //
 //   level 0   k6_chunk_asm   every thread assembles its R rows on the fly (residual + Jacobian by duals, nothing
-//                            but u, b and the mesh weights is read) and eliminates them -> 10 numbers per chunk
-//             k6_form        reduced row of every chunk separator = row of the level-1 tridiagonal system
-//   level l   k6_chunk_sys   the same elimination on the stored rows of level l        -> level l+1 ...
-//   top       k6_top         a single CTA solves the last level (<= 4096 rows) with the batched-path solver
+//                            but u, b and the mesh weights is read) and eliminates them -> 7 numbers per chunk
+//   level l   k6_chunk_sys   forms its rows (one per chunk of level l-1) from those numbers, keeps them for the way
+//                            back, eliminates them                                        -> level l+1 ...
+//   top       k6_top         a single CTA forms and solves the last level (<= 4096 rows) with the batched-path solver
 //   level l   k6_back_sys    recompute the elimination, back-substitute with the separator values from level l+1
 //   level 0   k6_back_asm    recompute assembly + elimination, back-substitute, u -= h in place, per-tile sum of h^2
 //             k6_finalize    ||h||_2 per instance in a fixed summation order, stop test, counters, host notice
@@ -20,16 +20,22 @@
 
 namespace sb {
 
-constexpr int kLongR = 8, kLongTT = 256;  // decomposition of every level of the long-mesh path
+constexpr int kLongR = 8, kLongT0 = 128;  // level 0: rows per thread / threads per tile (tile = 1024 mesh nodes)
+constexpr int kLongTT = 256;              // stored levels and the top level: threads per tile
+constexpr int kLongRS = 16;               // stored levels (1 .. top-1): rows per thread = reduction factor per level
 
 struct LevelDev {      // one level of the recursive partition (level 0 has no stored rows: they are assembled)
     int n;             // rows
-    int ntiles;        // tiles of kLongR*kLongTT rows
-    size_t stride;     // doubles per instance in a, c, d, x  (= ntiles * kLongR * kLongTT)
-    size_t cstride;    // chunks per instance (= ntiles * kLongTT)
-    double *a, *c, *d; // normalised rows (unit diagonal) in tiled layout
-    double* x;         // solution of the level in tiled layout
-    double* chunk;     // [B][10][cstride]: y0 v0 w0 yL vL wL As Bs Cs ds of every chunk
+    int R;             // rows per thread in this level's tiled layout (level 0: kLongR, top: 1..16, else kLongRS)
+    int ntiles;        // tiles of R * (kLongT0 | kLongTT) rows
+    int nchunks;       // chunks of the level = rows of the next one (padding chunks included)
+    size_t stride;     // padded rows per instance (= ntiles * R * kLongTT)
+    double *a, *c, *d; // levels >= 1: normalised rows (unit diagonal) [B][stride], kept for the backward sweep
+    double* x;         // levels >= 1: solution of the level [B][stride]
+    double* sum;       // levels < top: [B][7][up_stride] chunk summaries y0 v0 w0 | ar bp Cs dp, each stored at the
+                       // position of the row it becomes in the next level's tiled layout
+    size_t up_stride;  // stride of the next level
+    int up_R;          // R of the next level
     double* edge;      // levels 0 and 1 only: [B][2*ntiles0 + 2] iterate at the first / last node of every level-0 tile
                        // and at mesh nodes 0 and Nx-1, saved by the forward sweep so that the backward sweep can
                        // update u in place (a tile's neighbours may already hold the new iterate)
@@ -41,14 +47,62 @@ SB_D size_t tiled_pos(int j, int R, int TT) {
     return (size_t)tile * Lt + (size_t)(il % R) * TT + il / R;
 }
 
-template <int R>
-SB_D void store_chunk(const ChunkThomas<1, R>& th, double* chunk, size_t cstride, size_t c) {
+// summary of the chunk of thread t of tile `tile` of level `lv`: the first-row representation (y0, v0, w0) and the
+// separator row with the chunk's own interior eliminated (ar, bp, Cs, dp); the next level combines it with the next
+// chunk into a reduced row.  The 256 chunks of a tile land, in the next level's tiled layout, in up_R runs of
+// 256/up_R consecutive positions: the values are transposed through shared memory (buf: 7*TT doubles, free to
+// overwrite after the barrier) so that consecutive threads write consecutive addresses.
+template <int R, int TT>
+SB_D void store_summary(const ChunkThomas<1, R>& th, const LevelDev& lv, int64_t k, int tile, int t, double* buf) {
     Vec<1> y0, yL; Mat<1> v0, w0, vL, wL;
     th.summary(y0, v0, w0, yL, vL, wL);
-    chunk[0 * cstride + c] = y0.a[0]; chunk[1 * cstride + c] = v0.a[0]; chunk[2 * cstride + c] = w0.a[0];
-    chunk[3 * cstride + c] = yL.a[0]; chunk[4 * cstride + c] = vL.a[0]; chunk[5 * cstride + c] = wL.a[0];
-    chunk[6 * cstride + c] = th.As.a[0]; chunk[7 * cstride + c] = th.Bs.a[0]; chunk[8 * cstride + c] = th.Cs.a[0];
-    chunk[9 * cstride + c] = th.ds.a[0];
+    const double As = th.As.a[0];
+    __syncthreads();
+    buf[0 * TT + t] = y0.a[0]; buf[1 * TT + t] = v0.a[0]; buf[2 * TT + t] = w0.a[0];
+    buf[3 * TT + t] = -(As * vL.a[0]);
+    buf[4 * TT + t] = fma(-As, wL.a[0], th.Bs.a[0]);
+    buf[5 * TT + t] = th.Cs.a[0];
+    buf[6 * TT + t] = fma(-As, yL.a[0], th.ds.a[0]);
+    __syncthreads();
+    const int run = TT / lv.up_R;                 // up_R is a power of two <= 16
+    const int ts = (t % run) * lv.up_R + t / run; // the chunk whose position follows that of thread t-1's chunk
+    const size_t us = lv.up_stride;
+    double* S = lv.sum + (size_t)k * 7 * us + tiled_pos(tile * TT + ts, lv.up_R, kLongTT);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) S[i * us] = buf[i * TT + ts];
+}
+
+// rows j0 .. j0+R-1 of the level above `below` (thread t of tile `tile` in that level's (R, TT) layout) from the
+// summaries of chunks j and j+1 of `below`; rows beyond the n chunks of `below` are identity rows.  All loads are
+// issued before anything is stored, so one DRAM latency covers the thread's R rows.
+template <int R, int TT>
+SB_D void form_rows(const LevelDev& below, int64_t k, int tile, int t, double (&ra)[R], double (&rc)[R], double (&rd)[R]) {
+    const int n = below.nchunks;
+    const size_t us = below.up_stride;
+    const double* S = below.sum + (size_t)k * 7 * us;
+    const int j0 = (tile * TT + t) * R;
+    const size_t p0 = (size_t)tile * R * TT + t;
+    // first-row representation of the chunk after the thread's last one
+    const size_t pl = (t + 1 < TT) ? (size_t)tile * R * TT + (t + 1) : (size_t)(tile + 1) * R * TT;
+    double y0[R + 1], v0[R + 1], w0[R + 1];
+#pragma unroll
+    for (int r = 0; r <= R; ++r) {
+        const size_t p = (r < R) ? p0 + (size_t)r * TT : pl;
+        const bool in = j0 + r < n;
+        y0[r] = in ? __ldg(S + 0 * us + p) : 0.0; v0[r] = in ? __ldg(S + 1 * us + p) : 0.0; w0[r] = in ? __ldg(S + 2 * us + p) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        ra[r] = 0.0; rc[r] = 0.0; rd[r] = 0.0;
+        if (j0 + r < n) {
+            const size_t p = p0 + (size_t)r * TT;
+            const double ar = __ldg(S + 3 * us + p), bp = __ldg(S + 4 * us + p), Cs = __ldg(S + 5 * us + p), dp = __ldg(S + 6 * us + p);
+            const double binv = fast_rcp(fma(-Cs, v0[r + 1], bp));
+            ra[r] = binv * ar;
+            rc[r] = -(binv * (Cs * w0[r + 1]));
+            rd[r] = binv * fma(-Cs, y0[r + 1], dp);
+        }
+    }
 }
 
 // mesh weight pointers of one tile
@@ -146,83 +200,58 @@ __global__ void __launch_bounds__(TT) k6_chunk_asm(ProbDev pd, double tt, double
     assemble_chunk<Fn, R, TT, SYM0, true, !SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
                                                  pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui,
                                                  ui + tiled_pos(pd.Nx - 1, R, TT));
-    store_chunk<R>(th, lv.chunk + (size_t)k * 10 * lv.cstride, lv.cstride, (size_t)tile * TT + t);
+    store_summary<R, TT>(th, lv, k, tile, t, k6sm + 2);
 }
 
-// reduced separator rows of level `lv` -> rows of the next level `up` (tiled layout of the next level)
-template <int RN, int TTN>
-__global__ void k6_form(LevelDev lv, LevelDev up, const int* active) {
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k = blockIdx.y;
-    if (c >= lv.cstride || !active[k]) return;
-    const double* ch = lv.chunk + (size_t)k * 10 * lv.cstride;
-    const size_t cs = lv.cstride;
-    Vec<1> yL, y0n, ds, dn; Mat<1> vL, wL, v0n, w0n, As, Bs, Cs, an, cn;
-    yL.a[0] = ch[3 * cs + c]; vL.a[0] = ch[4 * cs + c]; wL.a[0] = ch[5 * cs + c];
-    As.a[0] = ch[6 * cs + c]; Bs.a[0] = ch[7 * cs + c]; Cs.a[0] = ch[8 * cs + c]; ds.a[0] = ch[9 * cs + c];
-    const bool nx = c + 1 < cs;
-    y0n.a[0] = nx ? ch[0 * cs + c + 1] : 0.0; v0n.a[0] = nx ? ch[1 * cs + c + 1] : 0.0; w0n.a[0] = nx ? ch[2 * cs + c + 1] : 0.0;
-    ChunkThomas<1, 1>::reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
-    const size_t pos = (size_t)k * up.stride + tiled_pos((int)c, RN, TTN);
-    up.a[pos] = an.a[0]; up.c[pos] = cn.a[0]; up.d[pos] = dn.a[0];
-}
-
+// level l >= 1, forward: form the level's rows, keep them, eliminate, store the chunk summary
 template <int R, int TT>
-SB_D void load_sys_rows(const LevelDev& lv, int64_t k, int tile, int t, ChunkThomas<1, R>& th) {
-    const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const size_t o = base + (size_t)r * TT + t;
-        Mat<1> A, Bm, C; Vec<1> d;
-        A.a[0] = lv.a[o]; Bm.a[0] = 1.0; C.a[0] = lv.c[o]; d.a[0] = lv.d[o];
-        th.row(r, A, Bm, C, d);
-    }
-}
-
-// level l >= 1, forward
-template <int R, int TT>
-__global__ void __launch_bounds__(TT) k6_chunk_sys(LevelDev lv, const int* active) {
+__global__ void __launch_bounds__(TT) k6_chunk_sys(LevelDev lv, LevelDev below, const int* active) {
+    __shared__ double buf[7 * TT];
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
+    double ra[R], rc[R], rd[R];
+    form_rows<R, TT>(below, k, tile, t, ra, rc, rd);
     ChunkThomas<1, R> th;
-    load_sys_rows<R, TT>(lv, k, tile, t, th);
-    store_chunk<R>(th, lv.chunk + (size_t)k * 10 * lv.cstride, lv.cstride, (size_t)tile * TT + t);
+    const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT + t;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        lv.a[base + (size_t)r * TT] = ra[r]; lv.c[base + (size_t)r * TT] = rc[r]; lv.d[base + (size_t)r * TT] = rd[r];
+        Mat<1> A, Bm, C; Vec<1> d;
+        A.a[0] = ra[r]; Bm.a[0] = 1.0; C.a[0] = rc[r]; d.a[0] = rd[r];
+        th.row(r, A, Bm, C, d);
+    }
+    store_summary<R, TT>(th, lv, k, tile, t, buf);
 }
 
-// top level: one CTA per instance, rows fit one tile of RT*TT rows
+// top level: one CTA per instance forms its rows (RT per thread, one tile) and solves them
 template <int RT, int TT>
-__global__ void __launch_bounds__(TT) k6_top(LevelDev lv, const int* active) {
+__global__ void __launch_bounds__(TT) k6_top(LevelDev lv, LevelDev below, const int* active) {
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     const int64_t k = blockIdx.x;
     if (!active[k]) return;
+    double ra[RT], rc[RT], rd[RT];
+    form_rows<RT, TT>(below, k, 0, t, ra, rc, rd);
     ChunkThomas<1, RT> th;
-    const size_t base = (size_t)k * lv.stride;
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-        // the level is stored with the (kLongR, kLongTT) tiling; the top solver owns rows t*RT .. t*RT+RT-1
-        const int j = t * RT + r;
-        const size_t o = base + tiled_pos(j, kLongR, kLongTT);
         Mat<1> A, Bm, C; Vec<1> d;
-        const bool in = j < lv.n;
-        A.a[0] = in ? lv.a[o] : 0.0; Bm.a[0] = 1.0; C.a[0] = in ? lv.c[o] : 0.0; d.a[0] = in ? lv.d[o] : 0.0;
+        A.a[0] = ra[r]; Bm.a[0] = 1.0; C.a[0] = rc[r]; d.a[0] = rd[r];
         th.row(r, A, Bm, C, d);
     }
     Vec<1> x[RT];
     th.template finish<TT>(x, sm, t);
+    double* xo = lv.x + (size_t)k * lv.stride;
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-        const int j = t * RT + r;
-        if (j < lv.n) lv.x[base + tiled_pos(j, kLongR, kLongTT)] = x[r].a[0];
-    }
+    for (int r = 0; r < RT; ++r) xo[(size_t)r * TT + t] = x[r].a[0];
 }
 
 // separator unknowns of chunk c (own and previous) from the solution of the next level
-SB_D void separators(const LevelDev& up, int64_t k, size_t c, Vec<1>& xp, Vec<1>& xs) {
+SB_D void separators(const LevelDev& up, int64_t k, int c, Vec<1>& xp, Vec<1>& xs) {
     const double* xu = up.x + (size_t)k * up.stride;
-    xs.a[0] = xu[tiled_pos((int)c, kLongR, kLongTT)];
-    xp.a[0] = (c > 0) ? xu[tiled_pos((int)c - 1, kLongR, kLongTT)] : 0.0;
+    xs.a[0] = xu[tiled_pos(c, up.R, kLongTT)];
+    xp.a[0] = (c > 0) ? xu[tiled_pos(c - 1, up.R, kLongTT)] : 0.0;
 }
 
 // level l >= 1, backward
@@ -232,11 +261,17 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     ChunkThomas<1, R> th;
-    load_sys_rows<R, TT>(lv, k, tile, t, th);
-    Vec<1> xp, xs, x[R];
-    separators(up, k, (size_t)tile * TT + t, xp, xs);
-    th.back(x, xp, xs);
     const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const size_t o = base + (size_t)r * TT + t;
+        Mat<1> A, Bm, C; Vec<1> d;
+        A.a[0] = lv.a[o]; Bm.a[0] = 1.0; C.a[0] = lv.c[o]; d.a[0] = lv.d[o];
+        th.row(r, A, Bm, C, d);
+    }
+    Vec<1> xp, xs, x[R];
+    separators(up, k, tile * TT + t, xp, xs);
+    th.back(x, xp, xs);
 #pragma unroll
     for (int r = 0; r < R; ++r) lv.x[base + (size_t)r * TT + t] = x[r].a[0];
 }
@@ -279,7 +314,7 @@ __global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double 
                                                  pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff,
                                                  e + 2 * pd.ntiles, e + 2 * pd.ntiles + 1);
     Vec<1> xp, xs, h[R];
-    separators(up, k, (size_t)tile * TT + t, xp, xs);
+    separators(up, k, tile * TT + t, xp, xs);
     th.back(h, xp, xs);
     double ss = 0.0;
 #pragma unroll

@@ -76,13 +76,13 @@ FunctorEntry make_entry(const char* name) {
     fill_all<Fn>(e, std::make_integer_sequence<int, kNumDecomp>{});
     e.mass = k_mass_flags<Fn>;
     if constexpr (Fn::npde == 1) {
-        e.long_chunk[0] = k6_chunk_asm<Fn, kLongR, kLongTT, false>; e.long_chunk[1] = k6_chunk_asm<Fn, kLongR, kLongTT, true>;
-        e.long_back[0] = k6_back_asm<Fn, kLongR, kLongTT, false>; e.long_back[1] = k6_back_asm<Fn, kLongR, kLongTT, true>;
-        e.long_smem[0] = LongStage<Fn, kLongR, kLongTT, false>::bytes; e.long_smem[1] = LongStage<Fn, kLongR, kLongTT, true>::bytes;
-        e.long_assemble_jac[0] = k6_assemble<Fn, kLongR, kLongTT, false, true>;
-        e.long_assemble_jac[1] = k6_assemble<Fn, kLongR, kLongTT, true, true>;
-        e.long_assemble_val[0] = k6_assemble<Fn, kLongR, kLongTT, false, false>;
-        e.long_assemble_val[1] = k6_assemble<Fn, kLongR, kLongTT, true, false>;
+        e.long_chunk[0] = k6_chunk_asm<Fn, kLongR, kLongT0, false>; e.long_chunk[1] = k6_chunk_asm<Fn, kLongR, kLongT0, true>;
+        e.long_back[0] = k6_back_asm<Fn, kLongR, kLongT0, false>; e.long_back[1] = k6_back_asm<Fn, kLongR, kLongT0, true>;
+        e.long_smem[0] = LongStage<Fn, kLongR, kLongT0, false>::bytes; e.long_smem[1] = LongStage<Fn, kLongR, kLongT0, true>::bytes;
+        e.long_assemble_jac[0] = k6_assemble<Fn, kLongR, kLongT0, false, true>;
+        e.long_assemble_jac[1] = k6_assemble<Fn, kLongR, kLongT0, true, true>;
+        e.long_assemble_val[0] = k6_assemble<Fn, kLongR, kLongT0, false, false>;
+        e.long_assemble_val[1] = k6_assemble<Fn, kLongR, kLongT0, true, false>;
     } else {
         for (int s = 0; s < 2; ++s) { e.long_chunk[s] = nullptr; e.long_back[s] = nullptr; e.long_smem[s] = 0; e.long_assemble_jac[s] = nullptr; e.long_assemble_val[s] = nullptr; }
     }

@@ -272,7 +272,8 @@ def test_longmesh_transient_vs_oracle(ctx, oracle, monkeypatch, cfg, Nx, nsteps)
     fn = sb.Functor(c.functor, c.params)
     sol, hist, dev = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, hist=True, squeeze=False,
                               save="last", return_device=True)
-    assert dev.layout()["T"] == 256 and dev.info()["Nx"] == Nx
+    lay = dev.layout()
+    assert lay["R"] * lay["T"] < Nx and dev.info()["Nx"] == Nx          # tiled: the long-mesh path is in use
     r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None)
     err = np.abs(sol.u[-1] - r["u"][:, :, 0]).max(axis=1) / np.abs(r["u"][:, :, 0]).max(axis=1)
     assert err.max() < RTOL
