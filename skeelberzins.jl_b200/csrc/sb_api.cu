@@ -491,18 +491,18 @@ int longmesh_setup(sb_problem* pb) {
     if (lv[0].ntiles != pb->pd.ntiles) return fail(SB_ERR_INVALID, "long-mesh tiling mismatch");
     size_t total = 0;  // doubles
     for (size_t l = 0; l < lv.size(); ++l) {
-        if (l > 0) total += (l + 1 < lv.size() ? 4 : 1) * lv[l].stride * B;   // a, c, d, x (top: x only)
-        if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += 7 * lv[l].up_stride * B; }
+        if (l > 0) total += (l + 1 < lv.size() ? 5 : 1) * lv[l].stride * B;   // (a, c, d, -) records + x (top: x only)
+        if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += 8 * lv[l].up_stride * B; }
     }
     CU(cudaMalloc((void**)&pb->d_lm, total * sizeof(double)));
     CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));
     double* p = pb->d_lm;
     for (size_t l = 0; l < lv.size(); ++l) {
         if (l > 0) {
-            if (l + 1 < lv.size()) { lv[l].a = p; p += lv[l].stride * B; lv[l].c = p; p += lv[l].stride * B; lv[l].d = p; p += lv[l].stride * B; }
+            if (l + 1 < lv.size()) { lv[l].acd = reinterpret_cast<double2*>(p); p += 4 * lv[l].stride * B; }
             lv[l].x = p; p += lv[l].stride * B;
         }
-        if (l + 1 < lv.size()) { lv[l].sum = p; p += 7 * lv[l].up_stride * B; }
+        if (l + 1 < lv.size()) { lv[l].sum = reinterpret_cast<double2*>(p); p += 8 * lv[l].up_stride * B; }
     }
     CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
     lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;

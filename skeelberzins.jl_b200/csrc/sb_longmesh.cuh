@@ -30,10 +30,12 @@ struct LevelDev {      // one level of the recursive partition (level 0 has no s
     int ntiles;        // tiles of R * (kLongT0 | kLongTT) rows
     int nchunks;       // chunks of the level = rows of the next one (padding chunks included)
     size_t stride;     // padded rows per instance (= ntiles * R * kLongTT)
-    double *a, *c, *d; // levels >= 1: normalised rows (unit diagonal) [B][stride], kept for the backward sweep
+    double2* acd;      // levels 1 .. top-1: normalised rows (unit diagonal) [B][stride][(a, c), (d, -)], kept for the
+                       // backward sweep
     double* x;         // levels >= 1: solution of the level [B][stride]
-    double* sum;       // levels < top: [B][7][up_stride] chunk summaries y0 v0 w0 | ar bp Cs dp, each stored at the
-                       // position of the row it becomes in the next level's tiled layout
+    double2* sum;      // levels < top: [B][up_stride][(y0, v0), (w0, ar), (bp, Cs), (dp, -)] chunk summaries, each
+                       // stored at the position of the row it becomes in the next level's tiled layout.  One 64-byte
+                       // record per chunk (two full sectors), so the scattered positions cost no write amplification
     size_t up_stride;  // stride of the next level
     int up_R;          // R of the next level
     double* edge;      // levels 0 and 1 only: [B][2*ntiles0 + 2] iterate at the first / last node of every level-0 tile
@@ -47,61 +49,50 @@ SB_D size_t tiled_pos(int j, int R, int TT) {
     return (size_t)tile * Lt + (size_t)(il % R) * TT + il / R;
 }
 
-// summary of the chunk of thread t of tile `tile` of level `lv`: the first-row representation (y0, v0, w0) and the
-// separator row with the chunk's own interior eliminated (ar, bp, Cs, dp); the next level combines it with the next
-// chunk into a reduced row.  The 256 chunks of a tile land, in the next level's tiled layout, in up_R runs of
-// 256/up_R consecutive positions: the values are transposed through shared memory (buf: 7*TT doubles, free to
-// overwrite after the barrier) so that consecutive threads write consecutive addresses.
-template <int R, int TT>
-SB_D void store_summary(const ChunkThomas<1, R>& th, const LevelDev& lv, int64_t k, int tile, int t, double* buf) {
+// summary of chunk c of level `lv`: the first-row representation (y0, v0, w0) and the separator row with the
+// chunk's own interior eliminated (ar, bp, Cs, dp); the next level combines it with the next chunk into a reduced row
+template <int R>
+SB_D void store_summary(const ChunkThomas<1, R>& th, const LevelDev& lv, int64_t k, int c) {
     Vec<1> y0, yL; Mat<1> v0, w0, vL, wL;
     th.summary(y0, v0, w0, yL, vL, wL);
     const double As = th.As.a[0];
-    __syncthreads();
-    buf[0 * TT + t] = y0.a[0]; buf[1 * TT + t] = v0.a[0]; buf[2 * TT + t] = w0.a[0];
-    buf[3 * TT + t] = -(As * vL.a[0]);
-    buf[4 * TT + t] = fma(-As, wL.a[0], th.Bs.a[0]);
-    buf[5 * TT + t] = th.Cs.a[0];
-    buf[6 * TT + t] = fma(-As, yL.a[0], th.ds.a[0]);
-    __syncthreads();
-    const int run = TT / lv.up_R;                 // up_R is a power of two <= 16
-    const int ts = (t % run) * lv.up_R + t / run; // the chunk whose position follows that of thread t-1's chunk
-    const size_t us = lv.up_stride;
-    double* S = lv.sum + (size_t)k * 7 * us + tiled_pos(tile * TT + ts, lv.up_R, kLongTT);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) S[i * us] = buf[i * TT + ts];
+    double2* S = lv.sum + ((size_t)k * lv.up_stride + tiled_pos(c, lv.up_R, kLongTT)) * 4;
+    S[0] = make_double2(y0.a[0], v0.a[0]);
+    S[1] = make_double2(w0.a[0], -(As * vL.a[0]));
+    S[2] = make_double2(fma(-As, wL.a[0], th.Bs.a[0]), th.Cs.a[0]);
+    S[3] = make_double2(fma(-As, yL.a[0], th.ds.a[0]), 0.0);
 }
 
 // rows j0 .. j0+R-1 of the level above `below` (thread t of tile `tile` in that level's (R, TT) layout) from the
-// summaries of chunks j and j+1 of `below`; rows beyond the n chunks of `below` are identity rows.  All loads are
-// issued before anything is stored, so one DRAM latency covers the thread's R rows.
+// summaries of chunks j and j+1 of `below`; rows beyond the chunks of `below` are identity rows.  Branch-free: the
+// records of padding rows lie inside the zero-filled array and their results are discarded.
 template <int R, int TT>
 SB_D void form_rows(const LevelDev& below, int64_t k, int tile, int t, double (&ra)[R], double (&rc)[R], double (&rd)[R]) {
     const int n = below.nchunks;
-    const size_t us = below.up_stride;
-    const double* S = below.sum + (size_t)k * 7 * us;
+    const double2* S = below.sum + (size_t)k * below.up_stride * 4;
     const int j0 = (tile * TT + t) * R;
     const size_t p0 = (size_t)tile * R * TT + t;
-    // first-row representation of the chunk after the thread's last one
+    // record after the thread's last one: only its first-row representation is needed
     const size_t pl = (t + 1 < TT) ? (size_t)tile * R * TT + (t + 1) : (size_t)(tile + 1) * R * TT;
-    double y0[R + 1], v0[R + 1], w0[R + 1];
+    double2 q[R + 1][2];
 #pragma unroll
     for (int r = 0; r <= R; ++r) {
-        const size_t p = (r < R) ? p0 + (size_t)r * TT : pl;
         const bool in = j0 + r < n;
-        y0[r] = in ? __ldg(S + 0 * us + p) : 0.0; v0[r] = in ? __ldg(S + 1 * us + p) : 0.0; w0[r] = in ? __ldg(S + 2 * us + p) : 0.0;
+        const size_t p = (r < R) ? p0 + (size_t)r * TT : (in ? pl : p0);
+        q[r][0] = __ldg(S + p * 4 + 0); q[r][1] = __ldg(S + p * 4 + 1);
+        if (!in) { q[r][0] = make_double2(0.0, 0.0); q[r][1].x = 0.0; }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        ra[r] = 0.0; rc[r] = 0.0; rd[r] = 0.0;
-        if (j0 + r < n) {
-            const size_t p = p0 + (size_t)r * TT;
-            const double ar = __ldg(S + 3 * us + p), bp = __ldg(S + 4 * us + p), Cs = __ldg(S + 5 * us + p), dp = __ldg(S + 6 * us + p);
-            const double binv = fast_rcp(fma(-Cs, v0[r + 1], bp));
-            ra[r] = binv * ar;
-            rc[r] = -(binv * (Cs * w0[r + 1]));
-            rd[r] = binv * fma(-Cs, y0[r + 1], dp);
-        }
+        const size_t p = p0 + (size_t)r * TT;
+        const double2 bc = __ldg(S + p * 4 + 2), dd = __ldg(S + p * 4 + 3);
+        const double ar = q[r][1].y, bp = bc.x, Cs = bc.y, dp = dd.x;
+        const double y0n = q[r + 1][0].x, v0n = q[r + 1][0].y, w0n = q[r + 1][1].x;
+        const double binv = fast_rcp(fma(-Cs, v0n, bp));
+        const bool in = j0 + r < n;
+        ra[r] = in ? binv * ar : 0.0;
+        rc[r] = in ? -(binv * (Cs * w0n)) : 0.0;
+        rd[r] = in ? binv * fma(-Cs, y0n, dp) : 0.0;
     }
 }
 
@@ -200,28 +191,28 @@ __global__ void __launch_bounds__(TT) k6_chunk_asm(ProbDev pd, double tt, double
     assemble_chunk<Fn, R, TT, SYM0, true, !SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
                                                  pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui,
                                                  ui + tiled_pos(pd.Nx - 1, R, TT));
-    store_summary<R, TT>(th, lv, k, tile, t, k6sm + 2);
+    store_summary<R>(th, lv, k, tile * TT + t);
 }
 
 // level l >= 1, forward: form the level's rows, keep them, eliminate, store the chunk summary
 template <int R, int TT>
 __global__ void __launch_bounds__(TT) k6_chunk_sys(LevelDev lv, LevelDev below, const int* active) {
-    __shared__ double buf[7 * TT];
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
     if (!active[k]) return;
     double ra[R], rc[R], rd[R];
     form_rows<R, TT>(below, k, tile, t, ra, rc, rd);
     ChunkThomas<1, R> th;
-    const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT + t;
+    double2* rows = lv.acd + ((size_t)k * lv.stride + (size_t)tile * R * TT + t) * 2;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        lv.a[base + (size_t)r * TT] = ra[r]; lv.c[base + (size_t)r * TT] = rc[r]; lv.d[base + (size_t)r * TT] = rd[r];
+        rows[(size_t)r * TT * 2 + 0] = make_double2(ra[r], rc[r]);
+        rows[(size_t)r * TT * 2 + 1] = make_double2(rd[r], 0.0);
         Mat<1> A, Bm, C; Vec<1> d;
         A.a[0] = ra[r]; Bm.a[0] = 1.0; C.a[0] = rc[r]; d.a[0] = rd[r];
         th.row(r, A, Bm, C, d);
     }
-    store_summary<R, TT>(th, lv, k, tile, t, buf);
+    store_summary<R>(th, lv, k, tile * TT + t);
 }
 
 // top level: one CTA per instance forms its rows (RT per thread, one tile) and solves them
@@ -262,11 +253,12 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
     if (!active[k]) return;
     ChunkThomas<1, R> th;
     const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT;
+    const double2* rows = lv.acd + (base + t) * 2;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const size_t o = base + (size_t)r * TT + t;
+        const double2 ac = __ldg(rows + (size_t)r * TT * 2), dd = __ldg(rows + (size_t)r * TT * 2 + 1);
         Mat<1> A, Bm, C; Vec<1> d;
-        A.a[0] = lv.a[o]; Bm.a[0] = 1.0; C.a[0] = lv.c[o]; d.a[0] = lv.d[o];
+        A.a[0] = ac.x; Bm.a[0] = 1.0; C.a[0] = ac.y; d.a[0] = dd.x;
         th.row(r, A, Bm, C, d);
     }
     Vec<1> xp, xs, x[R];
@@ -359,7 +351,8 @@ __global__ void __launch_bounds__(TT) k6_assemble(ProbDev pd, double tt, double 
 }
 
 // ||h||_2 per instance (fixed summation order: thread, lane tree, warps), stop test, counters; one CTA per instance,
-// the last one publishes the active count
+// the last one publishes the active count.  (Folding this into k6_back_asm with a per-instance ticket was measured:
+// the fence + returning atomic at the end of every tile's CTA costs more than this launch.)
 template <int UNUSED = 0>
 __global__ void __launch_bounds__(256) k6_finalize(ProbDev pd, const double* partial, double tol, int slot) {
     __shared__ double red[8];
