@@ -198,7 +198,8 @@ class DeviceProblem:
         self._h = h
         self.B, self.Nx, self.npde = functor.batch, x.size, functor.npde
         self.nparams, self.functor_id, self.m = functor.nparams, int(functor.id), int(m)
-        self._mesh_key = x.tobytes()
+        self._mesh_key = _mesh_fingerprint(x)
+        self._mesh_copy = x.copy()
         self.set_design(design)
 
     def close(self):
@@ -395,13 +396,19 @@ _pool = {}
 _POOL_MAX = 2
 
 
+def _mesh_fingerprint(x):
+    """Cheap key of a mesh for the problem pool (two passes over x instead of hashing its bytes: a 2^22-node mesh
+    costs 3 ms, not 25); a pooled problem is only reused after an exact comparison with its own copy of the mesh."""
+    return (x.size, float(x[0]), float(x[-1]), float(x.sum()), float(np.dot(x, x)))
+
+
 def _pool_key(ctx, m, x, functor):
-    return (id(ctx), int(m), int(functor.id), functor.batch, x.tobytes())
+    return (id(ctx), int(m), int(functor.id), functor.batch, _mesh_fingerprint(x))
 
 
 def _acquire(ctx, m, x, functor, design):
     lst = _pool.get(_pool_key(ctx, m, x, functor))
-    if lst:
+    if lst and np.array_equal(lst[-1]._mesh_copy, x):
         dev = lst.pop()
         dev.set_params(functor.params)
         dev.set_design(design)
@@ -439,16 +446,28 @@ class ProblemDefinition:
     m: int
     nb_design_var: int
     inival: np.ndarray          # [B, Nx*npde] flattened, component fastest (src/utils.jl:632)
-    xi: np.ndarray              # ξ
-    zeta: np.ndarray            # ζ
     pdefunction: Functor
     icfunction: object
     bdfunction: Functor
     device: DeviceProblem = field(repr=False, default=None)
+    _xi_zeta: tuple = field(repr=False, default=None)
 
     @property
     def jac(self):
         return self.device.debug_system()[1:]
+
+    def _quadrature(self):
+        if self._xi_zeta is None:
+            self._xi_zeta = self.device.quadrature()
+        return self._xi_zeta
+
+    @property
+    def xi(self):       # ξ (src/utils.jl:683-718); fetched from the library on first use
+        return self._quadrature()[0]
+
+    @property
+    def zeta(self):     # ζ
+        return self._quadrature()[1]
 
     def __len__(self):  # Base.length(pb) = nb_design_var, src/utils.jl:665
         return self.nb_design_var
@@ -606,10 +625,9 @@ def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design
     if u0.size == Nx * npde:
         u0 = np.broadcast_to(u0.reshape(1, Nx, npde), (B, Nx, npde))
     inival = np.ascontiguousarray(u0.reshape(B, Nx * npde))
-    xi, zeta = dev.quadrature()
     info = dev.info()
-    pb = ProblemDefinition(npde, Nx, x, tuple(tspan), info["singular"], int(m), params.nb_design_var, inival, xi,
-                           zeta, pdefun, icfun, pdefun, dev)
+    pb = ProblemDefinition(npde, Nx, x, tuple(tspan), info["singular"], int(m), params.nb_design_var, inival,
+                           pdefun, icfun, pdefun, dev)
     return Nx, npde, inival, pb
 
 
