@@ -66,6 +66,25 @@ cudaError_t launch_any(const void* func, dim3 grid, dim3 block, size_t smem, cud
     return cudaLaunchKernel(func, grid, block, p, smem, st);
 }
 
+// Launch with programmatic stream serialization: the kernel may begin (up to its griddepcontrol.wait) while the
+// previous kernel in the stream drains.  Used for the persistent Newton-iteration kernel, whose prologue (barrier
+// set-up, mesh weights -> shared memory) does not depend on the previous iteration.  SB_NO_PDL=1 disables it.
+template <class... Args>
+cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool off = getenv("SB_NO_PDL") != nullptr;
+    if (off) return launch_any(func, grid, block, smem, st, args...);
+    void* p[] = {(void*)&args...};
+    ++g_launches;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, func, p);
+}
+
 struct UserFunctor {
     std::string source, name;
     int npde, nparams;
@@ -1217,7 +1236,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         const int prev_slot = (pb->launched == 0) ? -1 : (int)((pb->launched - 1) % kSlots);
         const int parity = (int)(pb->launched & 1);
         if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
-        CU(launch_any(kern, dim3(pb->p_grid), block, pb->p_smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity));
+        CU(launch_pdl(kern, dim3(pb->p_grid), block, pb->p_smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity));
         CU(cudaGetLastError());
         pb->lazy_pending = false;   // pd.lazy_b stays set for this step: only iter_no == 0 reads b as the iterate
         if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));

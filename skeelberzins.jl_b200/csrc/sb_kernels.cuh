@@ -807,6 +807,13 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_newton_fused(ProbDev pd, double tt, doubl
 // of the CTA runs its own pipeline (own stages, own mbarriers, warp-level syncs only).
 // ---------------------------------------------------------------------------------------------
 SB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch: a kernel launched with programmatic stream serialization may start while its
+// predecessor in the stream is still draining; pdl_wait() returns once the predecessor has completed and its
+// writes are visible, pdl_release() lets the successor's CTAs take SM slots as they free up.  Both are no-ops in
+// a kernel launched the ordinary way.
+SB_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SB_D void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 SB_D void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -879,17 +886,10 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
     long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index per stage / parity
     uint64_t* bar = bars + 2 * g;
 
-    const int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
-    const int* list_in = (prev_slot < 0) ? nullptr : pd.list[parity];
-    int* list_out = pd.list[parity ^ 1];
-    const int stride = gridDim.x * G;
-    int j = blockIdx.x * G + g;
-    if (blockIdx.x * G >= n_in) {  // whole CTA has nothing to do
-        if (t == 0) group_done(pd, slot, gridDim.x * G);
-        return;
-    }
-
-    // mesh weights -> shared memory, once per CTA, by the bulk-copy engine (waited for right before first use)
+    // Prologue that does not depend on the previous Newton-iteration launch (it overlaps that launch's tail when
+    // this one was started with programmatic stream serialization): barriers, mesh weights -> shared memory, once
+    // per CTA, by the bulk-copy engine (waited for right before first use).
+    pdl_release();
     MeshDev mesh = pd.mesh;
     uint64_t* mesh_bar = bars + 2 * G;
     if constexpr (SYM0) mesh.gw = mesh_sm + LY::oGw;
@@ -916,6 +916,19 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         else bulk_g2s(mesh_sm + LY::oAB, pd.mesh.awbw, 4 * LB, mesh_bar);  // awbw[2L] and gwwf[2L] are contiguous
         if constexpr (Fn::c_unit) bulk_g2s(mesh_sm + LY::oIvol, pd.mesh.ivol, LB, mesh_bar);
         if constexpr (LY::kFrac) bulk_g2s(mesh_sm + LY::oFrac, pd.mesh.frac, 2 * LB, mesh_bar);
+    }
+
+    pdl_wait();  // everything below reads what the previous launch wrote (active count, list, u, b)
+    const int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
+    const int* list_in = (prev_slot < 0) ? nullptr : pd.list[parity];
+    int* list_out = pd.list[parity ^ 1];
+    const int stride = gridDim.x * G;
+    int j = blockIdx.x * G + g;
+    if (blockIdx.x * G >= n_in) {  // whole CTA has nothing to do
+        if (threadIdx.x == 0) mbar_wait(mesh_bar, 0);  // do not exit with the bulk copy in flight
+        __syncthreads();
+        if (t == 0) group_done(pd, slot, gridDim.x * G);
+        return;
     }
 
     constexpr uint32_t kBytes = (uint32_t)(L * P * sizeof(double));
