@@ -245,7 +245,10 @@ struct sb_problem {
     unsigned int* h_count = nullptr;  // mapped pinned: the kernels publish the active count of each launch here
     // step state
     double t_next = 0.0, inv_tau = 0.0;
-    long launched = 0, confirmed = 0;
+    long launched = 0, confirmed = 0;   // Newton-iteration launches / delivered counts of the current step
+    long slot_base = 0;                 // ring slot of the step's iteration 0 (the ring runs on across steps)
+    long total_launched = 0;            // launches through the ring since the problem was created
+    int slot_of(long it) const { return (int)((slot_base + it) % kSlots); }
     int64_t last_active = 0;
     bool mass_ready = false;
     // begin_step fusion (fused_tma): b = M.*u_{n+1} is written by the converging iteration of the previous step
@@ -1029,7 +1032,7 @@ static int prof_harvest(sb_problem* pb) {
     if (!pb->prof || pb->prof_harvested >= pb->launched) return SB_OK;
     CU(cudaStreamSynchronize(pb->ctx->stream));
     for (long j = pb->prof_harvested; j < pb->launched; ++j) {
-        const int s = (int)(j % kSlots);
+        const int s = pb->slot_of(j);
         const int64_t before = (j == 0) ? pb->pd.B : pb->prof_prev_active;
         float ms_a = 0.f, ms_s = 0.f;
         if (pb->design == SB_DESIGN_SPLIT) {
@@ -1099,7 +1102,6 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     pb->t_next = t_next; pb->inv_tau = inv_tau;
     pb->design = pb->design_pending;
     cudaStream_t st = pb->ctx->stream;
-    CU(cudaMemsetAsync(pb->d_count, 0, 2 * kSlots * sizeof(unsigned int), st));
     const bool lazy = pb->b_ready && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh && !getenv("SB_NO_LAZY_BEGIN");
     pb->b_ready = false;
     pb->lazy_pending = false;
@@ -1111,6 +1113,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
         int rc = run_begin_step_kernel(pb);
         if (rc) return rc;
     }
+    pb->slot_base = pb->slot_of(pb->launched);
     pb->launched = 0; pb->confirmed = 0; pb->last_active = pb->pd.B;
     return SB_OK;
 }
@@ -1138,16 +1141,20 @@ static int wait_slot(sb_problem* pb, int s, unsigned int* value) {
 }
 
 static int prepare_slot(sb_problem* pb, int* slot) {
-    const int s = (int)(pb->launched % kSlots);
+    const int s = pb->slot_of(pb->launched);
     pb->pd.iter_no = (int)pb->launched;  // Newton iteration number inside the step (lock-step: same for all active instances)
-    if (pb->launched >= kSlots) {  // ring wrapped: the slot's previous value must have been delivered, then re-zero it
-        if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; }
-        unsigned int v;
-        int rc = wait_slot(pb, s, &v);
-        if (rc) return rc;
-        if (pb->confirmed < pb->launched - kSlots + 1) pb->confirmed = pb->launched - kSlots + 1;
-        CU(cudaMemsetAsync(pb->d_count + s, 0, sizeof(unsigned int), pb->ctx->stream));
-        CU(cudaMemsetAsync(pb->d_count + kSlots + s, 0, sizeof(unsigned int), pb->ctx->stream));
+    if (pb->total_launched >= kSlots) {  // the slot's previous user (kSlots launches ago) must have delivered its count
+        if (pb->prof && pb->launched >= kSlots) { int rc = prof_harvest(pb); if (rc) return rc; }
+        volatile unsigned int* p = pb->h_count + s;
+        unsigned long spins = 0;
+        while (*p == kPending) {
+            if ((++spins & 0x3FFF) == 0) {
+                cudaError_t e = cudaStreamQuery(pb->ctx->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return fail(SB_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
+                if (e == cudaSuccess && *p == kPending) return fail(SB_ERR_CUDA, "Newton-iteration launch finished without reporting its active count");
+            }
+        }
+        if (pb->launched >= kSlots && pb->confirmed < pb->launched - kSlots + 1) pb->confirmed = pb->launched - kSlots + 1;
     }
     *((volatile unsigned int*)pb->h_count + s) = kPending;
     *slot = s;
@@ -1157,6 +1164,7 @@ static int prepare_slot(sb_problem* pb, int* slot) {
 static int finish_slot(sb_problem* pb, int slot) {
     (void)slot;
     pb->launched++;
+    pb->total_launched++;
     return SB_OK;
 }
 
@@ -1168,7 +1176,7 @@ int sb_residual_jacobian(sb_problem* pb) {
     if ((rc = materialize_begin(pb))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    const int ps = (int)(pb->launched % kSlots);
+    const int ps = pb->slot_of(pb->launched);
     if (pb->prof) CU(cudaEventRecord(pb->evA[ps], pb->ctx->stream));
     if (pb->longmesh)
         CU(launch_any(pb->ks.long_assemble_jac, dim3(pb->pd.ntiles, (unsigned)pb->pd.B), dim3(kLongT0), 0, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, 0));
@@ -1233,7 +1241,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
             if (const char* e = getenv("SB_PERSISTENT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < occ) occ = v; }
             pb->p_grid = (int)std::min<int64_t>((int64_t)occ * sms, (int64_t)grid.x);
         }
-        const int prev_slot = (pb->launched == 0) ? -1 : (int)((pb->launched - 1) % kSlots);
+        const int prev_slot = (pb->launched == 0) ? -1 : pb->slot_of(pb->launched - 1);
         const int parity = (int)(pb->launched & 1);
         if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
         CU(launch_pdl(kern, dim3(pb->p_grid), block, pb->p_smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot, prev_slot, parity));
@@ -1255,13 +1263,13 @@ int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active) {
     if (pb->launched == 0) { *n_active = pb->last_active; return SB_OK; }
     if (blocking) {
         unsigned int v;
-        int rc = wait_slot(pb, (int)((pb->launched - 1) % kSlots), &v);
+        int rc = wait_slot(pb, pb->slot_of(pb->launched - 1), &v);
         if (rc) return rc;
         pb->confirmed = pb->launched;
         pb->last_active = v;
     } else {
         while (pb->confirmed < pb->launched) {
-            const unsigned int v = *((volatile unsigned int*)pb->h_count + (pb->confirmed % kSlots));
+            const unsigned int v = *((volatile unsigned int*)pb->h_count + pb->slot_of(pb->confirmed));
             if (v == kPending) break;
             if (v == 0 && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh) pb->b_ready = true;
             pb->last_active = v;
@@ -1278,7 +1286,7 @@ int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active) {
     if (it < pb->launched - kSlots) return fail(SB_ERR_INVALID, "iteration %d is older than the %d-slot counter ring", it, kSlots);
     CU(cudaSetDevice(pb->ctx->device));
     unsigned int v;
-    int rc = wait_slot(pb, it % kSlots, &v);
+    int rc = wait_slot(pb, pb->slot_of(it), &v);
     if (rc) return rc;
     *n_active = v;
     if (pb->confirmed < it + 1) { pb->confirmed = it + 1; pb->last_active = v; }
@@ -1299,7 +1307,7 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
             if (rc) return rc;
         }
         unsigned int v;
-        int rc = wait_slot(pb, (int)((base + done) % kSlots), &v);
+        int rc = wait_slot(pb, pb->slot_of(base + done), &v);
         if (rc) return rc;
         n_act = v;
         done++;

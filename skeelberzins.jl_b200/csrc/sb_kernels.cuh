@@ -73,6 +73,9 @@ struct ProbDev {
 // Completion notice of a Newton-iteration launch without a copy node in the stream: every thread group takes a
 // ticket when it is done; the last one publishes the number of still-active instances straight into mapped
 // host memory, where the host loop polls it (src/utils.jl:329-333 is the decision it feeds).
+// The counters live in a ring of kRingSlots launches that cleans itself: the launch that closes slot s zeroes slot
+// s + kRingSlots/2, which no launch in flight can be using, so no memset ever sits between two Newton-iteration kernels.
+constexpr int kRingSlots = 128;
 SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups) {
     __threadfence();
     const unsigned int ticket = atomicAdd(pd.done_count + slot, 1u);
@@ -80,6 +83,9 @@ SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups) {
         __threadfence();
         const unsigned int c = atomicAdd(pd.active_count + slot, 0u);
         pd.host_count[slot] = c;
+        const int far = (slot + kRingSlots / 2) % kRingSlots;
+        pd.active_count[far] = 0u;
+        pd.done_count[far] = 0u;
         __threadfence_system();
     }
 }
