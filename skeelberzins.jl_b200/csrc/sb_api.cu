@@ -536,7 +536,8 @@ int longmesh_setup(sb_problem* pb) {
 template <int RT>
 void launch_top(sb_problem* pb, const LevelDev& top, const LevelDev& below) {
     const size_t smem = (size_t)(2 * 3 + 1) * kLongTT * sizeof(double);
-    k6_top<RT, kLongTT><<<(unsigned)pb->pd.B, kLongTT, smem, pb->ctx->stream>>>(top, below, pb->d_active);
+    launch_pdl((const void*)k6_top<RT, kLongTT>, dim3((unsigned)pb->pd.B), dim3(kLongTT), smem, pb->ctx->stream, top, below,
+               (const int*)pb->d_active);
 }
 
 // one Newton iteration of the long-mesh path; publishes the active count like the batched kernels
@@ -553,11 +554,12 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         }
         pb->ks.long_configured = true;
     }
-    CU(launch_any(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
-    for (int l = 1; l < top; ++l) {
-        k6_chunk_sys<kLongRS, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l - 1], pb->d_active);
-        ++g_launches;
-    }
+    // every kernel of the sequence is launched with programmatic stream serialization: launch latency and the
+    // dependence-free prologues (barrier set-up, mesh weights of the level-0 tiles) overlap the predecessor's tail
+    CU(launch_pdl(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
+    for (int l = 1; l < top; ++l)
+        CU(launch_pdl((const void*)k6_chunk_sys<kLongRS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l - 1],
+                      (const int*)pb->d_active));
     switch (pb->top_R) {
         case 1: launch_top<1>(pb, lv[top], lv[top - 1]); break;
         case 2: launch_top<2>(pb, lv[top], lv[top - 1]); break;
@@ -565,14 +567,11 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         case 8: launch_top<8>(pb, lv[top], lv[top - 1]); break;
         default: launch_top<16>(pb, lv[top], lv[top - 1]); break;
     }
-    ++g_launches;
-    for (int l = top - 1; l >= 1; --l) {
-        k6_back_sys<kLongRS, kLongTT><<<dim3(lv[l].ntiles, B), kLongTT, 0, st>>>(lv[l], lv[l + 1], pb->d_active);
-        ++g_launches;
-    }
-    CU(launch_any(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
-    k6_finalize<0><<<B, 256, 0, st>>>(pb->pd, pb->d_partial, tol, slot);
-    ++g_launches;
+    for (int l = top - 1; l >= 1; --l)
+        CU(launch_pdl((const void*)k6_back_sys<kLongRS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l + 1],
+                      (const int*)pb->d_active));
+    CU(launch_pdl(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
+    CU(launch_pdl((const void*)k6_finalize<0>, dim3(B), dim3(256), 0, st, pb->pd, (const double*)pb->d_partial, tol, slot));
     CU(cudaGetLastError());
     return SB_OK;
 }

@@ -121,30 +121,28 @@ struct LongStage {
     static constexpr size_t bytes = (on ? doubles : oB) * sizeof(double);   // m >= 1: the backward sweep stages u only
 };
 
+// Part 1, before pdl_wait(): barriers and the mesh weights, which no kernel ever writes -- this overlaps the tail of
+// the previous kernel in the stream.  Part 2, after it: u and b of the tile.
 template <class Fn, int R, int TT>
-SB_D void long_stage_tile(const ProbDev& pd, int64_t k, int tile, bool use_b, bool halo_u, double* sm, MeshDev& mesh,
-                          const double*& ub, const double*& bb) {
+SB_D void long_stage_weights(const ProbDev& pd, int tile, double* sm, MeshDev& mesh) {
     using LS = LongStage<Fn, R, TT, true>;
     constexpr int L = LS::L;
     constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // bar[0]: weights, bar[1]: state
     const size_t toff = (size_t)tile * L;
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar + 0, 1);
+        mbar_init(bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int lo = (tile > 0) ? 2 : 0, hi = (tile + 1 < pd.ntiles) ? 2 : 0;  // halo towards existing neighbours
-        const int ulo = halo_u ? lo : 0, uhi = halo_u ? hi : 0;
-        uint32_t bytes = (uint32_t)((L + ulo + uhi) * sizeof(double)) + (uint32_t)((L + lo) * sizeof(double));
-        if (use_b) bytes += LB;
+        const int lo = (tile > 0) ? 2 : 0;  // halo towards an existing neighbour
+        uint32_t bytes = (uint32_t)((L + lo) * sizeof(double));
         if (Fn::c_unit) bytes += LB;
         if (LS::kFrac) bytes += 2 * LB;
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(sm + LS::oU + 2 - ulo, pd.u + (size_t)k * pd.L + toff - ulo, (uint32_t)((L + ulo + uhi) * sizeof(double)), bar);
-        if (use_b) bulk_g2s(sm + LS::oB, pd.b + (size_t)k * pd.L + toff, LB, bar);
         bulk_g2s(sm + LS::oGw + 2 - lo, pd.mesh.gw + toff - lo, (uint32_t)((L + lo) * sizeof(double)), bar);
         if constexpr (Fn::c_unit) bulk_g2s(sm + LS::oIvol, pd.mesh.ivol + toff, LB, bar);
         if constexpr (LS::kFrac) bulk_g2s(sm + LS::oFrac, pd.mesh.frac + toff, 2 * LB, bar);
@@ -153,9 +151,32 @@ SB_D void long_stage_tile(const ProbDev& pd, int64_t k, int tile, bool use_b, bo
     mesh.gw = sm + LS::oGw + 2;
     if constexpr (Fn::c_unit) mesh.ivol = sm + LS::oIvol;
     if constexpr (LS::kFrac) mesh.frac = reinterpret_cast<const double2*>(sm + LS::oFrac);
+}
+
+// a CTA that turns out to have nothing to do must not exit with the weight copies in flight
+SB_D void long_stage_drain(double* sm) {
+    if (threadIdx.x == 0) mbar_wait(reinterpret_cast<uint64_t*>(sm), 0);
+}
+
+template <class Fn, int R, int TT>
+SB_D void long_stage_state(const ProbDev& pd, int64_t k, int tile, bool use_b, bool halo_u, double* sm,
+                           const double*& ub, const double*& bb) {
+    using LS = LongStage<Fn, R, TT, true>;
+    constexpr int L = LS::L;
+    constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+    const size_t toff = (size_t)tile * L;
+    if (threadIdx.x == 0) {
+        const int ulo = (halo_u && tile > 0) ? 2 : 0, uhi = (halo_u && tile + 1 < pd.ntiles) ? 2 : 0;
+        const uint32_t ubytes = (uint32_t)((L + ulo + uhi) * sizeof(double));
+        mbar_expect_tx(bar + 1, ubytes + (use_b ? LB : 0u));
+        bulk_g2s(sm + LS::oU + 2 - ulo, pd.u + (size_t)k * pd.L + toff - ulo, ubytes, bar + 1);
+        if (use_b) bulk_g2s(sm + LS::oB, pd.b + (size_t)k * pd.L + toff, LB, bar + 1);
+    }
     ub = sm + LS::oU + 2;
     bb = use_b ? sm + LS::oB : ub;       // tau = Inf: b is multiplied by 1/tau = 0 wherever it is still named
-    mbar_wait(bar, 0);
+    mbar_wait(bar + 1, 0);
+    mbar_wait(bar + 0, 0);
 }
 
 // level 0, forward: assemble + eliminate the chunk, store its summary
@@ -165,15 +186,21 @@ __global__ void __launch_bounds__(TT) k6_chunk_asm(ProbDev pd, double tt, double
     extern __shared__ __align__(16) double k6sm[];
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
-    if (!pd.active[k]) return;
     const size_t toff = (size_t)tile * R * TT;
+    MeshDev mesh;
+    pdl_release();
+    if constexpr (SYM0) long_stage_weights<Fn, R, TT>(pd, tile, k6sm, mesh);
+    else mesh = mesh_of_tile(pd.mesh, toff);
+    pdl_wait();
+    if (!pd.active[k]) {
+        if constexpr (SYM0) long_stage_drain(k6sm);
+        return;
+    }
     const double* ui = pd.u + (size_t)k * pd.L;
     const double* ub = ui + toff;
     const double* bb = pd.b + (size_t)k * pd.L + toff;
     const bool use_b = inv_tau != 0.0;  // stationary solves (tau = Inf) never look at b: rhs - b/tau = rhs
-    MeshDev mesh;
-    if constexpr (SYM0) long_stage_tile<Fn, R, TT>(pd, k, tile, use_b, true, k6sm, mesh, ub, bb);
-    else mesh = mesh_of_tile(pd.mesh, toff);
+    if constexpr (SYM0) long_stage_state<Fn, R, TT>(pd, k, tile, use_b, true, k6sm, ub, bb);
     double uc[R][1], bc[R][1];
 #pragma unroll
     for (int r = 0; r < R; ++r) { uc[r][0] = ub[r * TT + t]; bc[r][0] = use_b ? bb[r * TT + t] : 0.0; }
@@ -199,6 +226,8 @@ template <int R, int TT>
 __global__ void __launch_bounds__(TT) k6_chunk_sys(LevelDev lv, LevelDev below, const int* active) {
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
+    pdl_release();
+    pdl_wait();
     if (!active[k]) return;
     double ra[R], rc[R], rd[R];
     form_rows<R, TT>(below, k, tile, t, ra, rc, rd);
@@ -221,6 +250,8 @@ __global__ void __launch_bounds__(TT) k6_top(LevelDev lv, LevelDev below, const 
     extern __shared__ double sm[];
     const int t = threadIdx.x;
     const int64_t k = blockIdx.x;
+    pdl_release();
+    pdl_wait();
     if (!active[k]) return;
     double ra[RT], rc[RT], rd[RT];
     form_rows<RT, TT>(below, k, 0, t, ra, rc, rd);
@@ -250,6 +281,8 @@ template <int R, int TT>
 __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, const int* active) {
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
+    pdl_release();
+    pdl_wait();
     if (!active[k]) return;
     ChunkThomas<1, R> th;
     const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT;
@@ -275,8 +308,17 @@ __global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double 
     extern __shared__ __align__(16) double k6sm[];
     const int tile = blockIdx.x, t = threadIdx.x;
     const int64_t k = blockIdx.y;
-    if (!pd.active[k]) return;
     const size_t toff = (size_t)tile * R * TT;
+    using LS = LongStage<Fn, R, TT, SYM0>;
+    MeshDev mesh;
+    pdl_release();
+    if constexpr (SYM0) long_stage_weights<Fn, R, TT>(pd, tile, k6sm, mesh);
+    else mesh = mesh_of_tile(pd.mesh, toff);
+    pdl_wait();
+    if (!pd.active[k]) {
+        if constexpr (SYM0) long_stage_drain(k6sm);
+        return;
+    }
     double* ug = pd.u + (size_t)k * pd.L + toff;
     const double* ub = ug;
     const double* bb = pd.b + (size_t)k * pd.L + toff;
@@ -285,13 +327,10 @@ __global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double 
     // tile (the neighbours' edge nodes, both mesh ends for the boundary conditions) comes from the copy the
     // forward sweep saved in `edge`.
     const double* e = up.edge + (size_t)k * (2 * pd.ntiles + 2);
-    using LS = LongStage<Fn, R, TT, SYM0>;
-    MeshDev mesh;
     double uc[R][1], bc[R][1];
     if constexpr (SYM0) {
-        long_stage_tile<Fn, R, TT>(pd, k, tile, use_b, false, k6sm, mesh, ub, bb);
+        long_stage_state<Fn, R, TT>(pd, k, tile, use_b, false, k6sm, ub, bb);
     } else {
-        mesh = mesh_of_tile(pd.mesh, toff);
 #pragma unroll
         for (int r = 0; r < R; ++r) k6sm[LS::oU + 2 + r * TT + t] = ug[r * TT + t];
         ub = k6sm + LS::oU + 2;
@@ -358,6 +397,8 @@ __global__ void __launch_bounds__(256) k6_finalize(ProbDev pd, const double* par
     __shared__ double red[8];
     const int64_t k = blockIdx.x;
     const int t = threadIdx.x;
+    pdl_release();
+    pdl_wait();
     if (pd.active[k]) {
         const double* pk = partial + (size_t)k * pd.ntiles;
         double ss = 0.0;
