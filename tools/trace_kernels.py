@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--time-steps", type=int, default=3)
     ap.add_argument("--design", default="fused_tma")
     ap.add_argument("--last", type=int, default=40, help="print the last N kernel records")
+    ap.add_argument("--c-loop", action="store_true", help="time loop and Newton loop in C (sb_solve_steps)")
     args = ap.parse_args()
     c = ex.baseline_case(args.config)
     ctx = sb.Context(0)
@@ -34,7 +35,7 @@ def main():
         tg, _ = sb.time_grid(c.tspan, c.tstep)
         tg = tg[:args.time_steps + 1]
         return sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, design=args.design, tstep=tg,
-                        save="last", squeeze=False)
+                        save="last", squeeze=False, c_loop=args.c_loop)
 
     solve()
     solve()
