@@ -428,11 +428,12 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
         return fail(SB_ERR_PLUGIN, "nvrtcCreateProgram failed");
     for (const std::string& n : names) nvrtcAddNameExpression(prog, n.c_str());
     const std::string inc = "-I" + csrc_dir();
-    char d1[64], d2[64];
+    char d1[64], d2[64], d3[64];
     snprintf(d1, sizeof d1, "-DSB_TMA_STAGES=%d", (int)SB_TMA_STAGES);
     snprintf(d2, sizeof d2, "-DSB_PERSISTENT_WARPS_PER_SM=%d", (int)SB_PERSISTENT_WARPS_PER_SM);
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), d1, d2};
-    const nvrtcResult r = nvrtcCompileProgram(prog, 6, opts);
+    snprintf(d3, sizeof d3, "-DSB_PERSISTENT_WARPS_P2=%d", (int)SB_PERSISTENT_WARPS_P2);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), d1, d2, d3};
+    const nvrtcResult r = nvrtcCompileProgram(prog, 7, opts);
     if (r != NVRTC_SUCCESS) {
         size_t ls = 0;
         nvrtcGetProgramLogSize(prog, &ls);

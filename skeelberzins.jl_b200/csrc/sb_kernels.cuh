@@ -847,6 +847,9 @@ SB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef SB_PERSISTENT_WARPS_PER_SM
 #define SB_PERSISTENT_WARPS_PER_SM 16
 #endif
+#ifndef SB_PERSISTENT_WARPS_P2   // npde = 2: twice the registers per thread
+#define SB_PERSISTENT_WARPS_P2 (SB_PERSISTENT_WARPS_PER_SM / 2)
+#endif
 
 template <class Fn, int R, int TT, bool SYM0>
 struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
@@ -867,7 +870,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
 // thread; 2x2 block arithmetic needs about twice that, so it is given half the warps instead of spilling
 __host__ __device__ constexpr int persistent_min_blocks(int TT, int P) {
     const int threads = (TT == 32) ? kWarpBlockThreads : TT;
-    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_PER_SM / 2;
+    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_P2;
     return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;
 }
 template <class Fn, int R, int TT, bool SYM0>
