@@ -107,3 +107,63 @@ def test_user_functor_plugin_compiles_without_gpu(built_lib, Nx, m):
     bad = sb.register_user_functor("struct Nope { int x; };", "Nope", 1, 1)
     with pytest.raises(sb.SBError, match="NVRTC"):
         sb.user_functor_compile_check(bad, 64, 0)
+
+
+def _julia_ccalls():
+    """(symbol, return type, [argument types]) of every ccall in julia/SkeelBerzinsB200.jl."""
+    src = open(os.path.join(ROOT, "julia", "SkeelBerzinsB200.jl")).read()
+    out = []
+    for m in re.finditer(r"ccall\(\(:(sb_[a-z_0-9]+),\s*libsb\),\s*(\w+),\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:                                  # balanced scan over the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[m.end():i - 1]
+        args, cur, d = [], "", 0
+        for ch in tup:
+            if ch == "{":
+                d += 1
+            if ch == "}":
+                d -= 1
+            if ch == "," and d == 0:
+                args.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            args.append(cur.strip())
+        out.append((m.group(1), m.group(2), args))
+    return out
+
+
+def test_julia_shim_matches_the_c_abi():
+    """julia cannot run in this image, so the shim is checked statically: every ccall names an exported symbol and
+    passes the number and kind of arguments the header (through the ctypes table) declares."""
+    from skeelberzins_jl_b200 import _lib
+    kind = {  # Julia ccall type -> class of C type
+        "Cint": "int", "Cdouble": "double", "Int64": "int64", "Csize_t": "size", "Cstring": "ptr",
+    }
+
+    def jl_kind(t):
+        return "ptr" if t.startswith(("Ptr{", "Ref{")) else kind[t]
+
+    def c_kind(t):
+        if t in (ctypes.c_int,):
+            return "int"
+        if t in (ctypes.c_double,):
+            return "double"
+        if t in (ctypes.c_int64,):
+            return "int64"
+        if t in (ctypes.c_size_t,):
+            return "size"
+        return "ptr"
+
+    calls = _julia_ccalls()
+    assert len(calls) >= 25
+    for name, ret, args in calls:
+        assert name in _lib.SIGNATURES, "%s is not part of the C ABI" % name
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert (ret == "Cstring") == (restype is ctypes.c_char_p), name
+        assert len(args) == len(argtypes), "%s: the shim passes %d arguments, the header declares %d" % (name, len(args), len(argtypes))
+        for a, c in zip(args, argtypes):
+            assert jl_kind(a) == c_kind(c), "%s: %s vs %s" % (name, a, c)
