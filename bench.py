@@ -23,6 +23,7 @@ python bench.py --impl reference ...                     (CPU arm: oracle port o
 """
 import argparse
 import json
+import threading
 import os
 import subprocess
 import sys
@@ -52,6 +53,9 @@ def parse_args():
     ap.add_argument("--time-steps", type=int, default=0, help="truncate the time loop (testing only)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="instances in the cpu_baseline sample")
     ap.add_argument("--python-loop", action="store_true", help="drive Newton from Python instead of the C loop")
+    ap.add_argument("--streams", type=int, default=0, help="contiguous sub-batches per GPU, each with its own CUDA stream and "
+                    "host loops (1 = the whole batch in lock step; 0 = the measured best per config: 2 for cfg2 and cfg4, "
+                    "whose instances need different numbers of Newton iterations or long step sequences, else 1)")
     return ap.parse_args()
 
 
@@ -237,30 +241,52 @@ def run_ours(args):
     u0[:] = np.asarray(case.icfun(case.xmesh), dtype=np.float64).reshape(1, Nx, P)
     out_t = torch.empty((Bp, Nx, P), dtype=torch.float64).pin_memory()
 
-    stream = torch.cuda.Stream()
-    ctx = sb.Context(local, stream=stream.cuda_stream)
-    fn = sb.Functor(case.functor, prm)
-    dev = sb.DeviceProblem(ctx, case.m, case.xmesh, fn, design=args.design)
-    dev.upload(u0)
-    dev.checkpoint()
     tol, maxit = 1e-10, 100
     nsteps = tg.size - 1
-
     stationary = case.tspan is None
+    want_streams = args.streams if args.streams > 0 else {"2": 2, "4": 2}.get(str(args.config), 1)
+    n_str = 1 if (stationary or args.python_loop or Bp < 2 * want_streams) else want_streams
 
-    def solve_resident():
-        dev.rollback()
-        dev.mass_flags(tg[0], stationary=stationary)
+    # one context (= CUDA stream) and one device problem per contiguous sub-batch
+    stream = torch.cuda.Stream()
+    streams = [stream] + [torch.cuda.Stream() for _ in range(n_str - 1)]
+    ctxs = [sb.Context(local, stream=s_.cuda_stream) for s_ in streams]
+    ctx = ctxs[0]
+    bounds = [int(round(i * Bp / n_str)) for i in range(n_str + 1)]
+    fn = sb.Functor(case.functor, prm)
+    devs = []
+    for i in range(n_str):
+        d_ = sb.DeviceProblem(ctxs[i], case.m, case.xmesh, sb.Functor(case.functor, prm[bounds[i]:bounds[i + 1]]), design=args.design)
+        d_.upload(u0[bounds[i]:bounds[i + 1]])
+        d_.checkpoint()
+        devs.append(d_)
+    dev = devs[0]
+
+    def solve_one(d_):
         if not args.python_loop and not stationary:
-            dev.solve_steps(tg, tau, tol, maxit)
+            d_.solve_steps(tg, tau, tol, maxit)
             return
         for i in range(nsteps):
             tau_i = tau if tau is not None else tg[i + 1] - tg[i]
-            dev.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
+            d_.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
             if args.python_loop:
-                sb.api._newton_loop(dev, tol, maxit)
+                sb.api._newton_loop(d_, tol, maxit)
             else:
-                dev.newton_solve(tol, maxit)
+                d_.newton_solve(tol, maxit)
+
+    def solve_resident():
+        for d_ in devs:
+            d_.rollback()
+            d_.mass_flags(tg[0], stationary=stationary)
+        if n_str == 1:
+            solve_one(dev)
+            return
+        th = [threading.Thread(target=solve_one, args=(d_,)) for d_ in devs[1:]]
+        for t_ in th:
+            t_.start()
+        solve_one(dev)
+        for t_ in th:
+            t_.join()
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,8 +296,9 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         solve_resident()
-    ctx.synchronize()
-    inst_iters = dev.total_active_iterations()                 # per solve (deterministic)
+    for c_ in ctxs:
+        c_.synchronize()
+    inst_iters = sum(d_.total_active_iterations() for d_ in devs)      # per solve (deterministic)
     units_per_step = inst_iters * Nx
 
     # ---- value: K solves from HBM-resident inputs --------------------------------------------------
@@ -281,16 +308,23 @@ def run_ours(args):
     if sampler:
         sampler.start()
     l0 = sb.kernel_launches()
-    e0.record(stream)
+    tstream = torch.cuda.Stream()                              # timing stream: e0 precedes, e1 follows every sub-batch stream
+    e0.record(tstream)
+    for s_ in streams:
+        s_.wait_event(e0)
     for _ in range(args.steps):
         solve_resident()
-    e1.record(stream)
+    for s_ in streams:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        tstream.wait_event(ev)
+    e1.record(tstream)
     barrier()
     launches = sb.kernel_launches() - l0
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
-    assert dev.total_active_iterations() == inst_iters
-    status_bad = int((dev.status() != 0).sum())
+    assert sum(d_.total_active_iterations() for d_ in devs) == inst_iters
+    status_bad = int(sum((d_.status() != 0).sum() for d_ in devs))
 
     # ---- e2e: the public pdepe() call with host buffers ---------------------------------------------
     tstep_arg = case.tstep if not args.time_steps else tg
@@ -302,7 +336,7 @@ def run_ours(args):
             return sb.pdepe(case.m, f2, u0, f2, case.xmesh, ctx=ctx, design=args.design, squeeze=False,
                             c_loop=not args.python_loop)
         sol = sb.pdepe(case.m, f2, u0, f2, case.xmesh, tspan_arg, ctx=ctx, design=args.design, tstep=tstep_arg,
-                       save="last", squeeze=False, c_loop=not args.python_loop)
+                       save="last", squeeze=False, c_loop=not args.python_loop, streams=n_str)
         return sol.u[-1]
 
     for _ in range(2):
@@ -321,6 +355,13 @@ def run_ours(args):
     d2h = u0.nbytes + 4 * int(launches // max(args.steps, 1))   # final state + one 4-byte active counter per launch
 
     # ---- roofline: profiled solve, CUDA events around every Newton-iteration launch -------------------
+    if n_str > 1:                                              # kernel metrics are taken on the whole batch in one problem
+        for d_ in devs[1:]:
+            d_.close()
+        dev.close()
+        dev = sb.DeviceProblem(ctx, case.m, case.xmesh, fn, design=args.design)
+        dev.upload(u0)
+        dev.checkpoint()
     dev.rollback()
     dev.mass_flags(tg[0], stationary=stationary)
     dev.profile_begin()
@@ -410,7 +451,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg%s %s: B=%d instances/GPU x Nx=%d, %d implicit-Euler steps per bench step, "
                                    "tol 1e-10, maxit 100" % (args.config, case.name, Bp, Nx, nsteps),
-                       "design": args.design, "rows_per_thread": lay["R"], "threads_per_system": lay["T"],
+                       "design": args.design, "streams": n_str, "rows_per_thread": lay["R"], "threads_per_system": lay["T"],
                        "l2_policy": "inputs larger than L2 (state + rhs = %.0f MB per GPU%s)"
                                     % (2 * u0.nbytes / 1e6, "; split design adds %.0f MB of F/J" % (4 * P * u0.nbytes / 1e6) if args.design == "split" else ""),
                        "newton_loop": "python" if args.python_loop else "C (sb_newton_solve)",

@@ -684,14 +684,76 @@ def newton(pb, tau, timeStep, tol=1.0e-10, maxit=100, hist_flag=False, c_loop=Fa
 newton_stat = newton  # src/utils.jl:344-378: same loop, residual without mass matrix (flags all 1, inv_tau = 0)
 
 
+_stream_ctx = {}
+
+
+def _stream_contexts(ctx, n):
+    """ctx plus n-1 cached contexts (= CUDA streams) on the same GPU."""
+    lst = _stream_ctx.setdefault(id(ctx), [])
+    while len(lst) < n - 1:
+        lst.append(Context(ctx.device))
+    return [ctx] + lst[:n - 1]
+
+
+def _pdepe_streams(m, pdefun, icfun, bdfun, x, tspan, params, ctx, design, squeeze, streams):
+    """pdepe(save="last") for a batch split into `streams` contiguous sub-batches.  Every sub-batch is an ordinary
+    solve -- problem_init, mass flags, the time loop of src/pdepe.jl:90-108 with the Newton loop inside (in C,
+    sb_solve_steps) -- on its own stream and host thread; instances are independent, so the results are those of
+    the single-batch call."""
+    import threading
+    ctx = ctx or default_context(0)
+    B, npde, Nx = pdefun.batch, pdefun.npde, x.size
+    timeSteps, tau = time_grid(tspan, params.tstep)
+    if callable(icfun):
+        u0 = np.asarray(icfun(x), dtype=np.float64)
+    else:
+        u0 = np.asarray(icfun, dtype=np.float64)
+    shared = u0.size == Nx * npde
+    u0 = u0.reshape((1 if shared else B), Nx, npde)
+    bounds = [int(round(i * B / streams)) for i in range(streams + 1)]
+    out = pinned_empty((B, Nx, npde))
+    devs, errors = [], []
+    for i, c in enumerate(_stream_contexts(ctx, streams)):
+        lo, hi = bounds[i], bounds[i + 1]
+        fn = Functor(pdefun.id, pdefun.params[lo:hi])
+        dev = _acquire(c, m, x, fn, design)
+        dev.upload(np.broadcast_to(u0, (hi - lo, Nx, npde)) if shared else u0[lo:hi])
+        dev.mass_flags(timeSteps[0])
+        devs.append((dev, lo, hi))
+
+    def work(dev, lo, hi):
+        try:
+            if timeSteps.size > 1:
+                dev.solve_steps(timeSteps, tau, params.tol, params.maxit)
+            dev.download(out[lo:hi])
+        except Exception as e:          # re-raised on the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=d) for d in devs[1:]]
+    for t in threads:
+        t.start()
+    work(*devs[0])
+    for t in threads:
+        t.join()
+    for dev, _, _ in devs:
+        _release(dev)
+    if errors:
+        raise errors[0]
+    u = out[:, :, 0] if npde == 1 else np.ascontiguousarray(np.transpose(out, (0, 2, 1)))
+    return DiffEqArray([u], timeSteps[-1:])
+
+
 def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused_tma", save="all",
-          squeeze=None, c_loop=False, return_device=False, alias_compat=False, **kwargs):
+          squeeze=None, c_loop=False, return_device=False, alias_compat=False, streams=1, **kwargs):
     """Batched pdepe.  With `tspan`: transient solve by implicit Euler (src/pdepe.jl:42-128); without:
     stationary solve by one Newton solve with tau = Inf, t = 1 (src/pdepe.jl:156-192).
 
     Extra keyword arguments of this implementation: ctx (Context / GPU), design ("fused" | "split"),
     save ("all": every time step as the reference does | "last": only u(t_end), for very large batches),
-    squeeze (drop the batch axis; default: when the functor has a single instance).
+    squeeze (drop the batch axis; default: when the functor has a single instance),
+    streams (with save="last" and c_loop: split the batch into that many contiguous sub-batches, each with its own
+    CUDA stream, time loop and Newton loop on its own host thread -- the sub-batches' launches interleave on the
+    GPU, so one sub-batch's nearly converged iterations no longer leave SMs idle).
     Returns what the reference returns: sol | (sol, pb) | (sol, storage) | (sol, pb, storage); stationary:
     u | (u, hist) | (u, pb) | (u, pb, hist).  Unlike the reference stored states are the
     true states, not the in-place masked aliases; alias_compat=True reproduces the reference's stored values
@@ -712,6 +774,10 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     else:
         assert not (np.isscalar(params.tstep) and np.isinf(params.tstep)), \
             "Adjust time step or try the alternative method for solving elliptic problems"
+
+    if (streams > 1 and not stationary and save != "all" and c_loop and not params.hist and not params.data
+            and not return_device and params.solver == "euler" and isinstance(pdefun, Functor) and pdefun.batch >= 2 * streams):
+        return _pdepe_streams(m, pdefun, icfun, bdfun, x, tspan, params, ctx, design, squeeze, int(streams))
 
     Nx, npde, inival, pb = problem_init(m, x, (0, 1) if stationary else tspan, pdefun, icfun, bdfun, params, ctx, design)
     dev = pb.device

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -46,7 +47,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
 
-long long g_launches = 0;  // kernels launched by this library (all contexts; not thread-safe by design)
+std::atomic<long long> g_launches{0};  // kernels launched by this library (all contexts; contexts may run on different host threads)
 
 // Kernel handles of one problem: host function pointers of the statically compiled registry kernels, or
 // cudaKernel_t handles of kernels compiled at run time (NVRTC) for a user functor.  Both launch through

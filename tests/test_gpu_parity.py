@@ -422,3 +422,21 @@ def test_large_batch_of_small_problems(ctx, oracle):
     idx = np.array([0, 1, 2, 9999, 20000])
     r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params[idx], c.initial()[idx], tg, None)
     assert _relerr(sol.u[-1][idx], r["u"][:, :, 0]) < RTOL
+
+
+@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 64, 1024, 5), ("4", 48, 256, 20)])
+@pytest.mark.parametrize("streams", [2, 3])
+def test_sub_batches_on_streams_are_transparent(ctx, oracle, cfg, B, Nx, nsteps, streams):
+    """pdepe(streams=n): the batch split into contiguous sub-batches, each with its own stream and host loops, gives
+    bit-identical states to the single-batch call (instances are independent) and matches the oracle."""
+    c = ex.baseline_case(cfg, B=B, Nx=Nx)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:nsteps + 1]
+    fn = sb.Functor(c.functor, c.params)
+    one = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, save="last", squeeze=False, c_loop=True)
+    many = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, save="last", squeeze=False, c_loop=True,
+                    streams=streams)
+    assert np.array_equal(one.u[-1], many.u[-1])
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None)
+    uo = r["u"][:, :, 0] if c.npde == 1 else np.transpose(r["u"], (0, 2, 1))
+    assert _relerr(many.u[-1], uo) < RTOL
