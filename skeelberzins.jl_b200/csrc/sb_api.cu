@@ -249,6 +249,7 @@ struct sb_problem {
     long launched = 0, confirmed = 0;   // Newton-iteration launches / delivered counts of the current step
     long slot_base = 0;                 // ring slot of the step's iteration 0 (the ring runs on across steps)
     long total_launched = 0;            // launches through the ring since the problem was created
+    long predicted_iters = 0;           // Newton iterations the previous solve needed (0: unknown) -- speculation limit
     int slot_of(long it) const { return (int)((slot_base + it) % kSlots); }
     int64_t last_active = 0;
     bool mass_ready = false;
@@ -1300,10 +1301,16 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
     CU(cudaSetDevice(pb->ctx->device));
     const long depth = 2;  // iterations kept in flight beyond the last one whose count has been read
     const long base = pb->launched;
+    // Speculation limit: launches are enqueued ahead of the host's knowledge only up to the number of iterations
+    // the previous solve needed (consecutive time steps need the same or one fewer); past that, the next iteration
+    // is launched only once the previous one has reported active instances.  A step that behaves like its
+    // predecessor then ends without a surplus no-op launch; one that needs more pays a host round trip.
+    const long limit = (pb->predicted_iters > 0 && !getenv("SB_NO_PREDICT")) ? pb->predicted_iters : (long)maxit;
     long done = 0;          // iterations whose active count has been read
     int64_t n_act = pb->pd.B;
     while (true) {
-        while (pb->launched - base < maxit && (pb->launched - base) - done < depth) {
+        while (pb->launched - base < maxit && (pb->launched - base) - done < depth &&
+               ((pb->launched - base) < limit || (pb->launched - base) == done)) {
             int rc = sb_newton_iteration(pb, tol);
             if (rc) return rc;
         }
@@ -1317,6 +1324,7 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
         if (n_act == 0) break;
         if (done >= maxit) break;
     }
+    pb->predicted_iters = done;
     if (iters_done) *iters_done = (int)(pb->launched - base);
     if (n_act != 0) return fail(SB_ERR_CONVERGENCE, "convergence failed");  // src/utils.jl:336
     return SB_OK;
