@@ -54,8 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=64, help="instances in the cpu_baseline sample")
     ap.add_argument("--python-loop", action="store_true", help="drive Newton from Python instead of the C loop")
     ap.add_argument("--streams", type=int, default=0, help="contiguous sub-batches per GPU, each with its own CUDA stream and "
-                    "host loops (1 = the whole batch in lock step; 0 = the measured best per config: 2 for cfg2 and cfg4, "
-                    "whose instances need different numbers of Newton iterations or long step sequences, else 1)")
+                    "host loops (1 = the whole batch in lock step; 0 = the measured best: 2 for the transient batched configs)")
     return ap.parse_args()
 
 
@@ -244,7 +243,7 @@ def run_ours(args):
     tol, maxit = 1e-10, 100
     nsteps = tg.size - 1
     stationary = case.tspan is None
-    want_streams = args.streams if args.streams > 0 else {"2": 2, "4": 2}.get(str(args.config), 1)
+    want_streams = args.streams if args.streams > 0 else 2
     n_str = 1 if (stationary or args.python_loop or Bp < 2 * want_streams) else want_streams
 
     # one context (= CUDA stream) and one device problem per contiguous sub-batch

@@ -208,7 +208,12 @@ int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active);
 int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done);
 
 /* convenience: nsteps implicit-Euler steps (the time loop of src/pdepe.jl:90-108 driven from C; no state is
- * stored in between).  tgrid[nsteps+1] is the time grid; tau > 0: constant time step, else tau_i = diff(tgrid).  */
+ * stored in between).  tgrid[nsteps+1] is the time grid; tau > 0: constant time step, else tau_i = diff(tgrid).
+ * With the fused_tma design the host still launches every Newton iteration and reads every launch's count, but a
+ * launch that finds every instance converged starts the next time step itself (time grid and step counter on the
+ * device), so the launches enqueued ahead of the host's knowledge are never no-ops.  Same states and iteration
+ * counts as the step-by-step loop (SB_NO_DEVICE_STEPPING=1 selects that loop).  steps_done (may be NULL) = completed
+ * time steps; SB_ERR_CONVERGENCE as in sb_newton_solve.                                                              */
 int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done);
 
 /* diagnostics (host arrays of length B unless stated)                                            */

@@ -393,7 +393,7 @@ class DeviceProblem:
 # again with the same mesh / batch / functor, and re-using the device allocations (cudaMalloc/cudaFree
 # synchronise the device) is what keeps the end-to-end call close to the kernel time.
 _pool = {}
-_POOL_MAX = 2
+_POOL_MAX = 4          # pooled device problems (a call with streams=n holds n of them)
 
 
 def _mesh_fingerprint(x):

@@ -233,6 +233,9 @@ struct sb_problem {
     std::vector<LevelDev> lv;
     int top_R = 1;
     double *d_lm = nullptr, *d_partial = nullptr;
+    int* d_auto = nullptr;              // device-side stepping: {time step, iteration} (sb_solve_steps)
+    double* d_tgrid = nullptr;          // its time grid
+    int tgrid_cap = 0;
     int p_grid = 0;                 // persistent grid of the fused_tma kernel (0: not configured yet)
     size_t p_smem = 0;
     std::vector<double> xmesh, xi, zeta;
@@ -814,12 +817,12 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     TRY(dev_alloc(&pb->d_list, (size_t)2 * B));
 #undef TRY
     if (rc != SB_OK) { sb_problem_destroy(pb); return rc; }
-    cudaError_t e = cudaHostAlloc((void**)&pb->h_count, kSlots * sizeof(unsigned int), cudaHostAllocMapped);
+    cudaError_t e = cudaHostAlloc((void**)&pb->h_count, 3 * kSlots * sizeof(unsigned int), cudaHostAllocMapped);  // count | step | iteration
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     unsigned int* d_hcount = nullptr;
     e = cudaHostGetDevicePointer((void**)&d_hcount, pb->h_count, 0);
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
-    for (int i = 0; i < kSlots; ++i) pb->h_count[i] = 0;
+    for (int i = 0; i < 3 * kSlots; ++i) pb->h_count[i] = 0;
     cudaStream_t st = ctx->stream;
     e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && f_nparams > 0)
@@ -885,7 +888,7 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
     cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
-    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list); cudaFree(pb->d_lm); cudaFree(pb->d_partial);
+    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list); cudaFree(pb->d_lm); cudaFree(pb->d_partial); cudaFree(pb->d_auto); cudaFree(pb->d_tgrid);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
@@ -1330,9 +1333,65 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
     return SB_OK;
 }
 
+// The time loop with device-side stepping (fused_tma): the host launches Newton iterations exactly as in
+// sb_newton_solve -- two in flight beyond the one it waits for -- but a launch that finds every instance converged
+// starts the next time step itself (ProbDev::auto_*), so the look-ahead launches at the end of a step are the first
+// iterations of the next one instead of no-ops and the GPU never waits for the host's "step finished" round trip.
+// The host follows through the mapped (count, step, iteration) triple of every launch and enforces maxit.
+static int solve_steps_auto(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done) {
+    cudaStream_t st = pb->ctx->stream;
+    if (pb->tgrid_cap < nsteps + 1) {
+        if (pb->d_tgrid) CU(cudaFree(pb->d_tgrid));
+        CU(cudaMalloc((void**)&pb->d_tgrid, (size_t)(nsteps + 1) * sizeof(double)));
+        pb->tgrid_cap = nsteps + 1;
+    }
+    if (!pb->d_auto) CU(cudaMalloc((void**)&pb->d_auto, 2 * sizeof(int)));
+    CU(cudaMemcpyAsync(pb->d_tgrid, tgrid, (size_t)(nsteps + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(pb->d_auto, 0, 2 * sizeof(int), st));
+    const double tau0 = (tau > 0) ? tau : tgrid[1] - tgrid[0];
+    int rc = sb_begin_step(pb, tgrid[1], std::isinf(tau0) ? 0.0 : 1.0 / tau0);   // b = M.*u_0 (or already there)
+    if (rc) return rc;
+    pb->pd.auto_on = 1; pb->pd.auto_nsteps = nsteps; pb->pd.auto_state = pb->d_auto;
+    pb->pd.auto_tgrid = pb->d_tgrid; pb->pd.auto_tau = (tau > 0) ? tau : -1.0;
+    const long depth = 2;
+    long read = 0;
+    int fail_step = -1, last_step = 0;
+    bool finished = false;
+    while (!finished) {
+        while (pb->launched - read <= depth) {
+            rc = sb_newton_iteration(pb, tol);
+            if (rc) { pb->pd.auto_on = 0; return rc; }
+        }
+        unsigned int count;
+        rc = wait_slot(pb, pb->slot_of(read), &count);
+        if (rc) { pb->pd.auto_on = 0; return rc; }
+        const int s = pb->slot_of(read);
+        const int step = (int)*((volatile unsigned int*)pb->h_count + kSlots + s);
+        const int iter = (int)*((volatile unsigned int*)pb->h_count + 2 * kSlots + s);
+        ++read;
+        last_step = step;
+        if (step >= nsteps || (count == 0 && step == nsteps - 1)) finished = true;
+        else if (count != 0 && iter + 1 >= maxit) { fail_step = step; finished = true; }   // src/utils.jl:336
+    }
+    // launches still in flight find nothing to do (or, after a failure, iterate on); what follows in the stream waits for them
+    pb->pd.auto_on = 0;
+    pb->confirmed = pb->launched;
+    pb->last_active = (fail_step >= 0) ? 1 : 0;
+    pb->b_ready = (fail_step < 0);
+    pb->predicted_iters = 0;
+    if (steps_done) *steps_done = (fail_step >= 0) ? fail_step : std::min(last_step + 1, nsteps);
+    if (fail_step >= 0) return fail(SB_ERR_CONVERGENCE, "convergence failed");
+    return SB_OK;
+}
+
 int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done) {
     if (!pb || !tgrid || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
     if (steps_done) *steps_done = 0;
+    if (pb->design_pending == SB_DESIGN_FUSED_TMA && !pb->longmesh && !pb->prof && !pb->pd.hist && nsteps > 1 && maxit >= 2 &&
+        !getenv("SB_NO_DEVICE_STEPPING")) {
+        CU(cudaSetDevice(pb->ctx->device));
+        return solve_steps_auto(pb, nsteps, tgrid, tau, tol, maxit, steps_done);
+    }
     for (int i = 0; i < nsteps; ++i) {                                    // src/pdepe.jl:90
         const double tau_i = (tau > 0) ? tau : tgrid[i + 1] - tgrid[i];  // :92 (scalar tstep | diff of the vector grid)
         int rc = sb_begin_step(pb, tgrid[i + 1], std::isinf(tau_i) ? 0.0 : 1.0 / tau_i);

@@ -67,7 +67,15 @@ struct ProbDev {
     unsigned int* active_count;  // [slots]
     int* list[2];          // compacted indices of the instances still active (ping-pong between iterations)
     unsigned int* done_count;             // [slots] groups (systems' thread groups / CTAs) that finished the launch
-    volatile unsigned int* host_count;    // [slots] mapped pinned host memory: active count of a finished launch
+    volatile unsigned int* host_count;    // [3][slots] mapped pinned host memory: active count of a finished launch,
+                                          // and (device-side stepping) the time step / iteration it belonged to
+    // Device-side time stepping (sb_solve_steps): a launch that finds every instance converged starts the next time
+    // step itself, so the host's look-ahead launches are useful work instead of no-ops; the host follows through
+    // host_count.  Off (auto_on == 0) for every other entry point.
+    int auto_on, auto_nsteps;
+    int* auto_state;                      // [2] time step, Newton iteration inside it: what the next launch continues with
+    const double* auto_tgrid;             // [auto_nsteps + 1]
+    double auto_tau;                      // constant time step, or <= 0: tgrid[s+1] - tgrid[s]
 };
 
 // Completion notice of a Newton-iteration launch without a copy node in the stream: every thread group takes a
@@ -76,12 +84,19 @@ struct ProbDev {
 // The counters live in a ring of kRingSlots launches that cleans itself: the launch that closes slot s zeroes slot
 // s + kRingSlots/2, which no launch in flight can be using, so no memset ever sits between two Newton-iteration kernels.
 constexpr int kRingSlots = 128;
-SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups) {
+SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups, int auto_step = -1, int auto_iter = 0) {
     __threadfence();
     const unsigned int ticket = atomicAdd(pd.done_count + slot, 1u);
     if (ticket == total_groups - 1) {
         __threadfence();
         const unsigned int c = atomicAdd(pd.active_count + slot, 0u);
+        if (auto_step >= 0) {  // device-side stepping: where the next launch continues, and what this one was
+            pd.auto_state[0] = auto_step;
+            pd.auto_state[1] = auto_iter + 1;
+            pd.host_count[kRingSlots + slot] = (unsigned int)auto_step;
+            pd.host_count[2 * kRingSlots + slot] = (unsigned int)auto_iter;
+            __threadfence_system();
+        }
         pd.host_count[slot] = c;
         const int far = (slot + kRingSlots / 2) % kRingSlots;
         pd.active_count[far] = 0u;
@@ -649,9 +664,8 @@ SB_D void load_chunk(const double* base, int t, double (&v)[R][P]) {
 // host; the total counter is a fire-and-forget reduction.  Returns the position in the compacted list of
 // still-active instances (-1 when the instance converged); the caller stores list_out[pos] = k later, so
 // the latency of the returning atomic is not exposed.
-SB_D int finalize_system(const ProbDev& pd, int64_t k, double ss, double tol, int slot) {
+SB_D int finalize_system(const ProbDev& pd, int64_t k, double ss, double tol, int slot, int it) {
     const double nm = ::sqrt(ss);
-    const int it = pd.iter_no;
     pd.norm[k] = nm;
     if (pd.hist && it < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it] = nm;
     pd.iters[k] = it + 1;
@@ -679,7 +693,7 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
     }
     ss = system_sum<TT>(ss, sm, t);
     if (t == 0) {
-        const int pos = finalize_system(pd, k, ss, tol, slot);
+        const int pos = finalize_system(pd, k, ss, tol, slot, pd.iter_no);
         if (pos >= 0 && list_out) list_out[pos] = (int)k;
         group_done(pd, slot, gridDim.x * (TT == 32 ? kWarpBlockThreads / 32 : 1));
     }
@@ -928,15 +942,37 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
     }
 
     pdl_wait();  // everything below reads what the previous launch wrote (active count, list, u, b)
-    const int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
-    const int* list_in = (prev_slot < 0) ? nullptr : pd.list[parity];
+    int n_in = (prev_slot < 0) ? (int)pd.B : (int)pd.active_count[prev_slot];
+    int it_no = pd.iter_no;                       // Newton iteration number inside the step
+    // first iteration of a step that skipped k_begin_step: the Newton iterate is b = M.*u_n itself (src/utils.jl:309)
+    bool from_b = pd.lazy_b && it_no == 0;
+    int auto_step = -1;
+    if (pd.auto_on) {  // device-side stepping: step / iteration come from the previous launch, not from the host
+        const int s0 = pd.auto_state[0], i0 = pd.auto_state[1];
+        const bool advance = (i0 > 0 && n_in == 0);          // the previous launch converged the last instances
+        auto_step = s0 + (advance ? 1 : 0);
+        it_no = advance ? 0 : i0;
+        if (auto_step >= pd.auto_nsteps) {                    // past the last time step: nothing left to do
+            if (threadIdx.x == 0) mbar_wait(mesh_bar, 0);
+            __syncthreads();
+            if (t == 0) group_done(pd, slot, gridDim.x * G, auto_step, it_no);
+            return;
+        }
+        tt = pd.auto_tgrid[auto_step + 1];
+        const double tau_s = (pd.auto_tau > 0.0) ? pd.auto_tau : tt - pd.auto_tgrid[auto_step];
+        inv_tau = (tau_s > 1.0e300) ? 0.0 : 1.0 / tau_s;
+        from_b = (it_no == 0);                                // every instance left b = M.*u_{n+1} when it converged
+        if (from_b) n_in = (int)pd.B;
+        parity = it_no & 1;
+    }
+    const int* list_in = (from_b || prev_slot < 0) ? nullptr : pd.list[parity];
     int* list_out = pd.list[parity ^ 1];
     const int stride = gridDim.x * G;
     int j = blockIdx.x * G + g;
     if (blockIdx.x * G >= n_in) {  // whole CTA has nothing to do
         if (threadIdx.x == 0) mbar_wait(mesh_bar, 0);  // do not exit with the bulk copy in flight
         __syncthreads();
-        if (t == 0) group_done(pd, slot, gridDim.x * G);
+        if (t == 0) group_done(pd, slot, gridDim.x * G, auto_step, it_no);
         return;
     }
 
@@ -949,8 +985,6 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         if (j + stride < n_in) k_next2 = list_in ? list_in[j + stride] : j + stride;
     }
     // fetch instance kk into buffer `stage`; its index is published in kslot[seq & 1] (seq = position in this group's sequence)
-    // first iteration of a step that skipped k_begin_step: the Newton iterate is b = M.*u_n itself (src/utils.jl:309)
-    const bool from_b = pd.lazy_b && pd.iter_no == 0;
     auto issue = [&](long long kk, int stage, int seq) {
         kslot[seq & 1] = kk;
         mbar_expect_tx(bar + stage, (from_b ? 1 : 2) * kBytes + kPrmBytes + kMassBytes);
@@ -1045,13 +1079,13 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         }
         if (t == 0) {
             if (from_b) pd.active[k] = 1;
-            pend_pos = finalize_system(pd, k, ss, tol, slot);
+            pend_pos = finalize_system(pd, k, ss, tol, slot, it_no);
             pend_k = (int)k;
         }
     }
     if (t == 0) {
         if (pend_pos >= 0) list_out[pend_pos] = pend_k;
-        group_done(pd, slot, gridDim.x * G);
+        group_done(pd, slot, gridDim.x * G, auto_step, it_no);
     }
 }
 

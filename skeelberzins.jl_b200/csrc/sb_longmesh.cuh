@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) k6_finalize(ProbDev pd, const double* par
         if (t == 0) {
 #pragma unroll
             for (int w = 1; w < 8; ++w) ss += red[w];
-            finalize_system(pd, k, ss, tol, slot);
+            finalize_system(pd, k, ss, tol, slot, pd.iter_no);
         }
     }
     if (t == 0) group_done(pd, slot, gridDim.x);

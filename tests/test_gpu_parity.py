@@ -440,3 +440,37 @@ def test_sub_batches_on_streams_are_transparent(ctx, oracle, cfg, B, Nx, nsteps,
     r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None)
     uo = r["u"][:, :, 0] if c.npde == 1 else np.transpose(r["u"], (0, 2, 1))
     assert _relerr(many.u[-1], uo) < RTOL
+
+
+@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 40, 1024, 8), ("3a", 24, 512, 10), ("4", 24, 256, 12), ("2", 700, 100, 4)])
+@pytest.mark.parametrize("vector_tstep", [False, True])
+def test_device_side_stepping_matches_the_host_loop(ctx, oracle, cfg, B, Nx, nsteps, vector_tstep):
+    """sb_solve_steps lets a look-ahead launch that finds every instance converged start the next time step itself.
+    States and per-instance iteration totals must equal those of the loop driven step by step from the host, and the
+    oracle's."""
+    c = ex.baseline_case(cfg, B=B, Nx=Nx)
+    tg, tau = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:nsteps + 1]
+    fn = sb.Functor(c.functor, c.params)
+    kw = dict(tstep=(tg if vector_tstep else c.tstep))
+    sols, its = [], []
+    for c_loop in (False, True):
+        sol, dev = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, save="last", squeeze=False,
+                            c_loop=c_loop, return_device=True, **kw)
+        sols.append(sol.u[-1].copy())
+        its.append(dev.total_iters().copy())
+        assert (dev.status() == 0).all()
+        dev.close()
+    assert np.array_equal(sols[0], sols[1])
+    assert np.array_equal(its[0], its[1])
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None if vector_tstep else tau)
+    uo = r["u"][:, :, 0] if c.npde == 1 else np.transpose(r["u"], (0, 2, 1))
+    assert _relerr(sols[1], uo) < RTOL
+    assert np.array_equal(its[1], r["iters"].sum(axis=1))
+
+
+def test_device_side_stepping_reports_convergence_failure(ctx):
+    c = ex.example102()
+    fn = sb.Functor(c.functor, c.params)
+    with pytest.raises(sb.ConvergenceFailed):
+        sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=ctx, tstep=c.tstep, save="last", c_loop=True, maxit=3)
