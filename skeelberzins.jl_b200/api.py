@@ -716,13 +716,14 @@ def _pdepe_streams(m, pdefun, icfun, bdfun, x, tspan, params, ctx, design, squee
     for i, c in enumerate(_stream_contexts(ctx, streams)):
         lo, hi = bounds[i], bounds[i + 1]
         fn = Functor(pdefun.id, pdefun.params[lo:hi])
-        dev = _acquire(c, m, x, fn, design)
-        dev.upload(np.broadcast_to(u0, (hi - lo, Nx, npde)) if shared else u0[lo:hi])
-        dev.mass_flags(timeSteps[0])
-        devs.append((dev, lo, hi))
+        devs.append((_acquire(c, m, x, fn, design), lo, hi))
 
     def work(dev, lo, hi):
+        # upload, solve and download of a sub-batch on its own stream: the copies of one sub-batch overlap the
+        # other's kernels
         try:
+            dev.upload(np.broadcast_to(u0, (hi - lo, Nx, npde)) if shared else u0[lo:hi])
+            dev.mass_flags(timeSteps[0])
             if timeSteps.size > 1:
                 dev.solve_steps(timeSteps, tau, params.tol, params.maxit)
             dev.download(out[lo:hi])
