@@ -474,3 +474,31 @@ def test_device_side_stepping_reports_convergence_failure(ctx):
     fn = sb.Functor(c.functor, c.params)
     with pytest.raises(sb.ConvergenceFailed):
         sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=ctx, tstep=c.tstep, save="last", c_loop=True, maxit=3)
+
+
+def test_device_side_stepping_hands_over_to_the_host_loop_and_back(ctx, oracle):
+    """sb_solve_steps (device-side stepping) for a few steps, then steps driven call by call from the host, then
+    sb_solve_steps again on the same problem: the ring of counters, the look-ahead launches still in flight and the
+    'b is ready' hand-over must all line up.  Final state and iteration totals against the oracle."""
+    c = ex.baseline_case("2", B=96, Nx=512)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:13]
+    fn = sb.Functor(c.functor, c.params)
+    dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn)
+    dev.upload(c.initial())
+    dev.mass_flags(tg[0])
+    tol, maxit = 1e-10, 100
+    dev.solve_steps(tg[0:5], None, tol, maxit)                       # steps 1-4 on the device-side path
+    for i in range(4, 8):                                           # steps 5-8 from the host, mixed loops
+        dev.begin_step(tg[i + 1], 1.0 / (tg[i + 1] - tg[i]))
+        if i % 2:
+            dev.newton_solve(tol, maxit)
+        else:
+            sb.api._newton_loop(dev, tol, maxit)
+    dev.solve_steps(tg[8:13], None, tol, maxit)                      # steps 9-12 on the device-side path again
+    u = dev.download()
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None)
+    assert _relerr(u, r["u"]) < RTOL
+    assert np.array_equal(dev.total_iters(), r["iters"].sum(axis=1))
+    assert (dev.status() == 0).all()
+    dev.close()
