@@ -20,7 +20,7 @@
 
 namespace sb {
 
-constexpr int kLongR = 8, kLongT0 = 128;  // level 0: rows per thread / threads per tile (tile = 1024 mesh nodes)
+constexpr int kLongR = 8, kLongT0 = 64;   // level 0: rows per thread / threads per tile (tile = 512 mesh nodes; measured: 128 -> 137 us, 64 -> 134 us, 32 -> 136 us per cfg5 iteration)
 constexpr int kLongTT = 256;              // stored levels and the top level: threads per tile
 constexpr int kLongRS = 16;               // stored levels (1 .. top-1): rows per thread = reduction factor per level
 
