@@ -101,6 +101,11 @@ enum sb_design {
 const char* sb_version(void);
 const char* sb_last_error(void);
 int sb_device_count(int* count);
+/* Guard mode (environment SB_GUARD=1 before the first call): every device array of a problem is allocated with
+ * 4 KiB of canary bytes on both sides, checked when it is freed.  violations = arrays whose canaries were overwritten
+ * so far, arrays_checked (may be NULL) = arrays checked so far.  A substitute for a memory checker where none can run. */
+int sb_debug_guard_violations(int64_t* violations, int64_t* arrays_checked);
+
 /* number of CUDA kernels this library has launched so far in the process (bench.py's gpu_launches) */
 int sb_kernel_launches(int64_t* count);
 /* stream == NULL: the context creates its own non-blocking stream; otherwise a cudaStream_t of the

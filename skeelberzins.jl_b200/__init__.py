@@ -10,7 +10,7 @@ from . import examples, sharding, timegrid  # noqa: F401
 from .api import (ODEFunction, ODEProblem, jac_prototype, reshape_solution,  # noqa: F401
                   ConvergenceFailed, Context, DeviceProblem, DiffEqArray, Functor, Params,  # noqa: F401
                   ProblemDefinition, SBError, SkeelBerzinsDiscretization, assemble_, default_context,
-                  functor_info, interpolate_sol_space, interpolate_sol_time, kernel_launches, mass_matrix, pdeval, newton, newton_stat, pdepe, pinned_empty, problem_init, register_user_functor, user_functor_compile_check)
+                  clear_pool, functor_info, guard_violations, interpolate_sol_space, interpolate_sol_time, kernel_launches, mass_matrix, pdeval, newton, newton_stat, pdepe, pinned_empty, problem_init, register_user_functor, user_functor_compile_check)
 from .timegrid import julia_range, time_grid  # noqa: F401
 
 __version__ = "0.1.0"

@@ -23,6 +23,7 @@ SIGNATURES = {
     "sb_last_error": (_c.c_char_p, []),
     "sb_device_count": (_c.c_int, [_c.POINTER(_c.c_int)]),
     "sb_kernel_launches": (_c.c_int, [_c.POINTER(_c.c_int64)]),
+    "sb_debug_guard_violations": (_c.c_int, [_c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
     "sb_host_alloc": (_c.c_int, [_c.c_size_t, _c.POINTER(_vp)]),
     "sb_host_free": (_c.c_int, [_vp]),
     "sb_ctx_create": (_c.c_int, [_c.c_int, _vp, _c.POINTER(_vp)]),

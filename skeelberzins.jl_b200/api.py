@@ -76,6 +76,13 @@ def functor_info(fid):
     return npde.value, nprm.value, name.value.decode()
 
 
+def guard_violations():
+    """(violations, arrays_checked) of guard mode (SB_GUARD=1): device arrays whose canary bytes were overwritten."""
+    v, n = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(_lib.load().sb_debug_guard_violations(ctypes.byref(v), ctypes.byref(n)))
+    return v.value, n.value
+
+
 def kernel_launches():
     """CUDA kernels launched by the library so far in this process."""
     n = ctypes.c_int64()

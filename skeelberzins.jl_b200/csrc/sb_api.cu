@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/skeelberzins_b200.h"
@@ -197,9 +199,59 @@ inline double ipow(double x, int n) {
     return r;
 }
 
+// ---- guard mode (SB_GUARD=1): every device array of a problem gets 4 KiB of canary bytes on both sides; they are
+// checked when the array is freed and violations are counted (sb_debug_guard_violations).  compute-sanitizer is not
+// available on every pool; this catches out-of-bounds WRITES of any kernel over a whole test run.
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+std::atomic<long long> g_guard_violations{0}, g_guard_arrays{0};
+struct GuardRec { char* base; size_t bytes; };
+std::mutex g_guard_mu;
+std::unordered_map<void*, GuardRec> g_guard;
+bool guard_on() { static const bool on = getenv("SB_GUARD") != nullptr; return on; }
+
+cudaError_t guarded_malloc(void** p, size_t bytes) {
+    if (!guard_on()) return cudaMalloc(p, bytes);
+    char* base = nullptr;
+    cudaError_t e = cudaMalloc((void**)&base, bytes + 2 * kGuardBytes);
+    if (e != cudaSuccess) return e;
+    cudaMemset(base, kGuardByte, kGuardBytes);
+    cudaMemset(base + kGuardBytes + bytes, kGuardByte, kGuardBytes);
+    *p = base + kGuardBytes;
+    static std::atomic<bool> selftest{getenv("SB_GUARD_SELFTEST") != nullptr};   // positive control: spoil one canary byte once
+    if (selftest.exchange(false)) cudaMemset(base + kGuardBytes + bytes, 0, 1);
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guard[*p] = GuardRec{base, bytes};
+    return cudaSuccess;
+}
+
+cudaError_t guarded_free(void* p) {
+    if (!p) return cudaSuccess;
+    if (guard_on()) {
+        GuardRec r{nullptr, 0};
+        {
+            std::lock_guard<std::mutex> lk(g_guard_mu);
+            auto it = g_guard.find(p);
+            if (it != g_guard.end()) { r = it->second; g_guard.erase(it); }
+        }
+        if (r.base) {
+            std::vector<unsigned char> h(2 * kGuardBytes);
+            cudaDeviceSynchronize();
+            cudaMemcpy(h.data(), r.base, kGuardBytes, cudaMemcpyDeviceToHost);
+            cudaMemcpy(h.data() + kGuardBytes, r.base + kGuardBytes + r.bytes, kGuardBytes, cudaMemcpyDeviceToHost);
+            bool bad = false;
+            for (unsigned char c : h) bad |= (c != kGuardByte);
+            if (bad) ++g_guard_violations;
+            ++g_guard_arrays;
+            return cudaFree(r.base);
+        }
+    }
+    return cudaFree(p);
+}
+
 template <class T>
 int dev_alloc(T** p, size_t n) {
-    CU(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CU(guarded_malloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
     return SB_OK;
 }
 
@@ -281,9 +333,9 @@ size_t node_elems(const sb_problem* pb) { return (size_t)pb->pd.B * pb->pd.L * p
 
 int ensure_tmp(sb_problem* pb, size_t elems) {
     if (pb->tmp_elems >= elems) return SB_OK;
-    if (pb->d_tmp) cudaFree(pb->d_tmp);
+    if (pb->d_tmp) guarded_free(pb->d_tmp);
     pb->d_tmp = nullptr; pb->tmp_elems = 0;
-    CU(cudaMalloc((void**)&pb->d_tmp, elems * sizeof(double)));
+    CU(guarded_malloc((void**)&pb->d_tmp, elems * sizeof(double)));
     pb->tmp_elems = elems;
     return SB_OK;
 }
@@ -291,7 +343,7 @@ int ensure_tmp(sb_problem* pb, size_t elems) {
 int ensure_jacobian(sb_problem* pb) {
     if (pb->d_J) return SB_OK;
     const size_t n = node_elems(pb) * pb->P;
-    CU(cudaMalloc((void**)&pb->d_J, 3 * n * sizeof(double)));
+    CU(guarded_malloc((void**)&pb->d_J, 3 * n * sizeof(double)));
     pb->pd.Jl = pb->d_J; pb->pd.Jd = pb->d_J + n; pb->pd.Ju = pb->d_J + 2 * n;
     return SB_OK;
 }
@@ -522,7 +574,7 @@ int longmesh_setup(sb_problem* pb) {
         if (l > 0) total += (l + 1 < lv.size() ? 5 : 1) * lv[l].stride * B;   // (a, c, d, -) records + x (top: x only)
         if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += 8 * lv[l].up_stride * B; }
     }
-    CU(cudaMalloc((void**)&pb->d_lm, total * sizeof(double)));
+    CU(guarded_malloc((void**)&pb->d_lm, total * sizeof(double)));
     CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));
     double* p = pb->d_lm;
     for (size_t l = 0; l < lv.size(); ++l) {
@@ -532,7 +584,7 @@ int longmesh_setup(sb_problem* pb) {
         }
         if (l + 1 < lv.size()) { lv[l].sum = reinterpret_cast<double2*>(p); p += 8 * lv[l].up_stride * B; }
     }
-    CU(cudaMalloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
+    CU(guarded_malloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
     lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;
     pb->lv = lv;
     pb->top_R = lv.back().R;
@@ -597,6 +649,13 @@ int sb_host_alloc(size_t bytes, void** out) {
 
 int sb_host_free(void* p) {
     if (p) CU(cudaFreeHost(p));
+    return SB_OK;
+}
+
+int sb_debug_guard_violations(int64_t* violations, int64_t* arrays_checked) {
+    if (!violations) return fail(SB_ERR_INVALID, "violations is NULL");
+    *violations = g_guard_violations;
+    if (arrays_checked) *arrays_checked = g_guard_arrays;
     return SB_OK;
 }
 
@@ -886,9 +945,9 @@ int sb_problem_destroy(sb_problem* pb) {
     if (!pb) return SB_OK;
     cudaSetDevice(pb->ctx->device);
     cudaStreamSynchronize(pb->ctx->stream);
-    cudaFree(pb->d_mesh); cudaFree(pb->d_prm); cudaFree(pb->d_u); cudaFree(pb->d_b); cudaFree(pb->d_F); cudaFree(pb->d_J);
-    cudaFree(pb->d_mass); cudaFree(pb->d_norm); cudaFree(pb->d_hist); cudaFree(pb->d_tmp); cudaFree(pb->d_active);
-    cudaFree(pb->d_iters); cudaFree(pb->d_status); cudaFree(pb->d_total); cudaFree(pb->d_count); cudaFree(pb->d_ckpt); cudaFree(pb->d_list); cudaFree(pb->d_lm); cudaFree(pb->d_partial); cudaFree(pb->d_auto); cudaFree(pb->d_tgrid);
+    guarded_free(pb->d_mesh); guarded_free(pb->d_prm); guarded_free(pb->d_u); guarded_free(pb->d_b); guarded_free(pb->d_F); guarded_free(pb->d_J);
+    guarded_free(pb->d_mass); guarded_free(pb->d_norm); guarded_free(pb->d_hist); guarded_free(pb->d_tmp); guarded_free(pb->d_active);
+    guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
@@ -1341,11 +1400,11 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
 static int solve_steps_auto(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done) {
     cudaStream_t st = pb->ctx->stream;
     if (pb->tgrid_cap < nsteps + 1) {
-        if (pb->d_tgrid) CU(cudaFree(pb->d_tgrid));
-        CU(cudaMalloc((void**)&pb->d_tgrid, (size_t)(nsteps + 1) * sizeof(double)));
+        if (pb->d_tgrid) CU(guarded_free(pb->d_tgrid));
+        CU(guarded_malloc((void**)&pb->d_tgrid, (size_t)(nsteps + 1) * sizeof(double)));
         pb->tgrid_cap = nsteps + 1;
     }
-    if (!pb->d_auto) CU(cudaMalloc((void**)&pb->d_auto, 2 * sizeof(int)));
+    if (!pb->d_auto) CU(guarded_malloc((void**)&pb->d_auto, 2 * sizeof(int)));
     CU(cudaMemcpyAsync(pb->d_tgrid, tgrid, (size_t)(nsteps + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(pb->d_auto, 0, 2 * sizeof(int), st));
     const double tau0 = (tau > 0) ? tau : tgrid[1] - tgrid[0];
@@ -1440,7 +1499,7 @@ int sb_state_checkpoint(sb_problem* pb) {
     CU(cudaSetDevice(pb->ctx->device));
     const size_t bytes = node_elems(pb) * sizeof(double);
     { int rc = materialize_begin(pb); if (rc) return rc; }
-    if (!pb->d_ckpt) CU(cudaMalloc((void**)&pb->d_ckpt, bytes));
+    if (!pb->d_ckpt) CU(guarded_malloc((void**)&pb->d_ckpt, bytes));
     CU(cudaMemcpyAsync(pb->d_ckpt, pb->d_u, bytes, cudaMemcpyDeviceToDevice, pb->ctx->stream));
     return SB_OK;
 }
@@ -1493,10 +1552,10 @@ int sb_enable_history(sb_problem* pb, int cap) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     CU(cudaSetDevice(pb->ctx->device));
     CU(cudaStreamSynchronize(pb->ctx->stream));
-    if (pb->d_hist) { cudaFree(pb->d_hist); pb->d_hist = nullptr; }
+    if (pb->d_hist) { guarded_free(pb->d_hist); pb->d_hist = nullptr; }
     pb->pd.hist = nullptr; pb->pd.hist_cap = 0;
     if (cap > 0) {
-        CU(cudaMalloc((void**)&pb->d_hist, (size_t)pb->pd.B * cap * sizeof(double)));
+        CU(guarded_malloc((void**)&pb->d_hist, (size_t)pb->pd.B * cap * sizeof(double)));
         CU(cudaMemset(pb->d_hist, 0, (size_t)pb->pd.B * cap * sizeof(double)));
         pb->pd.hist = pb->d_hist; pb->pd.hist_cap = cap;
     }
