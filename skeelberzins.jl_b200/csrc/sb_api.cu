@@ -203,7 +203,7 @@ inline double ipow(double x, int n) {
 // checked when the array is freed and violations are counted (sb_debug_guard_violations).  compute-sanitizer is not
 // available on every pool; this catches out-of-bounds WRITES of any kernel over a whole test run.
 constexpr size_t kGuardBytes = 4096;
-constexpr int kGuardByte = 0xA5;
+constexpr int kGuardByte = 0xFF;   // all-ones: a double read from a guard region is a NaN, so out-of-bounds READS that matter poison the results
 std::atomic<long long> g_guard_violations{0}, g_guard_arrays{0};
 struct GuardRec { char* base; size_t bytes; };
 std::mutex g_guard_mu;
