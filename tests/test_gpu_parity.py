@@ -502,3 +502,24 @@ def test_device_side_stepping_hands_over_to_the_host_loop_and_back(ctx, oracle):
     assert np.array_equal(dev.total_iters(), r["iters"].sum(axis=1))
     assert (dev.status() == 0).all()
     dev.close()
+
+
+@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 1300, 1024, 4), ("3a", 2500, 512, 6), ("4", 1200, 256, 10)])
+def test_repeated_solves_are_bitwise_identical(ctx, cfg, B, Nx, nsteps):
+    """Determinism as a race detector: more instances than persistent CTAs (every CTA runs several systems through its
+    prefetch pipeline), look-ahead launches overlapping their predecessors, two streams.  Ten repetitions must give
+    the same bits -- a shared-memory or hand-over race would show up as a difference."""
+    c = ex.baseline_case(cfg, B=B, Nx=Nx)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:nsteps + 1]
+    fn = sb.Functor(c.functor, c.params)
+    ref = None
+    for rep in range(10):
+        sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, save="last", squeeze=False,
+                       c_loop=True, streams=1 + rep % 2)
+        u = np.array(sol.u[-1])
+        assert np.isfinite(u).all()
+        if ref is None:
+            ref = u
+        else:
+            assert np.array_equal(u, ref), "repetition %d differs" % rep
