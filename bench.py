@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--python-loop", action="store_true", help="drive Newton from Python instead of the C loop")
     ap.add_argument("--streams", type=int, default=0, help="contiguous sub-batches per GPU, each with its own CUDA stream and "
                     "host loops (1 = the whole batch in lock step; 0 = the measured best: 2 for the transient batched configs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's B instances PER GPU (default, what the driver's 1..8 sweep runs); "
+                         "strong: the config's B instances in total, B/N per GPU (SURVEY 8(e): 512 per GPU at N = 8)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the host-owned-loop and out-of-L2 corroboration legs")
     return ap.parse_args()
 
 
@@ -62,9 +66,16 @@ def make_case(args, world):
     from skeelberzins_jl_b200 import examples as ex
     base = ex.baseline_case(args.config)
     Bp = args.batch or base.B
+    if args.scaling == "strong":
+        Bp = max(1, Bp // world)
     Nx = args.nx or base.xmesh.size
     case = ex.baseline_case(args.config, B=Bp * world, Nx=Nx)   # the sweep spans the whole job
     return case, Bp, Nx
+
+
+def ex_case_for(args, B, Nx):
+    from skeelberzins_jl_b200 import examples as ex
+    return ex.baseline_case(args.config, B=B, Nx=Nx)
 
 
 def time_grid_of(case, args):
@@ -91,7 +102,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -222,6 +233,18 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    pinned_cores = None
+    if world > 1:
+        # every rank spins on mapped host words from one host thread per stream: give each rank its own cores so that
+        # the max-over-ranks time is not set by two ranks sharing a core
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            if per >= 2:
+                pinned_cores = cores[local * per:(local + 1) * per]
+                os.sched_setaffinity(0, pinned_cores)
+        except Exception:
+            pinned_cores = None
     if world > 1:
         # NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION/INFO; stdout carries the one JSON line only
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
@@ -401,7 +424,10 @@ def run_ours(args):
         "noop_launches_profiled": prof["noop_launches"],
         "algorithmic_bytes_per_unit": bpu[dom], "units_per_launch_avg": prof["instance_iterations"] * Nx / n_launch,
         "kernel_ms_per_step": {k: v for k, v in kern.items()},
-        "kernel_share_of_step": min(1.0, sum(kern.values()) / (ms / args.steps)),
+        # raw ratio, not clamped: the profiled pass runs the whole batch on ONE stream with an event pair around
+        # every launch (serialised, no overlap between launches or sub-batches), the timed step does not -- so the
+        # summed kernel time may exceed the step time; > 1 means "the step is all kernel, and the kernels overlap"
+        "kernel_ms_profiled_over_step_ms": sum(kern.values()) / (ms / args.steps),
         "lockstep_efficiency": prof["instance_iterations"] / float(n_launch * Bp),
     }
     # the event pairs of the profiled pass serialise consecutive launches; in the timed region they overlap
@@ -417,10 +443,77 @@ def run_ours(args):
                                            "algorithmic_bytes_per_unit": sum(bpu.values()),
                                            "per_kernel_frac": {kk: prof["instance_iterations"] * Nx * bpu[kk] / (kern[kk] * 1e-3) / 1e9 / peak for kk in kern}}
 
+    # ---- host-owned loops (the north_star's literal control structure): the host language owns the time loop and the
+    # Newton loop and makes one C call per Newton iteration (api._newton_loop is what the Julia shim's loop does) ----
+    host_loop = None
+    out_of_l2 = None
+    if world == 1 and not args.no_extras and not stationary:
+        def solve_host_loop():
+            dev.rollback()
+            dev.mass_flags(tg[0], stationary=stationary)
+            for i in range(nsteps):
+                tau_i = tau if tau is not None else tg[i + 1] - tg[i]
+                dev.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
+                sb.api._newton_loop(dev, tol, maxit)
+        solve_host_loop()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_hl = max(1, min(args.steps, 4))
+        barrier()
+        g0.record(stream)
+        for _ in range(n_hl):
+            solve_host_loop()
+        g1.record(stream)
+        barrier()
+        ms_hl = g0.elapsed_time(g1) / n_hl
+        host_loop = {"value": units_per_step / (ms_hl * 1e-3), "unit": UNIT, "ms_per_step": ms_hl, "steps": n_hl,
+                     "note": "same workload, state resident in HBM, whole batch on one stream; time loop and Newton loop "
+                             "owned by the host language (Python here, the Julia shim's loop is the same): one C call per "
+                             "Newton iteration (sb_newton_iteration) + one wait on its active count (sb_wait_iteration), "
+                             "two iterations kept in flight"}
+
+    # ---- out-of-L2 corroboration: the same kernel on a batch whose state + rhs exceed the 126 MB L2 -----------------
+    if world == 1 and not args.no_extras and not longmesh and 2 * u0.nbytes < 200e6:
+        mult = int(np.ceil(260e6 / (2 * u0.nbytes)))
+        big = ex_case_for(args, Bp * mult, Nx)
+        dbig = sb.DeviceProblem(ctx, big.m, big.xmesh, sb.Functor(big.functor, big.params), design=args.design)
+        dbig.upload(np.ascontiguousarray(np.broadcast_to(u0[:1], (Bp * mult, Nx, P))))
+        dbig.mass_flags(tg[0], stationary=stationary)
+        n_big_steps = min(nsteps, max(2, 600 // max(1, int(prof["launches"] // max(nsteps, 1)))))   # ~600 launches
+        for leg in range(2):                                   # first leg warms up, second is timed
+            if leg == 1:
+                dbig.profile_begin()
+            for i in range(n_big_steps):
+                tau_i = tau if tau is not None else tg[i + 1] - tg[i]
+                dbig.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
+                dbig.newton_solve(tol, maxit)
+        pbig = dbig.profile_end()
+        dbig.close()
+        kb = pbig["ms_solve"] if args.design != "split" else pbig["ms_assemble"] + pbig["ms_solve"]
+        bytes_big = pbig["instance_iterations"] * Nx * sum(bpu.values())
+        ach_big = bytes_big / (kb * 1e-3) / 1e9
+        tr_big = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr_big = json.load(f).get("%s_out_of_l2" % args.design)
+        except Exception:
+            pass
+        out_of_l2 = {"instances": Bp * mult, "state_plus_rhs_MB": 2 * u0.nbytes * mult / 1e6, "time_steps": n_big_steps,
+                     "achieved": ach_big, "frac": ach_big / peak, "unit": "GB/s",
+                     "avg_launch_us": 1e3 * kb / max(pbig["launches"], 1), "launches_profiled": pbig["launches"],
+                     "traffic": tr_big,
+                     "note": "same kernel and sweep, %dx the instances: the working set no longer fits the L2, so this "
+                             "fraction (and the ncu dram bytes beside it) is the HBM evidence; the headline batch "
+                             "(%.0f MB) is L2-assisted" % (mult, 2 * u0.nbytes / 1e6)}
+    roofline["out_of_l2"] = out_of_l2
+
     # ---- reduce over ranks ---------------------------------------------------------------------------
     tot_units, max_ms, max_ms_e2e = float(units_per_step), float(ms), float(ms_e2e)
+    per_rank_ms = [float(ms) / args.steps]
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x[0]) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         max_ms, max_ms_e2e = float(t[0]), float(t[1])
         s = torch.tensor([float(units_per_step), float(launches)], dtype=torch.float64, device="cuda")
@@ -446,20 +539,31 @@ def run_ours(args):
         lay = dev.layout()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg%s %s: B=%d instances/GPU x Nx=%d, %d implicit-Euler steps per bench step, "
                                    "tol 1e-10, maxit 100" % (args.config, case.name, Bp, Nx, nsteps),
                        "design": args.design, "streams": n_str, "rows_per_thread": lay["R"], "threads_per_system": lay["T"],
-                       "l2_policy": "inputs larger than L2 (state + rhs = %.0f MB per GPU%s)"
-                                    % (2 * u0.nbytes / 1e6, "; split design adds %.0f MB of F/J" % (4 * P * u0.nbytes / 1e6) if args.design == "split" else ""),
-                       "newton_loop": "python" if args.python_loop else "C (sb_newton_solve)",
+                       "l2_policy": ("state + rhs = %.0f MB per GPU %s the 126 MB L2%s; no flush between solves: every Newton "
+                                     "iteration re-reads and rewrites the whole state, so a solve sweeps it hundreds of times; "
+                                     "roofline.out_of_l2 repeats the kernel measurement on a batch that does not fit")
+                                    % (2 * u0.nbytes / 1e6, "FITS IN" if 2 * u0.nbytes < 126e6 else "exceeds",
+                                       "; split design adds %.0f MB of F/J" % (4 * P * u0.nbytes / 1e6) if args.design == "split" else ""),
+                       "time_loop": ("host (Python), one C call per Newton iteration" if args.python_loop else
+                                     "C sb_newton_solve (stationary: one Newton solve)" if stationary else
+                                     "C sb_solve_steps: time loop and Newton loop in C, device-side stepping (a launch that finds "
+                                     "every instance converged starts the next time step itself)"),
+                       "scaling_mode": "%s: %d instances per GPU, %d in total" % (args.scaling, Bp, Bp * world),
+                       "per_rank_ms_per_step": {"min": min(per_rank_ms), "median": float(np.median(per_rank_ms)),
+                                                "max": max(per_rank_ms), "all": per_rank_ms},
+                       "host_cores_per_rank": pinned_cores,
                        "instances_total": Bp * world, "units_per_step": tot_units},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": max_ms_e2e / n_e2e, "steps": n_e2e, "result_checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "host_loop": host_loop,
             "cpu_baseline": cpu,
             "instances_not_converged_or_nonfinite": status_bad,
         }

@@ -373,10 +373,11 @@ struct NewtonWork {
 };
 
 // newton, src/utils.jl:303-337 / newton_stat, :344-378 (mass == nullptr).
-// returns number of iterations (>0) or -1 on "convergence failed" (:336).  hist (may be null) gets ||h||_2.
+// returns number of iterations (>0) or -1 on "convergence failed" (:336).  hist (may be null) gets ||h||_2 of
+// the first hist_cap iterations.
 template <int P>
 static int newton(const Problem& pb, const double* b, double tau, double t, const double* mass, double tol, int maxit,
-                  double* unP1, double* hist, NewtonWork& w) {
+                  double* unP1, double* hist, NewtonWork& w, int hist_cap = 1 << 30) {
     const int N = pb.Nx;
     const size_t n = (size_t)P * N;
     w.F.resize(n); w.Jl.resize(n * P); w.Jd.resize(n * P); w.Ju.resize(n * P);
@@ -399,7 +400,7 @@ static int newton(const Problem& pb, const double* b, double tau, double t, cons
         double ss = 0.0;
         for (size_t k = 0; k < n; ++k) { unP1[k] -= w.F[k]; ss += w.F[k] * w.F[k]; }                  // :321
         double nm = std::sqrt(ss);                                                                    // :323
-        if (hist) hist[it] = nm;
+        if (hist && it < hist_cap) hist[it] = nm;
         if (nm < tol) return it + 1;                                                                  // :329-333
     }
     return -1;                                                                                        // :336
@@ -420,7 +421,7 @@ static int solve_transient(const Problem& pb, double* u, int nt, const double* t
         double tau = tau_scalar > 0 ? tau_scalar : tgrid[i + 1] - tgrid[i];                           // :92
         for (size_t k = 0; k < n; ++k) un[k] = mass[k] * un[k];                                       // :94 lmul!
         int it = newton<P>(pb, un.data(), tau, tval, mass.data(), tol, maxit, unP1.data(),
-                           hist ? hist + (size_t)i * hist_cap : nullptr, w);
+                           hist ? hist + (size_t)i * hist_cap : nullptr, w, hist_cap);
         if (iters) iters[i] = it;
         if (it < 0) return it;
         un = unP1;                                                                                    // :106

@@ -130,7 +130,7 @@ def block_tridiag_solve(Jl, Jd, Ju, F):
 
 
 def pdepe_transient(fid, m, xmesh, prm, u0, tgrid, tau=None, tol=1e-10, maxit=100, hist=False,
-                    snapshots=False, nthreads=0):
+                    snapshots=False, nthreads=0, hist_cap=0):
     """Reference pdepe (src/pdepe.jl:42-128) per instance.  tau=None -> vector-tstep semantics
     (tau_i = diff(tgrid)); a float -> constant tstep.  Returns dict(u, iters, status[, hist, snapshots])."""
     npde, nprm, x, prm, B = _prep(fid, xmesh, prm)
@@ -139,11 +139,12 @@ def pdepe_transient(fid, m, xmesh, prm, u0, tgrid, tau=None, tol=1e-10, maxit=10
     nt = tg.size
     iters = np.zeros((B, max(nt - 1, 1)), dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)
-    H = np.full((B, max(nt - 1, 1), maxit), np.nan) if hist else None
+    hist_cap = int(hist_cap) or int(maxit)        # norms kept per step (the first hist_cap iterations)
+    H = np.full((B, max(nt - 1, 1), hist_cap), np.nan) if hist else None
     S = np.empty((B, nt, x.size, npde)) if snapshots else None
     rc = lib().sbo_pdepe_transient(int(fid), int(m), x.size, _d(x), ctypes.c_int64(B), _d(prm), _d(u), nt,
                                    _d(tg), ctypes.c_double(-1.0 if tau is None else tau),
-                                   ctypes.c_double(tol), int(maxit), _i(iters), _d(H), int(maxit), _d(S),
+                                   ctypes.c_double(tol), int(maxit), _i(iters), _d(H), hist_cap, _d(S),
                                    _i(status), int(nthreads))
     assert rc == 0
     out = dict(u=u, iters=iters[:, :nt - 1], status=status)

@@ -184,11 +184,14 @@ struct ChunkThomas {
         for (int i = 0; i < P; ++i) d.a[i] = w[2 * P * P + i];
     }
 
-    // shared memory needed by finish<TT>() in doubles
-    template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
+    // shared memory of finish<TT>() in doubles: the exchange region (two equations per warp) ...
+    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : 2 * NW * (TT / 32); }
+    // ... followed by one partial sum per warp for system_sum()
+    template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : exch_doubles<TT>() + TT / 32; }
 
     // representation of the chunk's first row: x_first = y0 - v0*x_prevsep - w0*x_sep
     // and of its last interior row:             x_last  = yL - vL*x_prevsep - wL*x_sep
+    // (from the forward factors, which stay intact: the long-mesh path recomputes them on the way back)
     SB_D void summary(Vec<P>& y0, Mat<P>& v0, Mat<P>& w0, Vec<P>& yL, Mat<P>& vL, Mat<P>& wL) const {
         if constexpr (R == 1) {
             y0 = vec_zero<P>(); v0 = mat_zero<P>(); w0 = neg(mat_identity<P>());
@@ -204,6 +207,21 @@ struct ChunkThomas {
             }
         }
     }
+    // The same recurrence kept for EVERY interior row, in place: afterwards x_r = dt[r] - vt[r]*x_prevsep - ct[r]*x_sep,
+    // so the back substitution has no chain between rows (explicit()).
+    SB_D void to_explicit() {
+#pragma unroll
+        for (int r = R - 3; r >= 0; --r) {
+            dt[r] = sub_mul(dt[r], ct[r], dt[r + 1]);
+            vt[r] = sub_mul(vt[r], ct[r], vt[r + 1]);
+            ct[r] = neg(mul(ct[r], ct[r + 1]));
+        }
+    }
+    SB_D void explicit_rows(Vec<P> (&x)[R], const Vec<P>& xp, const Vec<P>& xs) const {
+        x[R - 1] = xs;
+#pragma unroll
+        for (int r = 0; r < R - 1; ++r) x[r] = sub_mul(sub_mul(dt[r], vt[r], xp), ct[r], xs);
+    }
     // reduced row of the chunk's separator, normalised to unit diagonal, given the first-row representation
     // (v0n, w0n, y0n) of the next chunk
     static SB_D void reduced_row(const Mat<P>& As_, const Mat<P>& Bs_, const Mat<P>& Cs_, const Vec<P>& ds_, const Vec<P>& yL,
@@ -216,116 +234,163 @@ struct ChunkThomas {
         const Mat<P> binv = inverse_fast(br);
         an = mul(binv, ar); cn = mul(binv, cr); dn = mul(binv, dr);
     }
-    // unknowns of the chunk's rows from its own (xs) and the previous (xp) separator unknowns
+    // unknowns of the chunk's rows from its own (xs) and the previous (xp) separator unknowns (forward factors)
     SB_D void back(Vec<P> (&x)[R], const Vec<P>& xp, const Vec<P>& xs) const {
         x[R - 1] = xs;
 #pragma unroll
         for (int r = R - 2; r >= 0; --r) x[r] = sub_mul(sub_mul(dt[r], vt[r], xp), ct[r], x[r + 1]);
     }
 
-    // solve; x[r] = unknowns of the thread's rows.  t = thread index inside the system.
     struct NoHook { SB_D void operator()() const {} };
 
     template <int TT>
     SB_D void finish(Vec<P> (&x)[R], double* sm, int t) { finish<TT>(x, sm, t, NoHook()); }
 
-    // hook(): called by every thread right after the first synchronisation point of the system's thread group
-    // (all threads have then finished reading their inputs), e.g. to start the prefetch of the next instance
+    // Solve.  x[r] = unknowns of the thread's rows, t = thread index inside the system, sm = exch_doubles<TT>() doubles.
+    //
+    // Three levels, every warp busy at every level and ONE CTA barrier:
+    //  1. thread: the R-1 interior rows were eliminated against the separator by row(); to_explicit() turns the
+    //     factors into x_r = y_r - v_r*x_prevsep - w_r*x_sep.
+    //  2. warp: the 32 separators of a warp form a tridiagonal system whose two outer couplings reach into the
+    //     neighbouring warps: lane 0 to X_prev (the previous warp's last separator), lane 31 to X_next (the FIRST
+    //     ROW of the next warp's first chunk, kept as an unknown instead of being eliminated, so nothing has to cross
+    //     the warp boundary beforehand).  Parallel cyclic reduction with shuffles; an elimination step that would
+    //     reach outside the warp is skipped, which leaves the coefficient of X_prev / X_next in the a / c slot
+    //     ("spikes" at no cost).  After 5 steps  x_sep(lane) = d - a*X_prev - c*X_next.
+    //  3. CTA: per warp two equations in (X_prev, own first row F, own last separator L, X_next) go to shared memory;
+    //     after the barrier every thread eliminates through the TT/32 warps (a few dozen flops) and keeps the two
+    //     values its own warp needs.
+    // hook(): called by every thread right after the barrier (TT == 32: after the first shuffle), when all threads
+    // of the system have finished reading their inputs, e.g. to start the prefetch of the next instance.
     template <int TT, class Hook>
     SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+        constexpr int W = TT / 32;
+        const int lane = t & 31;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
-        summary(y0, v0, w0, yL, vL, wL);
-        // (v0, w0, y0) of thread t+1
+        if constexpr (R == 1) {
+            summary(y0, v0, w0, yL, vL, wL);
+        } else {
+            to_explicit();
+            y0 = dt[0]; v0 = vt[0]; w0 = ct[0];
+            yL = dt[R - 2]; vL = vt[R - 2]; wL = ct[R - 2];
+        }
+        // (v0, w0, y0) of thread t+1; lane 31 keeps the next warp's first row as the unknown X_next: x_first = X_next
         double mine[NW], nb[NW];
         pack(mine, v0, w0, y0);
-        if constexpr (TT == 32) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const double v = __shfl_down_sync(0xffffffffu, mine[w], 1);
-                nb[w] = (t < 31) ? v : 0.0;
-            }
-            hook();
-        } else {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
-            __syncthreads();
-            hook();
-#pragma unroll
-            for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
+        for (int w = 0; w < NW; ++w) {
+            const double v = __shfl_down_sync(0xffffffffu, mine[w], 1);
+            const bool wdiag = (w >= P * P) && (w < 2 * P * P) && ((w - P * P) / P == (w - P * P) % P);
+            nb[w] = (lane < 31) ? v : ((wdiag && t != TT - 1) ? -1.0 : 0.0);   // (the system's last row has no successor)
         }
+        if constexpr (W == 1) hook();
         Mat<P> v0n, w0n; Vec<P> y0n;
         unpack(nb, v0n, w0n, y0n);
         Mat<P> an, cn; Vec<P> dn;
         reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
 
-        Vec<P> xs, xp;  // this thread's and the previous thread's separator unknowns
-        if constexpr (TT == 32) {
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {  // parallel cyclic reduction across the warp
-                double om[NW], op[NW];
-                pack(mine, an, cn, dn);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const double a = __shfl_up_sync(0xffffffffu, mine[w], s);
-                    const double c = __shfl_down_sync(0xffffffffu, mine[w], s);
-                    om[w] = (t >= s) ? a : 0.0;
-                    op[w] = (t + s < 32) ? c : 0.0;
-                }
-                Mat<P> am, cm, ap, cp; Vec<P> dm, dp;
-                unpack(om, am, cm, dm);
-                unpack(op, ap, cp, dp);
-                const Mat<P> a2 = neg(mul(an, am));
-                const Mat<P> c2 = neg(mul(cn, cp));
-                const Mat<P> b2 = sub_mul(sub_mul(mat_identity<P>(), an, cm), cn, ap);
-                const Vec<P> d2 = sub_mul(sub_mul(dn, an, dm), cn, dp);
-                const Mat<P> inv = inverse_fast(b2);
-                an = mul(inv, a2); cn = mul(inv, c2); dn = mul(inv, d2);
-            }
-            xs = dn;
-#pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const double v = __shfl_up_sync(0xffffffffu, xs.a[i], 1);
-                xp.a[i] = (t > 0) ? v : 0.0;
-            }
-        } else {
-            constexpr int Q = TT / 32;  // reduced rows per lane of warp 0
-            double* red = sm + NW * TT;
-            double* xsm = sm + 2 * NW * TT;
+        for (int s = 1; s < 32; s <<= 1) {  // parallel cyclic reduction across the warp
+            double om[NW], op[NW];
             pack(mine, an, cn, dn);
 #pragma unroll
-            for (int w = 0; w < NW; ++w) red[w * TT + t] = mine[w];
-            __syncthreads();
-            if (t < 32) {
-                ChunkThomas<P, Q> lvl2;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    double rw[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + t * Q + q];
-                    Mat<P> a, c; Vec<P> d;
-                    unpack(rw, a, c, d);
-                    lvl2.row(q, a, mat_identity<P>(), c, d);
-                }
-                Vec<P> y[Q];
-                lvl2.template finish<32>(y, nullptr, t);
-#pragma unroll
-                for (int q = 0; q < Q; ++q)
-#pragma unroll
-                    for (int i = 0; i < P; ++i) xsm[i * TT + t * Q + q] = y[q].a[i];
+            for (int w = 0; w < NW; ++w) {
+                om[w] = __shfl_up_sync(0xffffffffu, mine[w], s);
+                op[w] = __shfl_down_sync(0xffffffffu, mine[w], s);
             }
-            __syncthreads();
+            const bool hu = lane >= s, hd = lane + s < 32;   // the partner row exists inside the warp
+            Mat<P> am, cm, ap, cp; Vec<P> dm, dp;
+            unpack(om, am, cm, dm);
+            unpack(op, ap, cp, dp);
+            Mat<P> anm = an, cnp = cn;                        // multipliers of the elimination (0: step skipped)
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                xs.a[i] = xsm[i * TT + t];
-                xp.a[i] = (t > 0) ? xsm[i * TT + t - 1] : 0.0;
+            for (int i = 0; i < P * P; ++i) { anm.a[i] = hu ? an.a[i] : 0.0; cnp.a[i] = hd ? cn.a[i] : 0.0; }
+            const Mat<P> b2 = sub_mul(sub_mul(mat_identity<P>(), anm, cm), cnp, ap);
+            const Vec<P> d2 = sub_mul(sub_mul(dn, anm, dm), cnp, dp);
+            Mat<P> a2 = neg(mul(an, am)), c2 = neg(mul(cn, cp));
+            if constexpr (W > 1) {                            // skipped step: the coefficient stays (it multiplies X_prev / X_next)
+#pragma unroll
+                for (int i = 0; i < P * P; ++i) { a2.a[i] = hu ? a2.a[i] : an.a[i]; c2.a[i] = hd ? c2.a[i] : cn.a[i]; }
+            } else {                                          // one warp = the whole system: nothing outside
+#pragma unroll
+                for (int i = 0; i < P * P; ++i) { a2.a[i] = hu ? a2.a[i] : 0.0; c2.a[i] = hd ? c2.a[i] : 0.0; }
             }
+            const Mat<P> inv = inverse_fast(b2);
+            an = mul(inv, a2); cn = mul(inv, c2); dn = mul(inv, d2);
         }
-        back(x, xp, xs);
+
+        Vec<P> xs = dn, xp;
+        Vec<P> Xp = vec_zero<P>();
+        if constexpr (W > 1) {
+            const int wi = t >> 5;
+            // warp wi:  F + fa*L(wi-1) + fc*F(wi+1) = fd   (its first row, lane 0)
+            //           L + la*L(wi-1) + lc*F(wi+1) = ld   (its last separator, lane 31)
+            double* eq = sm + (size_t)wi * 2 * NW;
+            if (lane == 0) {
+                pack(mine, sub_mul(v0, w0, an), neg(mul(w0, cn)), sub_mul(y0, w0, dn));
+#pragma unroll
+                for (int w = 0; w < NW; ++w) eq[w] = mine[w];
+            }
+            if (lane == 31) {
+                pack(mine, an, cn, dn);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) eq[NW + w] = mine[w];
+            }
+            __syncthreads();
+            hook();
+            // forward: L(w) = al[w] - be[w]*F(w+1),  F(w) = ga[w] - de[w]*F(w+1)
+            Vec<P> al[W], ga[W]; Mat<P> be[W], de[W];
+            {
+                Mat<P> la;
+                double rw[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) rw[w] = sm[NW + w];
+                unpack(rw, la, be[0], al[0]);                 // warp 0 has no predecessor: la = 0
+            }
+#pragma unroll
+            for (int w = 1; w < W; ++w) {
+                double rw[NW];
+                Mat<P> fa, fc; Vec<P> fd;
+#pragma unroll
+                for (int q = 0; q < NW; ++q) rw[q] = sm[(size_t)w * 2 * NW + q];
+                unpack(rw, fa, fc, fd);
+                const Mat<P> G = inverse_fast(sub_mul(mat_identity<P>(), fa, be[w - 1]));
+                ga[w] = mul(G, sub_mul(fd, fa, al[w - 1]));
+                de[w] = mul(G, fc);
+                if (w < W - 1) {
+                    Mat<P> la, lc; Vec<P> ld;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) rw[q] = sm[(size_t)w * 2 * NW + NW + q];
+                    unpack(rw, la, lc, ld);
+                    const Mat<P> lab = mul(la, be[w - 1]);
+                    al[w] = sub_mul(sub_mul(ld, la, al[w - 1]), neg(lab), ga[w]);
+                    be[w] = sub_mul(lc, neg(lab), de[w]);
+                }
+            }
+            // backward: every warp picks up X_prev = L(wi-1) and X_next = F(wi+1)
+            Vec<P> Fn = vec_zero<P>(), Xn = vec_zero<P>();
+#pragma unroll
+            for (int w = W - 1; w >= 1; --w) {
+                const Vec<P> Fw = sub_mul(ga[w], de[w], Fn);
+                const Vec<P> Lp = sub_mul(al[w - 1], be[w - 1], Fw);
+                if (wi == w) { Xp = Lp; Xn = Fn; }
+                Fn = Fw;
+            }
+            if (wi == 0) Xn = Fn;
+            xs = sub_mul(sub_mul(dn, an, Xp), cn, Xn);
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const double v = __shfl_up_sync(0xffffffffu, xs.a[i], 1);
+            xp.a[i] = (lane > 0) ? v : Xp.a[i];
+        }
+        if constexpr (R == 1) x[0] = xs;
+        else explicit_rows(x, xp, xs);
     }
 };
 
-// sum over the TT threads of a system, result valid in thread t == 0.  sm: >= TT/32 doubles that no
-// thread of the system reads any more (callers pass the exchange region of finish()).
+// sum over the TT threads of a system, result valid in thread t == 0.  sm: TT/32 doubles that no thread of the
+// system reads any more (the partial-sum slots behind the exchange region of finish())
 template <int TT>
 SB_D double system_sum(double v, double* sm, int t) {
 #pragma unroll
@@ -691,7 +756,7 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
             }
         }
     }
-    ss = system_sum<TT>(ss, sm, t);
+    ss = system_sum<TT>(ss, sm + ChunkThomas<P, R>::template exch_doubles<TT>(), t);
     if (t == 0) {
         const int pos = finalize_system(pd, k, ss, tol, slot, pd.iter_no);
         if (pos >= 0 && list_out) list_out[pos] = (int)k;
@@ -872,10 +937,10 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
     static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
     static constexpr int oGw = 0, oAB = oGw + nGw, oIvol = oAB + nAB, oFrac = oIvol + nIvol, mesh_doubles = oFrac + nFrac;
-    static constexpr int scratch = ChunkThomas<P, R>::template smem_doubles<TT>();
-    // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], instance index [2]
+    static constexpr int scratch = 2 * ChunkThomas<P, R>::template exch_doubles<TT>();   // exchange region of finish(), double-buffered
+    // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], mass flags kept [4P], instance index [2]
     static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
-                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 2 * 4 * P, group_doubles = oK + 2;
+                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 2;
     static constexpr int bar_doubles = 2 * G + 2;  // mbarriers (8 bytes): S per group (2 reserved) + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
@@ -904,8 +969,8 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
     double* pbuf = grp + LY::oPrm;    // [S][NPS]
     double* mbuf = grp + LY::oMass;   // [S][4P]
     double* scratch = grp + LY::oScr;
-    double* sums = grp + LY::oSum;    // [2][8]
-    double* keep = grp + LY::oKeep;   // [2][4P] mass flags of the instance in flight (the stage may be refilled early)
+    double* sums = grp + LY::oSum;    // [2][8] per-warp sums of h^2 of the instance in flight / the one before
+    double* keep = grp + LY::oKeep;   // [4P] TT == 32: mass flags of the instance in flight
     long long* kslot = reinterpret_cast<long long*>(grp + LY::oK);  // [2] instance index per stage / parity
     uint64_t* bar = bars + 2 * g;
 
@@ -999,10 +1064,52 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
     mbar_wait(mesh_bar, 0);
 
     int pend_pos = -1, pend_k = 0;  // deferred list write of the previous instance (thread t == 0)
+    // The outcome of an instance (converged or not) needs the sum of h^2 over all warps of its CTA.  Instead of a
+    // second CTA barrier per instance, the per-warp sums are parked in shared memory and the instance is closed
+    // ("settled") behind the one barrier of the NEXT instance's solve (or a final one after the loop).
+    int64_t prev_k = -1;
+    // close an instance: un = its new iterate (this thread's rows), ss = ||h||^2, mk = its mass flags
+    auto settle = [&](int64_t kk, double ss, const double (&un)[R][P], const double* mk) {
+        if (::sqrt(ss) < tol) {
+            // converged: this is u_{n+1}.  Write b = M .* u_{n+1} for the next time step right away (src/pdepe.jl:94),
+            // which then needs no separate pass over the state.
+            double* bg = pd.b + (size_t)kk * L * P;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = t * R + r;
+                if (i < pd.Nx) {
+                    const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) bg[(size_t)(r * TT + t) * P + p] = mk[cls * P + p] * un[r][p];
+                }
+            }
+        }
+        if (t == 0) {
+            if (from_b) pd.active[kk] = 1;
+            pend_pos = finalize_system(pd, kk, ss, tol, slot, it_no);
+            pend_k = (int)kk;
+        }
+    };
+    // TT > 32: call with every warp past its store into sums[it_prev & 1] (i.e. behind a CTA barrier)
+    auto settle_prev = [&](int it_prev) {
+        const double* sl = sums + (it_prev & 1) * 8;
+        double ss = sl[0];                    // every thread forms the same total in the same order
+#pragma unroll
+        for (int w = 1; w < TT / 32; ++w) ss += sl[w];
+        double un[R][P];
+        if (::sqrt(ss) < tol) {               // u is read back from L2, where this very thread wrote it a moment ago
+            const double* ug = pd.u + (size_t)prev_k * L * P;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < P; ++p) un[r][p] = __ldcg(ug + (size_t)(r * TT + t) * P + p);
+        }
+        settle(prev_k, ss, un, pd.mass + (size_t)prev_k * 4 * P);
+    };
     int it = 0;
     for (; j < n_in; j += stride, ++it) {
         const int stage = (S == 2) ? (it & 1) : 0;
-        // the producer refills: S == 2 -> the other stage, now (released by the previous iteration's reduction barrier);
+        // the producer refills: S == 2 -> the other stage, now (released by the previous iteration's barrier);
         //                       S == 1 -> the same buffers, as soon as the whole group has consumed them (hook below)
         auto prefetch = [&]() {
             if (t == 0) {
@@ -1020,8 +1127,9 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         const double* mass = mbuf + stage * 4 * P;
         mbar_wait(bar + stage, (S == 2) ? ((it >> 1) & 1) : (it & 1));
         const int64_t k = kslot[it & 1];
-        double* kp = keep + (it & 1) * 4 * P;
-        if (t < 3 * P) kp[t] = mass[t];
+        if constexpr (TT == 32) {   // mass flags of the instance in flight (S == 1: the stage is refilled before they are used)
+            if (t < 3 * P) keep[t] = mass[t];
+        }
 
         double uc[R][P], bc[R][P];
 #pragma unroll
@@ -1031,57 +1139,50 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         ChunkThomas<P, R> th;
         assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, us, bs, mass, t, tt, inv_tau, prm, uc, bc, th);
         Vec<P> h[R];
-        if constexpr (S == 2) {
-            th.template finish<TT>(h, scratch, t);
+        double* exch = scratch + (it & 1) * (LY::scratch / 2);
+        if constexpr (TT == 32) {
+            __syncwarp();  // every lane is done with the staged inputs
+            if constexpr (S == 2) th.template finish<TT>(h, exch, t);
+            else th.template finish<TT>(h, exch, t, prefetch);
         } else {
-            if constexpr (TT == 32) __syncwarp();  // every lane is done with the staged inputs
-            th.template finish<TT>(h, scratch, t, prefetch);
+            // behind the barrier inside finish(): every thread has consumed the staged inputs (S == 1: refill them) and
+            // every warp has parked its partial sum of the previous instance (settle it)
+            auto hook = [&]() {
+                if constexpr (S == 1) prefetch();
+                if (it > 0) settle_prev(it - 1);
+            };
+            th.template finish<TT>(h, exch, t, hook);
         }
 
-        // update, ||h||^2 of the system; the barrier of this reduction also releases the stage and the scratch
+        // update, ||h||^2 of the system
         double* ug = pd.u + (size_t)k * L * P;
         double ss = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) uc[r][p] -= h[r].a[p];
             if (t * R + r < pd.Nx) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    ug[(size_t)(r * TT + t) * P + p] = uc[r][p] - h[r].a[p];
+                    ug[(size_t)(r * TT + t) * P + p] = uc[r][p];
                     ss += h[r].a[p] * h[r].a[p];
                 }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
-        if constexpr (TT > 32) {  // every thread forms the same total (same order as thread 0) -> all know the outcome
-            double* sl = sums + (it & 1) * 8;
-            if ((t & 31) == 0) sl[t >> 5] = ss;
-            __syncthreads();
-            ss = sl[0];
-#pragma unroll
-            for (int w = 1; w < TT / 32; ++w) ss += sl[w];
+        if constexpr (TT > 32) {
+            if ((t & 31) == 0) sums[(it & 1) * 8 + (t >> 5)] = ss;
+            prev_k = k;
         } else {
             ss = __shfl_sync(0xffffffffu, ss, 0);
+            settle(k, ss, uc, keep);
+            __syncwarp();   // keep[] is rewritten by the next instance
         }
-        if (::sqrt(ss) < tol) {
-            // converged: this is u_{n+1}.  Write b = M .* u_{n+1} for the next time step right away (src/pdepe.jl:94),
-            // which then needs no separate pass over the state.
-            double* bg = pd.b + (size_t)k * L * P;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = t * R + r;
-                if (i < pd.Nx) {
-                    const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) bg[(size_t)(r * TT + t) * P + p] = kp[cls * P + p] * (uc[r][p] - h[r].a[p]);
-                }
-            }
-        }
-        if (t == 0) {
-            if (from_b) pd.active[k] = 1;
-            pend_pos = finalize_system(pd, k, ss, tol, slot, it_no);
-            pend_k = (int)k;
-        }
+    }
+    if constexpr (TT > 32) {
+        __syncthreads();
+        if (it > 0) settle_prev(it - 1);
     }
     if (t == 0) {
         if (pend_pos >= 0) list_out[pend_pos] = pend_k;

@@ -101,7 +101,7 @@ void fill_solve(SolveKernel (&tab)[kNumDecomp], std::integer_sequence<int, D...>
 inline size_t solve_smem_bytes(int P, int d) {
     const int TT = kDecomp[d].TT;
     if (TT == 32) return 0;
-    return (size_t)(2 * (2 * P * P + P) + P) * TT * sizeof(double);
+    return (size_t)(2 * (2 * P * P + P) * (TT / 32) + TT / 32) * sizeof(double);   // ChunkThomas::smem_doubles<TT>()
 }
 
 // defined in the per-functor translation units
