@@ -99,6 +99,9 @@ enum sb_design {
 
 /* ---- library / context ---------------------------------------------------------------------- */
 const char* sb_version(void);
+/* digest of the sources (csrc/, include/) and compiler flags the library was built from; the host mirror
+ * compares it with the tree it runs from, so a stale library fails loudly instead of running old kernels */
+const char* sb_build_digest(void);
 const char* sb_last_error(void);
 int sb_device_count(int* count);
 /* Guard mode (environment SB_GUARD=1 before the first call): every device array of a problem is allocated with
@@ -176,6 +179,11 @@ int sb_mass_download(sb_problem* pb, double* mass_host);
 /* assemble!(du,u,pb,t) (src/assembler.jl:19-125) on reference-layout HOST vectors of B instances;
  * copies in, runs the residual-only kernel, copies out.  u_host==NULL: use the resident state.   */
 int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host);
+/* The same operator on DEVICE memory -- the right-hand side f(du,u,p,t) = assemble!(du,u,pb,t) an ODE/DAE
+ * integrator calls when it keeps its vectors on the GPU (src/diffEq.jl:18-27).  d_u, d_du: device pointers,
+ * reference layout [B][Nx][npde]; d_u == NULL: the resident state.  Asynchronous on the context's stream: no
+ * allocation after the first call, no host synchronisation.                                           */
+int sb_assemble_device(sb_problem* pb, const double* d_u, double t, double* d_du);
 
 /* pdeval(m, xmesh, u_approx, x_eval, pb) (src/utils.jl:396-438; the same evaluation serves interpolate_sol_space,
  * :460-559): value and x-derivative of the solution at nq points shared by the batch, by the interpolation the

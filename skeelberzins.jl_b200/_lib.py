@@ -21,6 +21,7 @@ _vp = _c.c_void_p
 SIGNATURES = {
     "sb_version": (_c.c_char_p, []),
     "sb_last_error": (_c.c_char_p, []),
+    "sb_build_digest": (_c.c_char_p, []),
     "sb_device_count": (_c.c_int, [_c.POINTER(_c.c_int)]),
     "sb_kernel_launches": (_c.c_int, [_c.POINTER(_c.c_int64)]),
     "sb_debug_guard_violations": (_c.c_int, [_c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "sb_mass_flags": (_c.c_int, [_vp, _c.c_double, _c.c_int]),
     "sb_mass_download": (_c.c_int, [_vp, _vp]),
     "sb_assemble": (_c.c_int, [_vp, _vp, _c.c_double, _vp]),
+    "sb_assemble_device": (_c.c_int, [_vp, _vp, _c.c_double, _vp]),
     "sb_pdeval": (_c.c_int, [_vp, _vp, _c.c_int, _vp, _vp, _vp]),
     "sb_begin_step": (_c.c_int, [_vp, _c.c_double, _c.c_double]),
     "sb_residual_jacobian": (_c.c_int, [_vp]),
@@ -78,18 +80,26 @@ class SBError(RuntimeError):
         self.code = code
 
 
+def _build_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_sb_build", os.path.join(HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load():
-    """Load the shared library (build it first with skeelberzins.jl_b200/build.py or __graft_entry__.build())."""
+    """Load the shared library (build it first with skeelberzins.jl_b200/build.py or __graft_entry__.build()).
+
+    The library carries the digest of the sources it was built from; if csrc/ or include/ have changed since, this
+    raises instead of silently running old kernels (SB_ALLOW_STALE=1 overrides; tuning builds named by SB_LIB_PATH are
+    not checked)."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             # not a fallback: the only implementation is the CUDA library; build it in-tree if nvcc is here
             try:
-                import importlib.util
-                spec = importlib.util.spec_from_file_location("_sb_build", os.path.join(HERE, "build.py"))
-                mod = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(mod)
-                mod.build()
+                _build_module().build()
             except Exception as exc:
                 raise ImportError("%s is not built and building it failed (%s): run `python "
                                   "skeelberzins.jl_b200/build.py` (there is no CPU fallback)" % (LIB_PATH, exc))
@@ -98,6 +108,13 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if "SB_LIB_PATH" not in os.environ and not os.environ.get("SB_ALLOW_STALE"):
+            have = lib.sb_build_digest().decode()
+            want = _build_module().sources_digest()
+            if have != want:
+                raise ImportError("%s is stale: built from sources with digest %s..., the tree has %s... -- run `python "
+                                  "skeelberzins.jl_b200/build.py` (SB_ALLOW_STALE=1 to load it anyway)"
+                                  % (LIB_PATH, have[:12], want[:12]))
         _lib = lib
     return _lib
 

@@ -158,6 +158,26 @@ def pinned_empty(shape):
     return _pinned.empty(shape)
 
 
+def _is_device_array(a):
+    return hasattr(a, "__cuda_array_interface__")
+
+
+def _device_ptr(a, n):
+    """device pointer of a float64 device array with n elements (or of a raw integer address)"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    cai = a.__cuda_array_interface__
+    if cai["typestr"] not in ("<f8", "=f8", "|f8"):
+        raise TypeError("device arrays must be float64")
+    if int(np.prod(cai["shape"])) != n:
+        raise ValueError("expected a device array of %d values, got shape %r" % (n, tuple(cai["shape"])))
+    if cai.get("strides") is not None:
+        raise ValueError("device arrays must be contiguous")
+    return ctypes.c_void_p(cai["data"][0])
+
+
 class Context:
     """One per GPU (sb_ctx).  stream: a cudaStream_t handle (int) to run on, or None for an own stream."""
 
@@ -294,6 +314,13 @@ class DeviceProblem:
         uu = None if u is None else self._nodes(u)
         _lib.check(self.lib.sb_assemble(self._h, _lib.ptr(uu), float(t), _lib.ptr(du)))
         return du
+
+    def assemble_device(self, d_u, t, d_du):
+        """assemble! on DEVICE memory (sb_assemble_device): d_u / d_du are device pointers (int) or objects with
+        ``__cuda_array_interface__`` (torch.cuda tensors, cupy arrays) holding float64 [B, Nx, npde] in reference
+        layout; d_u None: the resident state.  Asynchronous on the context's stream."""
+        _lib.check(self.lib.sb_assemble_device(self._h, _device_ptr(d_u, self.B * self.Nx * self.npde), float(t),
+                                               _device_ptr(d_du, self.B * self.Nx * self.npde)))
 
     def begin_step(self, t_next, inv_tau):
         _lib.check(self.lib.sb_begin_step(self._h, float(t_next), float(inv_tau)))
@@ -569,7 +596,9 @@ def interpolate_sol_space(u_approx, x_eval, times, pb, val=True, deriv=True):
 class ODEFunction:
     """DifferentialEquations.jl-facing operator (src/diffEq.jl:18-27): f(du, u, p, t) = assemble!(du, u, pb, t) on the
     GPU, the diagonal mass matrix when the problem is a DAE, and the block-tridiagonal Jacobian prototype.
-    Vectors are flat [B, Nx*npde] (component fastest), like pb.inival."""
+    Vectors are flat [B, Nx*npde] (component fastest), like pb.inival: numpy arrays (copied in and out) or device
+    arrays (anything with ``__cuda_array_interface__``, e.g. torch.cuda tensors: sb_assemble_device, asynchronous on the
+    context's stream, which should then be the integrator's stream -- Context(stream=...))."""
 
     def __init__(self, pb):
         self.pb = pb
@@ -578,6 +607,9 @@ class ODEFunction:
         self.jac_prototype = jac_prototype(pb.Nx, pb.npde)
 
     def __call__(self, du, u, p, t):
+        if _is_device_array(du):                     # integrator state on the GPU: no host round trip, asynchronous
+            self.pb.device.assemble_device(u, t, du)
+            return du
         return assemble_(du, u, self.pb, t)
 
 

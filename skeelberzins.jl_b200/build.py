@@ -41,6 +41,10 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def sources_digest():
+    return _sources_digest()
+
+
 def _sources_digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
@@ -77,7 +81,7 @@ def build(force=False, verbose=False, ptxas_verbose=False):
         jobs.append((obj, [nvcc] + flags + ["-DSB_FN=%s" % fn, "-DSB_ENTRY=%s" % entry, '-DSB_NAME="%s"' % name,
                                             "-c", os.path.join(CSRC, "sb_inst.cu"), "-o", obj]))
     api_obj = os.path.join(OBJ, "sb_api.o")
-    jobs.append((api_obj, [nvcc] + flags + ["-c", os.path.join(CSRC, "sb_api.cu"), "-o", api_obj]))
+    jobs.append((api_obj, [nvcc] + flags + ['-DSB_SOURCE_DIGEST="%s"' % digest, "-c", os.path.join(CSRC, "sb_api.cu"), "-o", api_obj]))
     logs = []
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1))) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -92,9 +93,23 @@ struct UserFunctor {
     std::string source, name;
     int npde, nparams;
 };
-std::vector<UserFunctor>& user_functors() {
-    static std::vector<UserFunctor> v;
+// Registered user functors.  Contexts are independent across host threads, the table is shared: every access goes
+// through these helpers (a deque never moves its elements, so the pointer a problem keeps stays valid).
+std::mutex g_uf_mu;
+std::deque<UserFunctor>& user_functors_unlocked() {
+    static std::deque<UserFunctor> v;
     return v;
+}
+const UserFunctor* user_functor(int functor_id) {
+    std::lock_guard<std::mutex> lk(g_uf_mu);
+    std::deque<UserFunctor>& v = user_functors_unlocked();
+    const int i = functor_id - SB_USER_FUNCTOR_BASE;
+    return (functor_id >= SB_USER_FUNCTOR_BASE && i < (int)v.size()) ? &v[i] : nullptr;
+}
+int add_user_functor(const UserFunctor& uf) {
+    std::lock_guard<std::mutex> lk(g_uf_mu);
+    user_functors_unlocked().push_back(uf);
+    return SB_USER_FUNCTOR_BASE + (int)user_functors_unlocked().size() - 1;
 }
 
 // reference layout [B][Nx][W] <-> device layout [B][tile][R][T][W]   (W doubles per node, tiles of Lt = R*T nodes,
@@ -165,8 +180,8 @@ __global__ void k_pdeval(const double* __restrict__ u, const double* __restrict_
 
 const FunctorEntry* registry() {
     static FunctorEntry table[SB_NUM_BUILTIN_FUNCTORS];
-    static bool init = false;
-    if (!init) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         table[SB_LIN_DIFF] = entry_lin_diff();
         table[SB_NONLIN_DIFF] = entry_nonlin_diff();
         table[SB_LIN_DIFF_CYL] = entry_lin_diff_cyl();
@@ -177,19 +192,17 @@ const FunctorEntry* registry() {
         table[SB_CONV_DIFF] = entry_conv_diff();
         table[SB_LIN_REACT] = entry_lin_react();
         table[SB_GENERIC_SCALAR] = entry_generic_scalar();
-        init = true;
-    }
+    });
     return table;
 }
 
 SolveKernel solve_kernel(int P, int dec) {
     static SolveKernel t1[kNumDecomp], t2[kNumDecomp];
-    static bool init = false;
-    if (!init) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         fill_solve<1>(t1, std::make_integer_sequence<int, kNumDecomp>{});
         fill_solve<2>(t2, std::make_integer_sequence<int, kNumDecomp>{});
-        init = true;
-    }
+    });
     return P == 1 ? t1[dec] : t2[dec];
 }
 
@@ -311,6 +324,11 @@ struct sb_problem {
     // begin_step fusion (fused_tma): b = M.*u_{n+1} is written by the converging iteration of the previous step
     bool b_ready = false;        // b already holds M.*u for the next step
     bool lazy_pending = false;   // the current step started without k_begin_step and no iteration has run yet
+    bool step_all_tma = false;   // every Newton iteration of the current step so far was a k_newton_fused_p launch: only that
+                                 // kernel writes b = M.*u_{n+1} when an instance converges and maintains the compacted list
+    double* d_uin = nullptr;     // scratch state in device layout for sb_assemble / sb_assemble_device / sb_pdeval (kept)
+    double* d_eval = nullptr;    // scratch of sb_pdeval: mesh | points | results (kept, grown on demand)
+    size_t eval_elems = 0;
     int step_design = -1;
     double* d_ckpt = nullptr;  // sb_state_checkpoint copy of u (device layout)
     // profiling (sb_profile_begin/end): timed events around every Newton-iteration launch
@@ -638,7 +656,11 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
 
 extern "C" {
 
-const char* sb_version(void) { return "skeelberzins_b200 0.1.0 (sm_100a)"; }
+const char* sb_version(void) { return "skeelberzins_b200 0.2.0 (sm_100a)"; }
+#ifndef SB_SOURCE_DIGEST
+#define SB_SOURCE_DIGEST "unknown"
+#endif
+const char* sb_build_digest(void) { return SB_SOURCE_DIGEST; }
 const char* sb_last_error(void) { return g_err.c_str(); }
 
 int sb_host_alloc(size_t bytes, void** out) {
@@ -712,9 +734,9 @@ int sb_ctx_synchronize(sb_ctx* ctx) {
 }
 
 int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_bytes) {
-    if (functor_id < SB_USER_FUNCTOR_BASE || functor_id >= SB_USER_FUNCTOR_BASE + (int)user_functors().size())
-        return fail(SB_ERR_INVALID, "functor id %d is not a registered user functor", functor_id);
-    const UserFunctor& uf = user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+    const UserFunctor* ufp = user_functor(functor_id);
+    if (!ufp) return fail(SB_ERR_INVALID, "functor id %d is not a registered user functor", functor_id);
+    const UserFunctor& uf = *ufp;
     int dec = pick_decomposition(Nx, uf.npde);
     bool longmesh = false;
     int R, TT;
@@ -730,8 +752,8 @@ int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_b
 }
 
 int sb_functor_info(int functor_id, int* npde, int* nparams, const char** name) {
-    if (functor_id >= SB_USER_FUNCTOR_BASE && functor_id < SB_USER_FUNCTOR_BASE + (int)user_functors().size()) {
-        const UserFunctor& u = user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+    if (const UserFunctor* up = user_functor(functor_id)) {
+        const UserFunctor& u = *up;
         if (npde) *npde = u.npde;
         if (nparams) *nparams = u.nparams;
         if (name) *name = u.name.c_str();
@@ -753,8 +775,7 @@ int sb_register_user_functor(sb_ctx* ctx, const char* cuda_source, const char* s
     if (nparams < 1) return fail(SB_ERR_INVALID, "a functor needs at least one per-instance parameter");
     UserFunctor uf;
     uf.source = cuda_source; uf.name = struct_name; uf.npde = npde; uf.nparams = nparams;
-    user_functors().push_back(uf);
-    *functor_id = SB_USER_FUNCTOR_BASE + (int)user_functors().size() - 1;
+    *functor_id = add_user_functor(uf);
     return SB_OK;   // kernels are compiled when a problem is created (they depend on the mesh decomposition)
 }
 
@@ -775,8 +796,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (functor_id >= 0 && functor_id < SB_NUM_BUILTIN_FUNCTORS) {
         fe = &registry()[functor_id];
         f_npde = fe->npde; f_nparams = fe->nparams; f_name = fe->name;
-    } else if (functor_id >= SB_USER_FUNCTOR_BASE && functor_id < SB_USER_FUNCTOR_BASE + (int)user_functors().size()) {
-        uf = &user_functors()[functor_id - SB_USER_FUNCTOR_BASE];
+    } else if ((uf = user_functor(functor_id)) != nullptr) {
         f_npde = uf->npde; f_nparams = uf->nparams; f_name = uf->name.c_str();
     } else {
         return fail(SB_ERR_INVALID, "unknown functor id %d", functor_id);
@@ -947,7 +967,7 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     guarded_free(pb->d_mesh); guarded_free(pb->d_prm); guarded_free(pb->d_u); guarded_free(pb->d_b); guarded_free(pb->d_F); guarded_free(pb->d_J);
     guarded_free(pb->d_mass); guarded_free(pb->d_norm); guarded_free(pb->d_hist); guarded_free(pb->d_tmp); guarded_free(pb->d_active);
-    guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid);
+    guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid); guarded_free(pb->d_uin); guarded_free(pb->d_eval);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
@@ -985,7 +1005,14 @@ int sb_problem_set_design(sb_problem* pb, int design) {
     if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED && design != SB_DESIGN_FUSED_TMA)
         return fail(SB_ERR_INVALID, "unknown design %d", design);
     pb->design_pending = design;  // takes effect at the next sb_begin_step (a step is never mixed)
-    if (pb->launched == 0) pb->design = design;
+    if (pb->launched == 0) {
+        if (design != SB_DESIGN_FUSED_TMA && pb->lazy_pending) {   // only the fused_tma kernel can start from b alone
+            CU(cudaSetDevice(pb->ctx->device));
+            int rc = materialize_begin(pb);
+            if (rc) return rc;
+        }
+        pb->design = design;
+    }
     return SB_OK;
 }
 
@@ -1046,29 +1073,56 @@ int sb_mass_download(sb_problem* pb, double* mass_host) {
     return SB_OK;
 }
 
-int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host) {
-    if (!pb || !du_host) return fail(SB_ERR_INVALID, "NULL argument");
-    CU(cudaSetDevice(pb->ctx->device));
-    if (!u_host) { int rc0 = materialize_begin(pb); if (rc0) return rc0; }
+// persistent scratch state (device layout) for entry points that take a state argument
+static int ensure_uin(sb_problem* pb) {
+    if (pb->d_uin) return SB_OK;
+    CU(guarded_malloc((void**)&pb->d_uin, node_elems(pb) * sizeof(double)));
+    return SB_OK;
+}
+
+// assemble! (src/assembler.jl:19-125) of the state in d_state (device layout) into d_F; asynchronous on the stream
+static int launch_assemble_val(sb_problem* pb, const double* d_state, double t) {
     ProbDev pd = pb->pd;
-    double* d_uin = nullptr;
-    if (u_host) {
-        CU(cudaMalloc((void**)&d_uin, node_elems(pb) * sizeof(double)));
-        int rc = upload_nodes(pb, u_host, d_uin, pb->P, 0);
-        if (rc) { cudaFree(d_uin); return rc; }
-        pd.u = d_uin;
-    }
+    pd.u = const_cast<double*>(d_state);
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     cudaError_t e;
     if (pb->longmesh) e = launch_any(pb->ks.long_assemble_val, dim3(pd.ntiles, (unsigned)pd.B), dim3(kLongT0), 0, pb->ctx->stream, pd, t, 0.0, 1);
     else e = launch_any(pb->ks.assemble_val, grid, block, 0, pb->ctx->stream, pd, t, 0.0, 1);
     if (e == cudaSuccess) e = cudaGetLastError();
-    int rc = SB_OK;
-    if (e != cudaSuccess) rc = fail(SB_ERR_CUDA, "k_assemble launch: %s", cudaGetErrorString(e));
-    if (rc == SB_OK) rc = download_nodes(pb, pb->d_F, du_host, pb->P);
-    if (d_uin) cudaFree(d_uin);
-    return rc;
+    if (e != cudaSuccess) return fail(SB_ERR_CUDA, "k_assemble launch: %s", cudaGetErrorString(e));
+    return SB_OK;
+}
+
+int sb_assemble(sb_problem* pb, const double* u_host, double t, double* du_host) {
+    if (!pb || !du_host) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc;
+    const double* d_state = pb->d_u;
+    if (u_host) {
+        if ((rc = ensure_uin(pb))) return rc;
+        if ((rc = upload_nodes(pb, u_host, pb->d_uin, pb->P, 0))) return rc;
+        d_state = pb->d_uin;
+    } else if ((rc = materialize_begin(pb))) return rc;
+    if ((rc = launch_assemble_val(pb, d_state, t))) return rc;
+    return download_nodes(pb, pb->d_F, du_host, pb->P);
+}
+
+// The same operator on DEVICE memory, for an ODE/DAE integrator that keeps its vectors on the GPU (src/diffEq.jl:18-27:
+// f(du, u, p, t) = assemble!(du, u, pb, t)).  d_u, d_du: device pointers, reference layout [B][Nx][npde]; d_u NULL: the
+// resident state.  Enqueued on the context's stream; no allocation after the first call, no synchronisation.
+int sb_assemble_device(sb_problem* pb, const double* d_u, double t, double* d_du) {
+    if (!pb || !d_du) return fail(SB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(pb->ctx->device));
+    int rc;
+    const double* d_state = pb->d_u;
+    if (d_u) {
+        if ((rc = ensure_uin(pb))) return rc;
+        if ((rc = to_device(pb, d_u, pb->d_uin, pb->P, 0))) return rc;
+        d_state = pb->d_uin;
+    } else if ((rc = materialize_begin(pb))) return rc;
+    if ((rc = launch_assemble_val(pb, d_state, t))) return rc;
+    return from_device(pb, pb->d_F, d_du, pb->P);
 }
 
 static int run_begin_step_kernel(sb_problem* pb) {
@@ -1129,33 +1183,31 @@ int sb_pdeval(sb_problem* pb, const double* u_host, int nq, const double* xq_hos
         if (idx == 1 || idx > Nx) return fail(SB_ERR_INVALID, "Evaluation point oustide of the spatial discretization.");
     }
     int rc = SB_OK;
-    double* d_uin = nullptr;
     const double* d_u = pb->d_u;
     if (u_host) {
-        CU(cudaMalloc((void**)&d_uin, node_elems(pb) * sizeof(double)));
-        rc = upload_nodes(pb, u_host, d_uin, P, 0);
-        if (rc) { cudaFree(d_uin); return rc; }
-        d_u = d_uin;
+        if ((rc = ensure_uin(pb))) return rc;
+        if ((rc = upload_nodes(pb, u_host, pb->d_uin, P, 0))) return rc;
+        d_u = pb->d_uin;
     } else if ((rc = materialize_begin(pb))) return rc;
-    double *d_x = nullptr, *d_q = nullptr, *d_o = nullptr;
     const size_t no = (size_t)pb->pd.B * nq * P;
-    cudaError_t e = cudaMalloc((void**)&d_x, (size_t)(Nx + nq) * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, 2 * no * sizeof(double));
-    cudaStream_t st = pb->ctx->stream;
-    if (e == cudaSuccess) { d_q = d_x + Nx; e = cudaMemcpyAsync(d_x, x.data(), Nx * sizeof(double), cudaMemcpyHostToDevice, st); }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, xq_host, nq * sizeof(double), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        const size_t n = (size_t)pb->pd.B * nq;
-        k_pdeval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_u, d_x, Nx, pb->pd.R, pb->pd.T, pb->pd.L, P, pb->pd.m, pb->pd.singular,
-                                                             pb->pd.B, nq, d_q, d_o, d_o + no);
-        ++g_launches;
-        e = cudaGetLastError();
+    const size_t need = (size_t)Nx + nq + 2 * no;              // mesh | points | u | dudx
+    if (pb->eval_elems < need) {
+        if (pb->d_eval) { CU(cudaStreamSynchronize(pb->ctx->stream)); guarded_free(pb->d_eval); pb->d_eval = nullptr; pb->eval_elems = 0; }
+        CU(guarded_malloc((void**)&pb->d_eval, need * sizeof(double)));
+        pb->eval_elems = need;
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(u_out, d_o, no * sizeof(double), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dudx_out, d_o + no, no * sizeof(double), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_x); cudaFree(d_o); cudaFree(d_uin);
-    if (e != cudaSuccess) return fail(SB_ERR_CUDA, "sb_pdeval: %s", cudaGetErrorString(e));
+    double *d_x = pb->d_eval, *d_q = d_x + Nx, *d_o = d_q + nq;
+    cudaStream_t st = pb->ctx->stream;
+    CU(cudaMemcpyAsync(d_x, x.data(), Nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_q, xq_host, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    const size_t n = (size_t)pb->pd.B * nq;
+    k_pdeval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_u, d_x, Nx, pb->pd.R, pb->pd.T, pb->pd.L, P, pb->pd.m, pb->pd.singular,
+                                                         pb->pd.B, nq, d_q, d_o, d_o + no);
+    ++g_launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(u_out, d_o, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(dudx_out, d_o + no, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SB_OK;
 }
 
@@ -1165,7 +1217,6 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; pb->prof_harvested = 0; }
     pb->t_next = t_next; pb->inv_tau = inv_tau;
     pb->design = pb->design_pending;
-    cudaStream_t st = pb->ctx->stream;
     const bool lazy = pb->b_ready && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh && !getenv("SB_NO_LAZY_BEGIN");
     pb->b_ready = false;
     pb->lazy_pending = false;
@@ -1179,6 +1230,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     }
     pb->slot_base = pb->slot_of(pb->launched);
     pb->launched = 0; pb->confirmed = 0; pb->last_active = pb->pd.B;
+    pb->step_all_tma = true;
     return SB_OK;
 }
 
@@ -1200,7 +1252,7 @@ static int wait_slot(sb_problem* pb, int s, unsigned int* value) {
         }
     }
     *value = v;
-    if (v == 0 && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh) pb->b_ready = true;  // every instance wrote its next b
+    if (v == 0 && pb->step_all_tma && !pb->longmesh) pb->b_ready = true;  // every instance wrote its next b when it converged
     return SB_OK;
 }
 
@@ -1258,8 +1310,10 @@ int sb_solve_update_norm(sb_problem* pb, double tol) {
         return fail(SB_ERR_UNSUPPORTED, "the long-mesh path solves from on-the-fly assembly only: use sb_newton_iteration");
     CU(cudaSetDevice(pb->ctx->device));
     int slot;
-    int rc = prepare_slot(pb, &slot);
+    int rc = materialize_begin(pb);
     if (rc) return rc;
+    pb->step_all_tma = false;   // k_solve neither writes the next step's b nor the compacted list
+    if ((rc = prepare_slot(pb, &slot))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     solve_kernel(pb->P, pb->dec)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
@@ -1276,6 +1330,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         int slot;
         int rc = prepare_slot(pb, &slot);
         if (rc) return rc;
+        pb->step_all_tma = false;
         if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
         rc = longmesh_iteration(pb, tol, slot);
         if (rc) return rc;
@@ -1288,9 +1343,13 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         return sb_solve_update_norm(pb, tol);
     }
     CU(cudaSetDevice(pb->ctx->device));
+    if (pb->design == SB_DESIGN_FUSED_TMA && pb->launched > 0 && !pb->step_all_tma)
+        return fail(SB_ERR_INVALID, "a fused_tma iteration cannot follow a split / fused / two-call iteration inside the same "
+                    "step: only fused_tma launches maintain the compacted list of active instances it reads");
     int slot;
-    int rc = prepare_slot(pb, &slot);
-    if (rc) return rc;
+    int rc = SB_OK;
+    if (pb->design != SB_DESIGN_FUSED_TMA && (rc = materialize_begin(pb))) return rc;   // k_newton_fused reads u and active[]
+    if ((rc = prepare_slot(pb, &slot))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
     if (pb->design == SB_DESIGN_FUSED_TMA) {
@@ -1314,6 +1373,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
         return finish_slot(pb, slot);
     }
+    pb->step_all_tma = false;
     if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
     CU(launch_any(pb->ks.fused, grid, block, smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot));
     CU(cudaGetLastError());
@@ -1335,7 +1395,7 @@ int sb_poll_active(sb_problem* pb, int blocking, int64_t* n_active) {
         while (pb->confirmed < pb->launched) {
             const unsigned int v = *((volatile unsigned int*)pb->h_count + pb->slot_of(pb->confirmed));
             if (v == kPending) break;
-            if (v == 0 && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh) pb->b_ready = true;
+            if (v == 0 && pb->step_all_tma && !pb->longmesh) pb->b_ready = true;
             pb->last_active = v;
             pb->confirmed++;
         }

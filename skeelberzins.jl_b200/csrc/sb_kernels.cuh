@@ -111,11 +111,17 @@ SB_D void group_done(const ProbDev& pd, int slot, unsigned int total_groups, int
 SB_D double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifdef SB_RCP_SHORT   // tuning: r0*(1+e)*(1+e^2), a dependency chain of 3 instead of 4 (last bit not self-corrected)
+    const double e = fma(-x, r, 1.0);
+    const double p = fma(r, e, r), e2 = e * e;
+    return fma(p, e2, p);
+#else
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     return r;
+#endif
 }
 
 template <int P> SB_D Mat<P> inverse_fast(const Mat<P>& A) {
@@ -185,7 +191,11 @@ struct ChunkThomas {
     }
 
     // shared memory of finish<TT>() in doubles: the exchange region (two equations per warp) ...
+#ifdef SB_FINISH_SERIAL   // tuning builds: the round-1 second level (warp 0 solves the separators alone), for A/B runs
+    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
+#else
     template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : 2 * NW * (TT / 32); }
+#endif
     // ... followed by one partial sum per warp for system_sum()
     template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : exch_doubles<TT>() + TT / 32; }
 
@@ -262,8 +272,68 @@ struct ChunkThomas {
     //     values its own warp needs.
     // hook(): called by every thread right after the barrier (TT == 32: after the first shuffle), when all threads
     // of the system have finished reading their inputs, e.g. to start the prefetch of the next instance.
+#ifdef SB_FINISH_SERIAL
     template <int TT, class Hook>
     SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+        if constexpr (TT == 32) finish_parallel<TT>(x, sm, t, hook);
+        else {
+            Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
+            if constexpr (R == 1) summary(y0, v0, w0, yL, vL, wL);
+            else { to_explicit(); y0 = dt[0]; v0 = vt[0]; w0 = ct[0]; yL = dt[R - 2]; vL = vt[R - 2]; wL = ct[R - 2]; }
+            double mine[NW], nb[NW];
+            pack(mine, v0, w0, y0);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
+            __syncthreads();
+            hook();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
+            Mat<P> v0n, w0n; Vec<P> y0n;
+            unpack(nb, v0n, w0n, y0n);
+            Mat<P> an, cn; Vec<P> dn;
+            reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
+            constexpr int Q = TT / 32;  // reduced rows per lane of warp 0
+            double* red = sm + NW * TT;
+            double* xsm = sm + 2 * NW * TT;
+            pack(mine, an, cn, dn);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) red[w * TT + t] = mine[w];
+            __syncthreads();
+            if (t < 32) {
+                ChunkThomas<P, Q> lvl2;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    double rw[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + t * Q + q];
+                    Mat<P> a, c; Vec<P> d;
+                    unpack(rw, a, c, d);
+                    lvl2.row(q, a, mat_identity<P>(), c, d);
+                }
+                Vec<P> y[Q];
+                lvl2.template finish_parallel<32>(y, nullptr, t, NoHook());
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                    for (int i = 0; i < P; ++i) xsm[i * TT + t * Q + q] = y[q].a[i];
+            }
+            __syncthreads();
+            Vec<P> xs, xp;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                xs.a[i] = xsm[i * TT + t];
+                xp.a[i] = (t > 0) ? xsm[i * TT + t - 1] : 0.0;
+            }
+            if constexpr (R == 1) x[0] = xs;
+            else explicit_rows(x, xp, xs);
+        }
+    }
+    template <int TT, class Hook>
+    SB_D void finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+#else
+    template <int TT, class Hook>
+    SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+#endif
         constexpr int W = TT / 32;
         const int lane = t & 31;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
@@ -1085,6 +1155,7 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
             }
         }
         if (t == 0) {
+            if (pend_pos >= 0) list_out[pend_pos] = pend_k;   // the entry of the instance settled before this one
             if (from_b) pd.active[kk] = 1;
             pend_pos = finalize_system(pd, kk, ss, tol, slot, it_no);
             pend_k = (int)kk;

@@ -79,13 +79,13 @@ SB_D void form_rows(const LevelDev& below, int64_t k, int tile, int t, double (&
     for (int r = 0; r <= R; ++r) {
         const bool in = j0 + r < n;
         const size_t p = (r < R) ? p0 + (size_t)r * TT : (in ? pl : p0);
-        q[r][0] = __ldg(S + p * 4 + 0); q[r][1] = __ldg(S + p * 4 + 1);
+        q[r][0] = __ldcg(S + p * 4 + 0); q[r][1] = __ldcg(S + p * 4 + 1);   // rewritten every iteration: L2, not the read-only path
         if (!in) { q[r][0] = make_double2(0.0, 0.0); q[r][1].x = 0.0; }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const size_t p = p0 + (size_t)r * TT;
-        const double2 bc = __ldg(S + p * 4 + 2), dd = __ldg(S + p * 4 + 3);
+        const double2 bc = __ldcg(S + p * 4 + 2), dd = __ldcg(S + p * 4 + 3);
         const double ar = q[r][1].y, bp = bc.x, Cs = bc.y, dp = dd.x;
         const double y0n = q[r + 1][0].x, v0n = q[r + 1][0].y, w0n = q[r + 1][1].x;
         const double binv = fast_rcp(fma(-Cs, v0n, bp));
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(TT) k6_top(LevelDev lv, LevelDev below, const 
 // separator unknowns of chunk c (own and previous) from the solution of the next level
 SB_D void separators(const LevelDev& up, int64_t k, int c, Vec<1>& xp, Vec<1>& xs) {
     const double* xu = up.x + (size_t)k * up.stride;
-    xs.a[0] = xu[tiled_pos(c, up.R, kLongTT)];
-    xp.a[0] = (c > 0) ? xu[tiled_pos(c - 1, up.R, kLongTT)] : 0.0;
+    xs.a[0] = __ldcg(xu + tiled_pos(c, up.R, kLongTT));
+    xp.a[0] = (c > 0) ? __ldcg(xu + tiled_pos(c - 1, up.R, kLongTT)) : 0.0;
 }
 
 // level l >= 1, backward
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
     const double2* rows = lv.acd + (base + t) * 2;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const double2 ac = __ldg(rows + (size_t)r * TT * 2), dd = __ldg(rows + (size_t)r * TT * 2 + 1);
+        const double2 ac = __ldcg(rows + (size_t)r * TT * 2), dd = __ldcg(rows + (size_t)r * TT * 2 + 1);   // written by k6_chunk_sys of this iteration
         Mat<1> A, Bm, C; Vec<1> d;
         A.a[0] = ac.x; Bm.a[0] = 1.0; C.a[0] = ac.y; d.a[0] = dd.x;
         th.row(r, A, Bm, C, d);

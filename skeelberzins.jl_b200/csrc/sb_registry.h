@@ -101,7 +101,8 @@ void fill_solve(SolveKernel (&tab)[kNumDecomp], std::integer_sequence<int, D...>
 inline size_t solve_smem_bytes(int P, int d) {
     const int TT = kDecomp[d].TT;
     if (TT == 32) return 0;
-    return (size_t)(2 * (2 * P * P + P) * (TT / 32) + TT / 32) * sizeof(double);   // ChunkThomas::smem_doubles<TT>()
+    return (P == 1 ? ChunkThomas<1, 1>::template smem_doubles<256>() * (size_t)TT / 256
+                   : ChunkThomas<2, 1>::template smem_doubles<256>() * (size_t)TT / 256) * sizeof(double);   // same for every R; linear in TT
 }
 
 // defined in the per-functor translation units

@@ -523,3 +523,75 @@ def test_repeated_solves_are_bitwise_identical(ctx, cfg, B, Nx, nsteps):
             ref = u
         else:
             assert np.array_equal(u, ref), "repetition %d differs" % rep
+
+
+def test_two_call_and_fused_tma_steps_alternate(ctx, oracle):
+    """The "b = M.*u_{n+1} is already there" shortcut of the fused_tma design must follow the kernel that actually ran,
+    not the configured design: steps driven through the two-call API (sb_residual_jacobian + sb_solve_update_norm)
+    alternate with fused_tma steps under the default design, and the result must be the oracle's."""
+    c = ex.baseline_case("2", B=24, Nx=200)
+    tg, tau = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:9]
+    tol, maxit = 1e-10, 100
+    dev = sb.DeviceProblem(ctx, c.m, c.xmesh, sb.Functor(c.functor, c.params))       # design: fused_tma
+    try:
+        dev.upload(c.initial())
+        dev.mass_flags(tg[0])
+        for i in range(tg.size - 1):
+            dev.begin_step(tg[i + 1], 1.0 / tau)
+            if i % 3 == 1:                                     # two-call API under the fused_tma design
+                for _ in range(maxit):
+                    dev.residual_jacobian()
+                    dev.solve_update_norm(tol)
+                    if dev.poll_active(True) == 0:
+                        break
+            elif i % 3 == 2:                                   # design switched right after a (possibly lazy) begin_step
+                dev.set_design("fused")
+                dev.newton_solve(tol, maxit)
+                dev.set_design("fused_tma")
+            else:
+                dev.newton_solve(tol, maxit)
+        u = dev.download().copy()
+        r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, tau)
+        assert _relerr(u, r["u"].reshape(u.shape)) < RTOL
+        assert (dev.total_iters() == r["iters"].sum(axis=1)).all()
+        # a fused_tma iteration after a two-call iteration inside one step would read a list nobody wrote: refused
+        dev.begin_step(tg[-1] + tau, 1.0 / tau)
+        dev.residual_jacobian()
+        dev.solve_update_norm(tol)
+        with pytest.raises(sb.SBError, match="cannot follow"):
+            dev.newton_iteration(tol)
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("cfg,Nx", [("2", 300), ("3a", 128), ("4", 96)])
+def test_assemble_on_device_memory(ctx, oracle, cfg, Nx):
+    """sb_assemble_device: the DiffEq-facing right-hand side (src/diffEq.jl:18-27) on device-resident vectors
+    (torch.cuda tensors through __cuda_array_interface__), no host round trip."""
+    import torch
+    c = ex.baseline_case(cfg, B=17, Nx=Nx)
+    rng = np.random.default_rng(5)
+    u = 0.5 + rng.random((c.B, Nx, c.npde))
+    tctx = sb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    dev = sb.DeviceProblem(tctx, c.m, c.xmesh, sb.Functor(c.functor, c.params))
+    try:
+        d_u = torch.from_numpy(u).cuda()
+        d_du = torch.empty_like(d_u)
+        for t in (0.2, 0.7):                                  # repeated calls reuse the scratch
+            dev.assemble_device(d_u, t, d_du)
+            torch.cuda.synchronize()
+            ref = oracle.assemble(c.functor, c.m, c.xmesh, c.params, u, t)
+            assert _relerr(d_du.cpu().numpy(), ref) < 1e-12
+            assert _relerr(dev.assemble(u, t), ref) < 1e-12    # host-pointer entry point, same kernel
+        fn = sb.Functor(c.functor, c.params)
+        pb = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, c.tspan, ctx=tctx, solver="DiffEq")
+        f = sb.ODEFunction(pb)
+        flat = d_u.reshape(c.B, -1)
+        out = torch.empty_like(flat)
+        f(out, flat, None, 0.2)
+        torch.cuda.synchronize()
+        assert _relerr(out.cpu().numpy().reshape(u.shape), oracle.assemble(c.functor, c.m, c.xmesh, c.params, u, 0.2)) < 1e-12
+        pb.device.close()
+    finally:
+        dev.close()
