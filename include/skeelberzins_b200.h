@@ -92,9 +92,12 @@ enum sb_design {
     SB_DESIGN_SPLIT = 0, /* assemble kernel writes F and the block-tridiagonal J to HBM; solve kernel
                             reads them (the two calls sb_residual_jacobian + sb_solve_update_norm)  */
     SB_DESIGN_FUSED = 1, /* one kernel per iteration; J and F never leave the SM                    */
-    SB_DESIGN_FUSED_TMA = 2 /* fused, persistent CTAs: u and b of the next instance are prefetched by the
+    SB_DESIGN_FUSED_TMA = 2, /* fused, persistent CTAs: u and b of the next instance are prefetched by the
                             bulk-copy engine (cp.async.bulk + mbarrier) while the current one is solved;
                             only instances still active are visited (compacted list)                */
+    SB_DESIGN_RESIDENT = 3 /* default.  Per-iteration entry points (sb_newton_iteration ...) as fused_tma; the loops
+                            driven from C (sb_newton_solve, sb_solve_steps, sb_solve_steps_opt) run as ONE launch in
+                            which every instance stays on its SM through all Newton iterations (and time steps)  */
 };
 
 /* ---- library / context ---------------------------------------------------------------------- */
@@ -222,18 +225,33 @@ int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done);
 
 /* convenience: nsteps implicit-Euler steps (the time loop of src/pdepe.jl:90-108 driven from C; no state is
  * stored in between).  tgrid[nsteps+1] is the time grid; tau > 0: constant time step, else tau_i = diff(tgrid).
- * With the fused_tma design the host still launches every Newton iteration and reads every launch's count, but a
- * launch that finds every instance converged starts the next time step itself (time grid and step counter on the
- * device), so the launches enqueued ahead of the host's knowledge are never no-ops.  Same states and iteration
- * counts as the step-by-step loop (SB_NO_DEVICE_STEPPING=1 selects that loop).  steps_done (may be NULL) = completed
- * time steps; SB_ERR_CONVERGENCE as in sb_newton_solve.                                                              */
+ * With the resident design (default) on a mesh in the batched range this is ONE kernel launch (csrc/sb_resident.cuh): the
+ * instances are independent, so every thread group keeps its instance on the SM through all Newton iterations of all
+ * time steps -- same arithmetic per iteration, hence the same states and per-instance iteration counts as the
+ * host-owned loops, without a launch per iteration or lock-step waiting.  The fused_tma design keeps the previous
+ * scheme (one launch per Newton iteration, time stepping on the device; SB_NO_DEVICE_STEPPING=1: the plain
+ * step-by-step loop).  sb_newton_solve uses the same kernel for the Newton loop of a single step.  steps_done (may be NULL) =
+ * completed time steps; SB_ERR_CONVERGENCE as in sb_newton_solve.                                                    */
 int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done);
+
+/* The same time loop with the per-instance extras of the whole-solve kernel (csrc/sb_resident.cuh: every instance stays
+ * on its SM from the first to the last Newton iteration of the solve; one launch):
+ *   tgrid_per_instance  host [B][nsteps+1] or NULL: every instance steps through its own time grid -- the reference's
+ *                       vector tstep (src/pdepe.jl:84-85,92), one vector per instance of the batch; tgrid/tau are then ignored
+ *   step_iters          host [B][nsteps] or NULL: Newton iterations of every instance in every step (src/utils.jl:323-333)
+ *   snapshots           host [nsteps+1][B][Nx][npde] or NULL (pinned memory recommended): every state including the
+ *                       initial one, what the reference stores (src/pdepe.jl:99-107); finished rounds of instances are
+ *                       copied out on a second stream while later rounds compute
+ * Needs the resident design (the default) and a mesh in the batched range; otherwise SB_ERR_UNSUPPORTED.           */
+int sb_solve_steps_opt(sb_problem* pb, int nsteps, const double* tgrid, const double* tgrid_per_instance, double tau,
+                       double tol, int maxit, int32_t* step_iters, double* snapshots, int* steps_done);
 
 /* diagnostics (host arrays of length B unless stated)                                            */
 int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iterations this step  */
 int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */
 int sb_get_last_norm(sb_problem* pb, double* norm_host);          /* ||h||_2 of last iteration    */
-int sb_get_status(sb_problem* pb, int32_t* status_host);          /* 0 ok,1 active,2 non-finite   */
+int sb_get_status(sb_problem* pb, int32_t* status_host);          /* 0 ok, 1 not converged, 2 non-finite / singular,
+                                                                     3 ok, solved with the pivoted fallback      */
 /* ||h||_2 history of the current step (Params.hist, src/utils.jl:305-307,325-327): enable with a
  * capacity (>= maxit), then after a step hist_host[k*cap + it] holds the norm of iteration it.     */
 int sb_enable_history(sb_problem* pb, int cap);

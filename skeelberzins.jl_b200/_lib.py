@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("SB_LIB_PATH", os.path.join(HERE, "libskeelberzins_b20
 
 SB_OK = 0
 SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_UNSUPPORTED, SB_ERR_CONVERGENCE, SB_ERR_PLUGIN = -1, -2, -3, -4, -5
-DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA = 0, 1, 2
+DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA, DESIGN_RESIDENT = 0, 1, 2, 3
 
 _c = ctypes
 _dp = _c.POINTER(_c.c_double)
@@ -60,6 +60,7 @@ SIGNATURES = {
     "sb_wait_iteration": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_c.c_int64)]),
     "sb_newton_solve": (_c.c_int, [_vp, _c.c_double, _c.c_int, _c.POINTER(_c.c_int)]),
     "sb_solve_steps": (_c.c_int, [_vp, _c.c_int, _vp, _c.c_double, _c.c_double, _c.c_int, _c.POINTER(_c.c_int)]),
+    "sb_solve_steps_opt": (_c.c_int, [_vp, _c.c_int, _vp, _vp, _c.c_double, _c.c_double, _c.c_int, _vp, _vp, _c.POINTER(_c.c_int)]),
     "sb_get_step_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_total_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_last_norm": (_c.c_int, [_vp, _vp]),

@@ -214,7 +214,7 @@ def default_context(device=0):
 class DeviceProblem:
     """Thin object wrapper of sb_problem: the per-iteration entry points of the C ABI."""
 
-    def __init__(self, ctx, m, xmesh, functor, design="fused_tma"):
+    def __init__(self, ctx, m, xmesh, functor, design="resident"):
         self.lib = _lib.load()
         self.ctx = ctx
         x = np.ascontiguousarray(xmesh, dtype=np.float64)
@@ -247,7 +247,8 @@ class DeviceProblem:
         _lib.check(self.lib.sb_problem_set_params(self._h, _lib.ptr(p)))
 
     def set_design(self, design):
-        names = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED, "fused_tma": _lib.DESIGN_FUSED_TMA}
+        names = {"split": _lib.DESIGN_SPLIT, "fused": _lib.DESIGN_FUSED, "fused_tma": _lib.DESIGN_FUSED_TMA,
+                 "resident": _lib.DESIGN_RESIDENT}
         d = names[design] if isinstance(design, str) else int(design)
         _lib.check(self.lib.sb_problem_set_design(self._h, d))
         self.design = {v: k for k, v in names.items()}[d]
@@ -256,6 +257,11 @@ class DeviceProblem:
         R, T, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _lib.check(self.lib.sb_problem_layout(self._h, ctypes.byref(R), ctypes.byref(T), ctypes.byref(w)))
         return dict(R=R.value, T=T.value, warp=bool(w.value))
+
+    def longmesh(self):
+        """True when the mesh is solved by the long-mesh path (tiles; more nodes than one thread group holds)."""
+        lay = self.layout()
+        return lay["R"] * lay["T"] < self.Nx
 
     def info(self):
         npde, Nx, B, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_int()
@@ -363,6 +369,31 @@ class DeviceProblem:
             raise ConvergenceFailed("convergence failed")
         _lib.check(rc)
         return done.value
+
+    def solve_steps_opt(self, tgrid, tau, tol, maxit, step_iters=False, snapshots=None, tgrid_per_instance=None):
+        """sb_solve_steps_opt: the whole-solve kernel with its per-instance extras.  tgrid_per_instance [B, nsteps+1]:
+        one time grid per instance; step_iters=True: returns the [B, nsteps] Newton iteration counts; snapshots: a
+        float64 array [nsteps+1, B, Nx, npde] (pinned: ``pinned_empty``) that receives every state."""
+        tgi = None
+        if tgrid_per_instance is not None:
+            tgi = np.ascontiguousarray(tgrid_per_instance, dtype=np.float64)
+            if tgi.ndim != 2 or tgi.shape[0] != self.B:
+                raise ValueError("tgrid_per_instance must be [B, nsteps+1]")
+            nsteps, tg = tgi.shape[1] - 1, None
+        else:
+            tg = np.ascontiguousarray(tgrid, dtype=np.float64)
+            nsteps = tg.size - 1
+        its = np.empty((self.B, nsteps), dtype=np.int32) if step_iters else None
+        if snapshots is not None and (snapshots.dtype != np.float64 or snapshots.size != (nsteps + 1) * self.B * self.Nx * self.npde
+                                      or not snapshots.flags.c_contiguous):
+            raise ValueError("snapshots must be a contiguous float64 array [nsteps+1, B, Nx, npde]")
+        done = ctypes.c_int()
+        rc = self.lib.sb_solve_steps_opt(self._h, nsteps, _lib.ptr(tg), _lib.ptr(tgi), float(tau) if tau is not None else -1.0,
+                                         float(tol), int(maxit), _lib.ptr(its), _lib.ptr(snapshots), ctypes.byref(done))
+        if rc == _lib.SB_ERR_CONVERGENCE:
+            raise ConvergenceFailed("convergence failed")
+        _lib.check(rc)
+        return its
 
     def _get(self, fn, dtype):
         out = np.empty(self.B, dtype=dtype)
@@ -641,7 +672,7 @@ def _merge_params(params, kwargs, stationary):
     return p
 
 
-def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design="fused_tma"):
+def problem_init(m, xmesh, tspan, pdefun, icfun, bdfun, params, ctx=None, design="resident"):
     """problem_init (src/utils.jl:609-663) for the whole batch."""
     if not isinstance(pdefun, Functor):
         raise TypeError("pdefun must be a registry Functor (device-compiled); arbitrary host closures cannot run "
@@ -783,13 +814,59 @@ def _pdepe_streams(m, pdefun, icfun, bdfun, x, tspan, params, ctx, design, squee
     return DiffEqArray([u], timeSteps[-1:])
 
 
-def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="fused_tma", save="all",
-          squeeze=None, c_loop=False, return_device=False, alias_compat=False, streams=1, **kwargs):
+def _pdepe_devices(devices, m, pdefun, icfun, bdfun, x, tspan, kw):
+    """pdepe for a batch sharded over the GPUs `devices` of this process: contiguous blocks of instances
+    (sharding.shard_range), one host thread and one context per GPU, no exchange between the shards (the instances are
+    independent); the results are put together in instance order."""
+    import threading
+    from .sharding import shard_range
+    B, Nx, npde = pdefun.batch, x.size, pdefun.npde
+    u0 = None if callable(icfun) else np.asarray(icfun, dtype=np.float64)
+    per_inst_ic = u0 is not None and u0.size == B * Nx * npde and B > 1
+    tstep = kw.get("tstep", None)
+    parts, errors = [None] * len(devices), []
+
+    def work(r, d):
+        lo, hi = shard_range(B, len(devices), r)
+        if hi <= lo:
+            return
+        try:
+            fn = Functor(pdefun.id, pdefun.params[lo:hi])
+            ic = u0.reshape(B, Nx, npde)[lo:hi] if per_inst_ic else icfun
+            kw_r = dict(kw)
+            if tstep is not None and np.ndim(tstep) == 2:
+                kw_r["tstep"] = np.asarray(tstep)[lo:hi]
+            parts[r] = pdepe(m, fn, ic, fn, x, tspan, ctx=default_context(int(d)), squeeze=False, **kw_r)
+        except Exception as e:          # re-raised on the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(r, d)) for r, d in enumerate(devices)]
+    for t_ in threads:
+        t_.start()
+    for t_ in threads:
+        t_.join()
+    if errors:
+        raise errors[0]
+    parts = [p for p in parts if p is not None]
+    if tspan is None:
+        return np.concatenate(parts, axis=0)
+    us = [np.concatenate([p.u[i] for p in parts], axis=0) for i in range(len(parts[0].u))]
+    ts = parts[0].t if np.ndim(parts[0].t) == 1 else np.concatenate([p.t for p in parts], axis=0)
+    return DiffEqArray(us, ts)
+
+
+def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, design="resident", save="all",
+          squeeze=None, c_loop=False, return_device=False, alias_compat=False, streams=1, devices=None, **kwargs):
     """Batched pdepe.  With `tspan`: transient solve by implicit Euler (src/pdepe.jl:42-128); without:
     stationary solve by one Newton solve with tau = Inf, t = 1 (src/pdepe.jl:156-192).
 
-    Extra keyword arguments of this implementation: ctx (Context / GPU), design ("fused" | "split"),
-    save ("all": every time step as the reference does | "last": only u(t_end), for very large batches),
+    Extra keyword arguments of this implementation: ctx (Context / GPU), design ("resident" | "fused_tma" | "fused" |
+    "split"), save ("all": every time step as the reference does | "last": only u(t_end), for very large batches),
+    c_loop (drive the time loop and the Newton loop from C: with the resident design the whole solve is one kernel
+    launch; default False = the loops are owned by this host code, one C call per Newton iteration, as in the reference),
+    tstep may also be a 2-D array [B, nsteps+1]: one time grid per instance (implies the whole-solve kernel),
+    devices (list of GPU ordinals: the batch is sharded over them by instance index, one host thread per GPU, no
+    exchange between shards; returns the solution only),
     squeeze (drop the batch axis; default: when the functor has a single instance),
     streams (with save="last" and c_loop: split the batch into that many contiguous sub-batches, each with its own
     CUDA stream, time loop and Newton loop on its own host thread -- the sub-batches' launches interleave on the
@@ -800,6 +877,16 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     (every sol.u[k] but the last -- and, for npde > 1, the first -- multiplied by the mass flags, src/pdepe.jl:87-107).
     """
     stationary = tspan is None
+    if devices is not None and len(devices) > 1:
+        if return_device or kwargs.get("data") or kwargs.get("hist") or (params is not None and (params.data or params.hist)):
+            raise ValueError("devices=[...] returns the solution only (no data / hist / return_device)")
+        kw = dict(kwargs, design=design, save=save, c_loop=c_loop, alias_compat=alias_compat, streams=streams)
+        if params is not None:
+            kw["params"] = params
+        sol = _pdepe_devices(list(devices), m, pdefun, icfun, bdfun, np.asarray(xmesh, dtype=np.float64), tspan, kw)
+        return sol
+    if devices is not None and len(devices) == 1 and ctx is None:
+        ctx = default_context(int(devices[0]))
     params = _merge_params(params or Params(tstep=np.inf if stationary else 1e-2), kwargs, stationary)
     if kwargs:
         raise TypeError("unknown keyword arguments: %s" % sorted(kwargs))
@@ -856,28 +943,55 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
             _release(dev)
         return out[0] if len(out) == 1 else tuple(out)
 
-    timeSteps, tau = time_grid(tspan, params.tstep)            # src/pdepe.jl:82-85
-    dev.mass_flags(timeSteps[0])                               # src/pdepe.jl:78-79
-    results = [shape(inival.reshape(B, Nx, npde))] if save == "all" else []
-    storage = []
-    if save != "all" and not params.hist and c_loop and timeSteps.size > 1:
-        dev.solve_steps(timeSteps, tau, params.tol, params.maxit)        # same loop, driven from C
-        timeSteps_loop = timeSteps[:1]
-    else:
-        timeSteps_loop = timeSteps
-    for i in range(timeSteps_loop.size - 1):                   # src/pdepe.jl:90
-        time_val = timeSteps[i + 1]
-        tstep_val = tau if tau is not None else timeSteps[i + 1] - timeSteps[i]
-        h = newton(pb, tstep_val, time_val, params.tol, params.maxit, params.hist, c_loop)      # :94-96
+    per_instance = np.ndim(params.tstep) == 2                   # one time grid per instance: tstep[B, nsteps+1]
+    if per_instance:
+        grids = np.ascontiguousarray(params.tstep, dtype=np.float64)
+        if grids.shape[0] != B or grids.shape[1] < 2:
+            raise ValueError("a 2-D tstep must hold one time grid per instance: [B, nsteps+1]")
         if params.hist:
-            it = dev.step_iters()
-            hs = [h[k, :it[k]] for k in range(B)]
-            storage.append(hs[0] if squeeze else hs)
+            raise ValueError("hist=True needs a time grid shared by the batch")
+        timeSteps, tau = grids, None
+        t0 = float(tspan[0])
+    else:
+        timeSteps, tau = time_grid(tspan, params.tstep)        # src/pdepe.jl:82-85
+        t0 = timeSteps[0]
+    dev.mass_flags(t0)                                         # src/pdepe.jl:78-79
+    nsteps = timeSteps.shape[-1] - 1
+    storage = []
+    whole = (per_instance or (c_loop and not params.hist)) and nsteps >= 1 and dev.design == "resident" and not dev.longmesh()
+    if per_instance and not whole:
+        raise ValueError("per-instance time grids need the resident design and a mesh in the batched range")
+    if whole:
+        # the time loop of src/pdepe.jl:90-108 in one launch (sb_solve_steps_opt); with save="all" every state is
+        # written by the kernel and streamed to pinned host memory round by round while later rounds compute
+        snaps = pinned_empty((nsteps + 1, B, Nx, npde)) if save == "all" else None
+        dev.solve_steps_opt(None if per_instance else timeSteps, tau, params.tol, params.maxit, snapshots=snaps,
+                            tgrid_per_instance=grids if per_instance else None)
         if save == "all":
+            results = [shape(snaps[i]) for i in range(nsteps + 1)]
+        else:
+            results = [shape(dev.download())]
+    else:
+        results = [shape(inival.reshape(B, Nx, npde))] if save == "all" else []
+        if save != "all" and not params.hist and c_loop and timeSteps.size > 1:
+            dev.solve_steps(timeSteps, tau, params.tol, params.maxit)        # same loop, driven from C
+            timeSteps_loop = timeSteps[:1]
+        else:
+            timeSteps_loop = timeSteps
+        for i in range(timeSteps_loop.size - 1):                   # src/pdepe.jl:90
+            time_val = timeSteps[i + 1]
+            tstep_val = tau if tau is not None else timeSteps[i + 1] - timeSteps[i]
+            h = newton(pb, tstep_val, time_val, params.tol, params.maxit, params.hist, c_loop)      # :94-96
+            if params.hist:
+                it = dev.step_iters()
+                hs = [h[k, :it[k]] for k in range(B)]
+                storage.append(hs[0] if squeeze else hs)
+            if save == "all":
+                results.append(shape(dev.download()))
+        if save != "all":
             results.append(shape(dev.download()))
     if save != "all":
-        results.append(shape(dev.download()))
-        sol = DiffEqArray(results, timeSteps[-1:])
+        sol = DiffEqArray(results, timeSteps[..., -1:])
     else:
         if alias_compat:
             Mm = shape(dev.mass())

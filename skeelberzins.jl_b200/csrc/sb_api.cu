@@ -50,15 +50,19 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 128;  // ring of per-iteration "still active" counters
 
+// designs whose per-iteration kernel is the persistent k_newton_fused_p (the resident design adds the whole-solve kernel
+// for the loops driven from C)
+inline bool is_tma(int design) { return design == SB_DESIGN_FUSED_TMA || design == SB_DESIGN_RESIDENT; }
+
 std::atomic<long long> g_launches{0};  // kernels launched by this library (all contexts; contexts may run on different host threads)
 
 // Kernel handles of one problem: host function pointers of the statically compiled registry kernels, or
 // cudaKernel_t handles of kernels compiled at run time (NVRTC) for a user functor.  Both launch through
 // cudaLaunchKernel.
 struct KernelSet {
-    const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr;
+    const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr, *resident = nullptr;
     const void *long_chunk = nullptr, *long_back = nullptr, *long_assemble_jac = nullptr, *long_assemble_val = nullptr;
-    size_t fused_p_smem = 0, long_smem = 0;
+    size_t fused_p_smem = 0, long_smem = 0, resident_smem = 0;
     bool long_configured = false;
     cudaLibrary_t lib = nullptr;  // owner of the run-time compiled kernels (user functors)
 };
@@ -326,6 +330,19 @@ struct sb_problem {
     bool lazy_pending = false;   // the current step started without k_begin_step and no iteration has run yet
     bool step_all_tma = false;   // every Newton iteration of the current step so far was a k_newton_fused_p launch: only that
                                  // kernel writes b = M.*u_{n+1} when an instance converges and maintains the compacted list
+    // whole-solve kernel (sb_resident.cuh)
+    int r_grid = 0;              // its grid (0: not configured yet)
+    double* d_itgrid = nullptr;  // per-instance time grids [B][nsteps+1]
+    size_t itgrid_cap = 0;
+    int* d_step_iters = nullptr; // [B][nsteps]
+    size_t step_iters_cap = 0;
+    double* d_snap = nullptr;    // [nsteps+1][B][Nx*P] snapshots, reference layout
+    size_t snap_cap = 0;
+    unsigned int* d_rmisc = nullptr;      // fail_step | max_iters | sum of iterations (2 words) | round counters [kMaxRounds]
+    unsigned int* h_rounds = nullptr;     // mapped pinned: round-complete flags [kMaxRounds]
+    cudaStream_t copy_stream = nullptr;   // D2H of finished snapshot rounds while later rounds compute
+    double* d_piv = nullptr;     // workspace pool of the pivoted fallback solve (band arrays) ...
+    int* d_piv_lock = nullptr;   // ... and its slot locks
     double* d_uin = nullptr;     // scratch state in device layout for sb_assemble / sb_assemble_device / sb_pdeval (kept)
     double* d_eval = nullptr;    // scratch of sb_pdeval: mesh | points | results (kept, grown on demand)
     size_t eval_elems = 0;
@@ -477,6 +494,9 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_fused_p_smem = sb::FusedPLayout<%s, %d, %d, %s>::bytes;\n",
              uf.name.c_str(), R, TT, sym);
     src += buf;
+    snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_resident_smem = sb::ResidentLayout<%s, %d, %d, %s>::bytes;\n",
+             uf.name.c_str(), R, TT, sym);
+    src += buf;
     if (longmesh) {
         snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_long_smem = sb::LongStage<%s, %d, %d, %s>::bytes;\n",
                  uf.name.c_str(), R, TT, sym);
@@ -492,6 +512,7 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     name("sb::k_assemble<%s, %d, %d, %s, false>");
     name("sb::k_newton_fused<%s, %d, %d, %s>");
     name("sb::k_newton_fused_p<%s, %d, %d, %s>");
+    name("sb::k_solve_resident<%s, %d, %d, %s>");
     if (longmesh) {
         name("sb::k6_chunk_asm<%s, %d, %d, %s>");
         name("sb::k6_back_asm<%s, %d, %d, %s>");
@@ -540,7 +561,7 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     KernelSet& ks = pb->ks;
     cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
-    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p,
+    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p, &ks.resident,
                             &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
     for (size_t i = 0; i < lowered.size(); ++i) {
         cudaKernel_t kern;
@@ -554,6 +575,10 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "reading the shared-memory size of the compiled kernel: %s", cudaGetErrorString(e));
     ks.fused_p_smem = (size_t)smem;
+    e = cudaLibraryGetGlobal(&dptr, &bytes, ks.lib, "sb_user_resident_smem");
+    if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "reading the shared-memory size of the compiled resident kernel: %s", cudaGetErrorString(e));
+    ks.resident_smem = (size_t)smem;
     if (pb->longmesh) {
         e = cudaLibraryGetGlobal(&dptr, &bytes, ks.lib, "sb_user_long_smem");
         if (e == cudaSuccess) e = cudaMemcpy(&smem, dptr, sizeof smem, cudaMemcpyDeviceToHost);
@@ -808,7 +833,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
 
     sb_problem* pb = new sb_problem;
     ctx->refs++;
-    pb->ctx = ctx; pb->fe = fe; pb->P = f_npde; pb->nparams = f_nparams; pb->design = pb->design_pending = SB_DESIGN_FUSED_TMA;
+    pb->ctx = ctx; pb->fe = fe; pb->P = f_npde; pb->nparams = f_nparams; pb->design = pb->design_pending = SB_DESIGN_RESIDENT;
     pb->dec = pick_decomposition(Nx, pb->P);
     if (getenv("SB_FORCE_LONGMESH") && pb->P == 1) pb->dec = -1;   // testing: long-mesh path on short meshes
     int R, T, ntiles = 1;
@@ -894,6 +919,12 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     TRY(dev_alloc(&pb->d_total, (size_t)B));
     TRY(dev_alloc(&pb->d_count, (size_t)2 * kSlots));  // active counts [kSlots] + done tickets [kSlots]
     TRY(dev_alloc(&pb->d_list, (size_t)2 * B));
+    constexpr int kPivSlots = 64;   // concurrent pivoted fallback solves (a group that finds none free waits for one)
+    const size_t piv_stride = (size_t)Nx * pb->P * ((pb->P == 1 ? BandShape<1>::ldab : BandShape<2>::ldab) + 1);
+    if (!pb->longmesh) {
+        TRY(dev_alloc(&pb->d_piv, kPivSlots * piv_stride));
+        TRY(dev_alloc(&pb->d_piv_lock, (size_t)kPivSlots));
+    }
 #undef TRY
     if (rc != SB_OK) { sb_problem_destroy(pb); return rc; }
     cudaError_t e = cudaHostAlloc((void**)&pb->h_count, 3 * kSlots * sizeof(unsigned int), cudaHostAllocMapped);  // count | step | iteration
@@ -916,6 +947,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_total, 0, B * sizeof(long long), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_norm, 0, B * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(pb->d_count, 0, 2 * kSlots * sizeof(unsigned int), st);
+    if (e == cudaSuccess && pb->d_piv_lock) e = cudaMemsetAsync(pb->d_piv_lock, 0, kPivSlots * sizeof(int), st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "problem upload: %s", cudaGetErrorString(e)); }
     // all-ones mass flags until sb_mass_flags is called
@@ -935,6 +967,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;
     pd.list[0] = pb->d_list; pd.list[1] = pb->d_list + B;
     pd.done_count = pb->d_count + kSlots; pd.host_count = d_hcount;
+    pd.piv_band = pb->d_piv; pd.piv_lock = pb->d_piv_lock; pd.piv_slots = pb->d_piv ? kPivSlots : 0; pd.piv_stride = piv_stride;
     pb->last_active = B;
     if (fe) {
         KernelSet& ks = pb->ks;
@@ -944,6 +977,8 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         ks.fused = (const void*)fe->fused[pb->dec][pb->sym0];
         ks.fused_p = (const void*)fe->fused_p[pb->dec][pb->sym0];
         ks.fused_p_smem = fe->fused_p_smem[pb->dec][pb->sym0];
+        ks.resident = (const void*)fe->resident[pb->dec][pb->sym0];
+        ks.resident_smem = fe->resident_smem[pb->dec][pb->sym0];
         ks.long_chunk = (const void*)fe->long_chunk[pb->sym0];
         ks.long_back = (const void*)fe->long_back[pb->sym0];
         ks.long_smem = fe->long_smem[pb->sym0];
@@ -967,7 +1002,9 @@ int sb_problem_destroy(sb_problem* pb) {
     cudaStreamSynchronize(pb->ctx->stream);
     guarded_free(pb->d_mesh); guarded_free(pb->d_prm); guarded_free(pb->d_u); guarded_free(pb->d_b); guarded_free(pb->d_F); guarded_free(pb->d_J);
     guarded_free(pb->d_mass); guarded_free(pb->d_norm); guarded_free(pb->d_hist); guarded_free(pb->d_tmp); guarded_free(pb->d_active);
-    guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid); guarded_free(pb->d_uin); guarded_free(pb->d_eval);
+    guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid); guarded_free(pb->d_uin); guarded_free(pb->d_eval); guarded_free(pb->d_piv); guarded_free(pb->d_piv_lock); guarded_free(pb->d_itgrid); guarded_free(pb->d_step_iters); guarded_free(pb->d_snap); guarded_free(pb->d_rmisc);
+    if (pb->h_rounds) cudaFreeHost(pb->h_rounds);
+    if (pb->copy_stream) cudaStreamDestroy(pb->copy_stream);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
     if (pb->ks.lib) cudaLibraryUnload(pb->ks.lib);
@@ -1002,11 +1039,11 @@ int sb_problem_quadrature(sb_problem* pb, double* xi, double* zeta) {
 
 int sb_problem_set_design(sb_problem* pb, int design) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
-    if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED && design != SB_DESIGN_FUSED_TMA)
+    if (design != SB_DESIGN_SPLIT && design != SB_DESIGN_FUSED && design != SB_DESIGN_FUSED_TMA && design != SB_DESIGN_RESIDENT)
         return fail(SB_ERR_INVALID, "unknown design %d", design);
     pb->design_pending = design;  // takes effect at the next sb_begin_step (a step is never mixed)
     if (pb->launched == 0) {
-        if (design != SB_DESIGN_FUSED_TMA && pb->lazy_pending) {   // only the fused_tma kernel can start from b alone
+        if (!is_tma(design) && pb->lazy_pending) {   // only the fused_tma kernel can start from b alone
             CU(cudaSetDevice(pb->ctx->device));
             int rc = materialize_begin(pb);
             if (rc) return rc;
@@ -1217,7 +1254,7 @@ int sb_begin_step(sb_problem* pb, double t_next, double inv_tau) {
     if (pb->prof) { int rc = prof_harvest(pb); if (rc) return rc; pb->prof_harvested = 0; }
     pb->t_next = t_next; pb->inv_tau = inv_tau;
     pb->design = pb->design_pending;
-    const bool lazy = pb->b_ready && pb->design == SB_DESIGN_FUSED_TMA && !pb->longmesh && !getenv("SB_NO_LAZY_BEGIN");
+    const bool lazy = pb->b_ready && is_tma(pb->design) && !pb->longmesh && !getenv("SB_NO_LAZY_BEGIN");
     pb->b_ready = false;
     pb->lazy_pending = false;
     pb->pd.lazy_b = 0;
@@ -1343,16 +1380,16 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         return sb_solve_update_norm(pb, tol);
     }
     CU(cudaSetDevice(pb->ctx->device));
-    if (pb->design == SB_DESIGN_FUSED_TMA && pb->launched > 0 && !pb->step_all_tma)
+    if (is_tma(pb->design) && pb->launched > 0 && !pb->step_all_tma)
         return fail(SB_ERR_INVALID, "a fused_tma iteration cannot follow a split / fused / two-call iteration inside the same "
                     "step: only fused_tma launches maintain the compacted list of active instances it reads");
     int slot;
     int rc = SB_OK;
-    if (pb->design != SB_DESIGN_FUSED_TMA && (rc = materialize_begin(pb))) return rc;   // k_newton_fused reads u and active[]
+    if (!is_tma(pb->design) && (rc = materialize_begin(pb))) return rc;   // k_newton_fused reads u and active[]
     if ((rc = prepare_slot(pb, &slot))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    if (pb->design == SB_DESIGN_FUSED_TMA) {
+    if (is_tma(pb->design)) {
         const void* kern = pb->ks.fused_p;
         if (pb->p_grid == 0) {  // one-time configuration: opt in to the shared memory, size the persistent grid
             pb->p_smem = pb->ks.fused_p_smem;
@@ -1417,10 +1454,167 @@ int sb_wait_iteration(sb_problem* pb, int it, int64_t* n_active) {
     return SB_OK;
 }
 
+}  // extern "C"
+
+// ---- whole solve in one launch (sb_resident.cuh) ---------------------------------------------------------------------
+constexpr int kMaxRounds = 4096;   // rounds of the persistent grid over the batch that snapshot streaming can track
+
+static bool resident_enabled(const sb_problem* pb) {
+    static const bool off = getenv("SB_NO_RESIDENT") != nullptr;
+    return !off && !pb->longmesh && pb->design_pending == SB_DESIGN_RESIDENT && pb->ks.resident != nullptr;
+}
+
+template <class T>
+static int grow(T** p, size_t* cap, size_t need, cudaStream_t st) {
+    if (*cap >= need) return SB_OK;
+    if (*p) { CU(cudaStreamSynchronize(st)); guarded_free(*p); *p = nullptr; *cap = 0; }
+    CU(guarded_malloc((void**)p, need * sizeof(T)));
+    *cap = need;
+    return SB_OK;
+}
+
+// nsteps implicit-Euler steps (tgrid != NULL) or one Newton solve at (t_single, inv_tau_single) on the b that
+// sb_begin_step prepared (tgrid == NULL), every instance resident on its SM from the first to the last iteration.
+static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const double* inst_tgrid, double tau, double t_single,
+                          double inv_tau_single, double tol, int maxit, int32_t* step_iters_host, double* snap_host,
+                          int* steps_done, int* max_iters_out) {
+    cudaStream_t st = pb->ctx->stream;
+    const ProbDev& pd = pb->pd;
+    const int64_t B = pd.B;
+    const bool b_given = (tgrid == nullptr && inst_tgrid == nullptr);
+    const int G = pb->warp ? kWarpBlockThreads / 32 : 1;
+    const unsigned threads = pb->warp ? kWarpBlockThreads : (unsigned)pd.T;
+    if (pb->r_grid == 0) {
+        CU(cudaFuncSetAttribute(pb->ks.resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->ks.resident_smem));
+        int occ = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb->ks.resident, (int)threads, pb->ks.resident_smem));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pb->ctx->device));
+        if (occ < 1) return fail(SB_ERR_UNSUPPORTED, "resident kernel does not fit on an SM (%zu bytes of shared memory)", pb->ks.resident_smem);
+        if (const char* e = getenv("SB_PERSISTENT_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < occ) occ = v; }
+        pb->r_grid = (int)std::min<int64_t>((int64_t)occ * sms, (B + G - 1) / G);
+    }
+    const int64_t stride = (int64_t)pb->r_grid * G;
+    const int rounds = (int)((B + stride - 1) / stride);
+    if (!pb->d_rmisc) {
+        CU(guarded_malloc((void**)&pb->d_rmisc, (4 + kMaxRounds) * sizeof(unsigned int)));
+        CU(cudaHostAlloc((void**)&pb->h_rounds, kMaxRounds * sizeof(unsigned int), cudaHostAllocMapped));
+    }
+    ResidentArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.nsteps = nsteps; ra.maxit = maxit; ra.b_given = b_given ? 1 : 0; ra.tol = tol; ra.tau = tau;
+    ra.t_single = t_single; ra.inv_tau_single = inv_tau_single;
+    if (tgrid) {
+        if (pb->tgrid_cap < nsteps + 1) {
+            if (pb->d_tgrid) { CU(cudaStreamSynchronize(st)); CU(guarded_free(pb->d_tgrid)); pb->d_tgrid = nullptr; }
+            CU(guarded_malloc((void**)&pb->d_tgrid, (size_t)(nsteps + 1) * sizeof(double)));
+            pb->tgrid_cap = nsteps + 1;
+        }
+        CU(cudaMemcpyAsync(pb->d_tgrid, tgrid, (size_t)(nsteps + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+        ra.tgrid = pb->d_tgrid;
+    }
+    if (inst_tgrid) {
+        const size_t n = (size_t)B * (nsteps + 1);
+        int rc = grow(&pb->d_itgrid, &pb->itgrid_cap, n, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(pb->d_itgrid, inst_tgrid, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        ra.inst_tgrid = pb->d_itgrid;
+    }
+    if (step_iters_host) {
+        int rc = grow(&pb->d_step_iters, &pb->step_iters_cap, (size_t)B * nsteps, st);
+        if (rc) return rc;
+        ra.step_iters = pb->d_step_iters;
+    }
+    const size_t row = (size_t)pd.Nx * pb->P;              // doubles per instance and snapshot
+    const bool stream_snaps = snap_host != nullptr && rounds <= kMaxRounds;
+    if (snap_host) {
+        int rc = grow(&pb->d_snap, &pb->snap_cap, (size_t)(nsteps + 1) * B * row, st);
+        if (rc) return rc;
+        ra.snap = pb->d_snap;
+        if (!pb->copy_stream) CU(cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking));
+    }
+    unsigned int init[4] = {0x7fffffffu, 0u, 0u, 0u};
+    CU(cudaMemcpyAsync(pb->d_rmisc, init, sizeof init, cudaMemcpyHostToDevice, st));
+    ra.fail_step = reinterpret_cast<int*>(pb->d_rmisc);
+    ra.max_iters = reinterpret_cast<int*>(pb->d_rmisc + 1);
+    ra.sum_iters = reinterpret_cast<unsigned long long*>(pb->d_rmisc + 2);
+    if (stream_snaps) {
+        CU(cudaMemsetAsync(pb->d_rmisc + 4, 0, (size_t)rounds * sizeof(unsigned int), st));
+        for (int r = 0; r < rounds; ++r) pb->h_rounds[r] = 0u;
+        unsigned int* d_h = nullptr;
+        CU(cudaHostGetDevicePointer((void**)&d_h, pb->h_rounds, 0));
+        ra.round_done = pb->d_rmisc + 4;
+        ra.host_rounds = d_h;
+    }
+    if (pb->prof) CU(cudaEventRecord(pb->evA[0], st));
+    CU(launch_any(pb->ks.resident, dim3((unsigned)pb->r_grid), dim3(threads), pb->ks.resident_smem, st, pb->pd, ra));
+    CU(cudaGetLastError());
+    if (pb->prof) CU(cudaEventRecord(pb->evB[0], st));
+    // from here on the state is what the kernel leaves: u = u(t_end), b unspecified
+    pb->b_ready = false; pb->lazy_pending = false; pb->pd.lazy_b = 0; pb->step_all_tma = false;
+    pb->launched = 0; pb->confirmed = 0;
+
+    if (snap_host) {
+        const int s0 = b_given ? 1 : 0;
+        if (stream_snaps) {
+            // finished rounds leave for the host while later rounds compute (src/pdepe.jl:99-107 stores every step)
+            for (int r = 0; r < rounds; ++r) {
+                volatile unsigned int* flag = pb->h_rounds + r;
+                unsigned long spins = 0;
+                while (*flag == 0u) {
+                    if ((++spins & 0x3FFF) == 0) {
+                        cudaError_t e = cudaStreamQuery(st);
+                        if (e == cudaSuccess) { if (*flag == 0u) return fail(SB_ERR_CUDA, "resident kernel ended without finishing round %d", r); break; }
+                        if (e != cudaErrorNotReady) return fail(SB_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(e));
+                    }
+                }
+                const int64_t k0 = (int64_t)r * stride, nk = std::min<int64_t>(stride, B - k0);
+                for (int s = s0; s <= nsteps; ++s) {
+                    const size_t off = ((size_t)s * B + k0) * row;
+                    CU(cudaMemcpyAsync(snap_host + off, pb->d_snap + off, (size_t)nk * row * sizeof(double), cudaMemcpyDeviceToHost, pb->copy_stream));
+                }
+            }
+            CU(cudaStreamSynchronize(pb->copy_stream));
+        } else {
+            CU(cudaStreamSynchronize(st));
+            const size_t off = (size_t)s0 * B * row;
+            CU(cudaMemcpy(snap_host + off, pb->d_snap + off, ((size_t)(nsteps + 1 - s0) * B * row) * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+    }
+    unsigned int res[4];
+    CU(cudaMemcpyAsync(res, pb->d_rmisc, sizeof res, cudaMemcpyDeviceToHost, st));
+    if (step_iters_host)
+        CU(cudaMemcpyAsync(step_iters_host, pb->d_step_iters, (size_t)B * nsteps * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int fail_step = (int)res[0];
+    unsigned long long sum_iters;
+    memcpy(&sum_iters, res + 2, sizeof sum_iters);
+    if (pb->prof) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, pb->evA[0], pb->evB[0]));
+        pb->prof_ms_solve += ms; pb->prof_launches += 1; pb->prof_inst_iters += (int64_t)sum_iters;
+    }
+    if (max_iters_out) *max_iters_out = (int)res[1];
+    const bool failed = fail_step != 0x7fffffff;
+    pb->last_active = failed ? 1 : 0;
+    pb->predicted_iters = 0;
+    if (steps_done) *steps_done = failed ? fail_step : nsteps;
+    if (failed) return fail(SB_ERR_CONVERGENCE, "convergence failed");   // src/utils.jl:336
+    return SB_OK;
+}
+
+extern "C" {
+
 int sb_newton_solve(sb_problem* pb, double tol, int maxit, int* iters_done) {
     if (!pb) return fail(SB_ERR_INVALID, "problem is NULL");
     if (maxit < 1) return fail(SB_ERR_INVALID, "maxit must be >= 1");
     CU(cudaSetDevice(pb->ctx->device));
+    if (resident_enabled(pb) && pb->design == SB_DESIGN_RESIDENT && pb->launched == 0) {
+        // the whole Newton loop of this step in one launch, on the b that sb_begin_step prepared
+        int mx = 0;
+        int rc = solve_resident(pb, 1, nullptr, nullptr, -1.0, pb->t_next, pb->inv_tau, tol, maxit, nullptr, nullptr, nullptr, &mx);
+        if (iters_done) *iters_done = mx;
+        return rc;
+    }
     const long depth = 2;  // iterations kept in flight beyond the last one whose count has been read
     const long base = pb->launched;
     // Speculation limit: launches are enqueued ahead of the host's knowledge only up to the number of iterations
@@ -1506,7 +1700,12 @@ static int solve_steps_auto(sb_problem* pb, int nsteps, const double* tgrid, dou
 int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, int* steps_done) {
     if (!pb || !tgrid || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
     if (steps_done) *steps_done = 0;
-    if (pb->design_pending == SB_DESIGN_FUSED_TMA && !pb->longmesh && !pb->prof && !pb->pd.hist && nsteps > 1 && maxit >= 2 &&
+    if (resident_enabled(pb) && (!pb->pd.hist || nsteps == 1) && maxit >= 1) {
+        CU(cudaSetDevice(pb->ctx->device));
+        pb->design = pb->design_pending;
+        return solve_resident(pb, nsteps, tgrid, nullptr, tau, 0.0, 0.0, tol, maxit, nullptr, nullptr, steps_done, nullptr);
+    }
+    if (is_tma(pb->design_pending) && !pb->longmesh && !pb->prof && !pb->pd.hist && nsteps > 1 && maxit >= 2 &&
         !getenv("SB_NO_DEVICE_STEPPING")) {
         CU(cudaSetDevice(pb->ctx->device));
         return solve_steps_auto(pb, nsteps, tgrid, tau, tol, maxit, steps_done);
@@ -1520,6 +1719,20 @@ int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, 
         if (steps_done) *steps_done = i + 1;
     }
     return SB_OK;
+}
+
+int sb_solve_steps_opt(sb_problem* pb, int nsteps, const double* tgrid, const double* tgrid_per_instance, double tau, double tol,
+                       int maxit, int32_t* step_iters, double* snapshots, int* steps_done) {
+    if (!pb || (!tgrid && !tgrid_per_instance) || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
+    if (steps_done) *steps_done = 0;
+    if (maxit < 1) return fail(SB_ERR_INVALID, "maxit must be >= 1");
+    if (pb->longmesh) return fail(SB_ERR_UNSUPPORTED, "sb_solve_steps_opt: the long-mesh path has no whole-solve kernel; use sb_solve_steps");
+    if (!resident_enabled(pb)) return fail(SB_ERR_UNSUPPORTED, "sb_solve_steps_opt needs the resident design (whole-solve kernel)");
+    if (pb->pd.hist && nsteps > 1) return fail(SB_ERR_UNSUPPORTED, "norm histories are kept per step: drive the steps one by one with hist enabled");
+    CU(cudaSetDevice(pb->ctx->device));
+    pb->design = pb->design_pending;
+    return solve_resident(pb, nsteps, tgrid_per_instance ? nullptr : tgrid, tgrid_per_instance, tgrid_per_instance ? -1.0 : tau, 0.0, 0.0,
+                          tol, maxit, step_iters, snapshots, steps_done, nullptr);
 }
 
 #define SB_GET(NAME, TYPE, DEVPTR)                                                                       \

@@ -19,12 +19,13 @@ template <int P> struct BandShape { static constexpr int kl = 2 * P - 1, ku = 2 
 
 // Solve A x = rhs in place (rhs <- x).  Returns 0, or j+1 if the pivot of column j is exactly zero (singular matrix:
 // rhs is then unspecified).  ab is overwritten by the factors.
-template <int KL, int KU>
-__host__ __device__ inline int banded_lu_solve(double* ab, int n, double* rhs) {
+// Ptr: double* on the host; volatile double* in the kernels (the band was written by other threads of the CTA)
+template <int KL, int KU, class Ptr>
+__host__ __device__ inline int banded_lu_solve(Ptr ab, int n, Ptr rhs) {
     constexpr int KV = KL + KU, LD = 2 * KL + KU + 1;
     int ju = 0, info = 0;
     for (int j = 0; j < n; ++j) {
-        double* col = ab + (size_t)j * LD;
+        Ptr col = ab + (size_t)j * LD;
         const int km = (KL < n - 1 - j) ? KL : n - 1 - j;
         int jp = 0;                                             // pivot search in A(j..j+km, j)
         double best = col[KV] < 0 ? -col[KV] : col[KV];
@@ -36,7 +37,7 @@ __host__ __device__ inline int banded_lu_solve(double* ab, int n, double* rhs) {
         { const int c = j + KU + jp; const int cm = c < n - 1 ? c : n - 1; if (cm > ju) ju = cm; }
         if (jp != 0) {                                          // interchange rows j and j+jp over columns j..ju, and the rhs
             for (int c = j; c <= ju; ++c) {
-                double* cc = ab + (size_t)c * LD;
+                Ptr cc = ab + (size_t)c * LD;
                 const int r0 = KV - (c - j);
                 const double tmp = cc[r0 + jp]; cc[r0 + jp] = cc[r0]; cc[r0] = tmp;
             }
@@ -44,25 +45,25 @@ __host__ __device__ inline int banded_lu_solve(double* ab, int n, double* rhs) {
         }
         if (km > 0) {
             const double ip = 1.0 / col[KV];
-            for (int p = 1; p <= km; ++p) col[KV + p] *= ip;    // multipliers
+            for (int p = 1; p <= km; ++p) col[KV + p] = col[KV + p] * ip;    // multipliers
             for (int c = j + 1; c <= ju; ++c) {                 // rank-1 update of the trailing band
-                double* cc = ab + (size_t)c * LD;
+                Ptr cc = ab + (size_t)c * LD;
                 const int r0 = KV - (c - j);
                 const double ujc = cc[r0];
                 if (ujc != 0.0)
-                    for (int p = 1; p <= km; ++p) cc[r0 + p] -= col[KV + p] * ujc;
+                    for (int p = 1; p <= km; ++p) cc[r0 + p] = cc[r0 + p] - col[KV + p] * ujc;
             }
             const double rj = rhs[j];                           // L^{-1} applied to the rhs on the fly
-            for (int p = 1; p <= km; ++p) rhs[j + p] -= col[KV + p] * rj;
+            for (int p = 1; p <= km; ++p) rhs[j + p] = rhs[j + p] - col[KV + p] * rj;
         }
     }
     if (info) return info;
     for (int j = n - 1; j >= 0; --j) {                          // U x = y
-        const double* col = ab + (size_t)j * LD;
+        Ptr col = ab + (size_t)j * LD;
         const double xj = rhs[j] / col[KV];
         rhs[j] = xj;
         const int lm = (KV < j) ? KV : j;
-        for (int p = 1; p <= lm; ++p) rhs[j - p] -= col[KV - p] * xj;
+        for (int p = 1; p <= lm; ++p) rhs[j - p] = rhs[j - p] - col[KV - p] * xj;
     }
     return 0;
 }

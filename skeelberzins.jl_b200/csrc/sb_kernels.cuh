@@ -15,6 +15,7 @@
 //   k_newton_fused<Fn,R,TT,SYM0>  K3+K4+K7 in one kernel: J and F never leave the SM
 //   k_begin_step, k_mass_flags
 #pragma once
+#include "sb_banded.cuh"
 #include "sb_dual.cuh"
 #include "sb_functors.cuh"
 
@@ -76,6 +77,12 @@ struct ProbDev {
     int* auto_state;                      // [2] time step, Newton iteration inside it: what the next launch continues with
     const double* auto_tgrid;             // [auto_nsteps + 1]
     double auto_tau;                      // constant time step, or <= 0: tgrid[s+1] - tgrid[s]
+    // Workspace of the pivoted fallback solve (sb_banded.cuh): piv_slots band arrays of piv_stride doubles each (band
+    // followed by the right-hand side), handed out through piv_lock[slot] (0 free, 1 taken)
+    double* piv_band;
+    int* piv_lock;
+    int piv_slots;
+    unsigned long long piv_stride;
 };
 
 // Completion notice of a Newton-iteration launch without a copy node in the stream: every thread group takes a
@@ -164,16 +171,36 @@ struct ChunkThomas {
     Mat<P> As, Bs, Cs;
     Vec<P> ds;
 
+    // Pivot-growth monitor.  Without row interchanges the elimination is only as good as its normalised factors are
+    // small: on (block) diagonally dominant matrices every entry of ct, inv*A and of the cyclic-reduction rows stays
+    // below 1 in magnitude.  mon = largest exponent word seen; above kGrowthHi (2^14; NaN and Inf included) the caller
+    // re-solves the instance with the pivoted banded LU of sb_banded.cuh.  Integer max on the high word: two ALU
+    // instructions per watched value, nothing on the fp64 pipe.
+    static constexpr unsigned kGrowthHi = (1023u + 14u) << 20;
+    unsigned mon = 0;
+    SB_D void watch(double v) {
+#ifndef SB_NO_PIVOT_MONITOR
+        mon = max(mon, (unsigned)__double2hiint(v) & 0x7fffffffu);
+#endif
+    }
+    SB_D void watch(const Mat<P>& M) {
+#pragma unroll
+        for (int i = 0; i < P * P; ++i) watch(M.a[i]);
+    }
+
     SB_D void row(int r, const Mat<P>& A, const Mat<P>& Bm, const Mat<P>& C, const Vec<P>& d) {
         if (r == R - 1) { As = A; Bs = Bm; Cs = C; ds = d; return; }
         if (r == 0) {
             const Mat<P> inv = inverse_fast(Bm);
             ct[0] = mul(inv, C); vt[0] = mul(inv, A); dt[0] = mul(inv, d);
+            watch(ct[0]); watch(vt[0]);
         } else {
             const Mat<P> inv = inverse_fast(sub_mul(Bm, A, ct[r - 1]));
+            const Mat<P> la = mul(inv, A);                    // normalised sub-diagonal block of the row
             ct[r] = mul(inv, C);
-            dt[r] = mul(inv, sub_mul(d, A, dt[r - 1]));
-            vt[r] = neg(mul(inv, mul(A, vt[r - 1])));
+            dt[r] = sub_mul(mul(inv, d), la, dt[r - 1]);
+            vt[r] = neg(mul(la, vt[r - 1]));
+            watch(ct[r]); watch(la);
         }
     }
 
@@ -194,7 +221,7 @@ struct ChunkThomas {
 #ifdef SB_FINISH_SERIAL   // tuning builds: the round-1 second level (warp 0 solves the separators alone), for A/B runs
     template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
 #else
-    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : 2 * NW * (TT / 32); }
+    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + 1) * (TT / 32); }
 #endif
     // ... followed by one partial sum per warp for system_sum()
     template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : exch_doubles<TT>() + TT / 32; }
@@ -254,7 +281,7 @@ struct ChunkThomas {
     struct NoHook { SB_D void operator()() const {} };
 
     template <int TT>
-    SB_D void finish(Vec<P> (&x)[R], double* sm, int t) { finish<TT>(x, sm, t, NoHook()); }
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t) { return finish<TT>(x, sm, t, NoHook()); }
 
     // Solve.  x[r] = unknowns of the thread's rows, t = thread index inside the system, sm = exch_doubles<TT>() doubles.
     //
@@ -272,10 +299,12 @@ struct ChunkThomas {
     //     values its own warp needs.
     // hook(): called by every thread right after the barrier (TT == 32: after the first shuffle), when all threads
     // of the system have finished reading their inputs, e.g. to start the prefetch of the next instance.
+    // Returns true (the same value in every thread of the system) when the pivot-growth monitor tripped anywhere in
+    // the system: x is then not to be trusted and the caller solves the instance again with row interchanges.
 #ifdef SB_FINISH_SERIAL
     template <int TT, class Hook>
-    SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
-        if constexpr (TT == 32) finish_parallel<TT>(x, sm, t, hook);
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+        if constexpr (TT == 32) return finish_parallel<TT>(x, sm, t, hook);
         else {
             Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
             if constexpr (R == 1) summary(y0, v0, w0, yL, vL, wL);
@@ -326,13 +355,14 @@ struct ChunkThomas {
             }
             if constexpr (R == 1) x[0] = xs;
             else explicit_rows(x, xp, xs);
+            return false;
         }
     }
     template <int TT, class Hook>
-    SB_D void finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+    SB_D bool finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
 #else
     template <int TT, class Hook>
-    SB_D void finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
 #endif
         constexpr int W = TT / 32;
         const int lane = t & 31;
@@ -358,6 +388,7 @@ struct ChunkThomas {
         unpack(nb, v0n, w0n, y0n);
         Mat<P> an, cn; Vec<P> dn;
         reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
+        watch(an); watch(cn);
 
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {  // parallel cyclic reduction across the warp
@@ -387,7 +418,13 @@ struct ChunkThomas {
             }
             const Mat<P> inv = inverse_fast(b2);
             an = mul(inv, a2); cn = mul(inv, c2); dn = mul(inv, d2);
+            watch(an); watch(cn);
         }
+#ifndef SB_NO_PIVOT_MONITOR
+        unsigned grow = __reduce_max_sync(0xffffffffu, mon);   // largest factor seen anywhere in the warp
+#else
+        unsigned grow = 0;
+#endif
 
         Vec<P> xs = dn, xp;
         Vec<P> Xp = vec_zero<P>();
@@ -405,9 +442,13 @@ struct ChunkThomas {
                 pack(mine, an, cn, dn);
 #pragma unroll
                 for (int w = 0; w < NW; ++w) eq[NW + w] = mine[w];
+                reinterpret_cast<unsigned*>(sm + 2 * NW * W)[2 * wi] = grow;
             }
             __syncthreads();
             hook();
+#pragma unroll
+            for (int w = 0; w < W; ++w) grow = max(grow, reinterpret_cast<const unsigned*>(sm + 2 * NW * W)[2 * w]);
+            mon = grow;
             // forward: L(w) = al[w] - be[w]*F(w+1),  F(w) = ga[w] - de[w]*F(w+1)
             Vec<P> al[W], ga[W]; Mat<P> be[W], de[W];
             {
@@ -427,6 +468,7 @@ struct ChunkThomas {
                 const Mat<P> G = inverse_fast(sub_mul(mat_identity<P>(), fa, be[w - 1]));
                 ga[w] = mul(G, sub_mul(fd, fa, al[w - 1]));
                 de[w] = mul(G, fc);
+                watch(de[w]);
                 if (w < W - 1) {
                     Mat<P> la, lc; Vec<P> ld;
 #pragma unroll
@@ -435,8 +477,10 @@ struct ChunkThomas {
                     const Mat<P> lab = mul(la, be[w - 1]);
                     al[w] = sub_mul(sub_mul(ld, la, al[w - 1]), neg(lab), ga[w]);
                     be[w] = sub_mul(lc, neg(lab), de[w]);
+                    watch(be[w]);
                 }
             }
+            grow = mon;                                       // the same in every thread: identical arithmetic on shared data
             // backward: every warp picks up X_prev = L(wi-1) and X_next = F(wi+1)
             Vec<P> Fn = vec_zero<P>(), Xn = vec_zero<P>();
 #pragma unroll
@@ -456,6 +500,7 @@ struct ChunkThomas {
         }
         if constexpr (R == 1) x[0] = xs;
         else explicit_rows(x, xp, xs);
+        return grow > kGrowthHi;
     }
 };
 
@@ -835,6 +880,106 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pivoted fallback (the reference's linear solve, src/utils.jl:317-319) for instances whose pivot-growth monitor
+// tripped in the parallel elimination: the thread group writes the block-tridiagonal system into a band array in
+// global memory, thread 0 factorises and solves it with row interchanges (sb_banded.cuh, one thread: slow, rare,
+// right), every thread picks up the unknowns of its rows.  status[k] = 3 records that the fallback ran (2: the matrix
+// is singular even with pivoting).
+// ---------------------------------------------------------------------------------------------
+template <int TT> SB_D void group_sync() { if constexpr (TT == 32) __syncwarp(); else __syncthreads(); }
+
+SB_D int piv_acquire(const ProbDev& pd, int start) {
+    int s = start % pd.piv_slots;
+    while (atomicCAS(pd.piv_lock + s, 0, 1) != 0) {     // holders never wait for anybody, so this ends
+        s = (s + 1 == pd.piv_slots) ? 0 : s + 1;
+        __nanosleep(200);
+    }
+    __threadfence();
+    return s;
+}
+SB_D void piv_release(const ProbDev& pd, int s) {
+    __threadfence();
+    atomicExch(pd.piv_lock + s, 0);
+}
+
+// slot for this thread group (taken by its thread 0, made known to all) and a zeroed band
+template <int P, int TT>
+SB_D int piv_begin(const ProbDev& pd, int t, int group, volatile int* sh_slot) {
+    int s = 0;
+    if (t == 0) s = piv_acquire(pd, group);
+    if constexpr (TT == 32) s = __shfl_sync(0xffffffffu, s, 0);
+    else {
+        if (t == 0) *sh_slot = s;
+        __syncthreads();
+        s = *sh_slot;
+    }
+    double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
+    const int n = pd.Nx * P * BandShape<P>::ldab;
+    for (int i = t; i < n; i += TT) ab[i] = 0.0;
+    group_sync<TT>();
+    return s;
+}
+
+template <int P>
+struct BandSink {   // row sink of assemble_chunk: block rows into LAPACK band storage, F into the right-hand side
+    double* ab; double* rhs; int i0, Nx;
+    SB_D void row(int r, const Mat<P>& A, const Mat<P>& Bm, const Mat<P>& C, const Vec<P>& d) {
+        const int i = i0 + r;
+        if (i >= Nx) return;                               // padding rows are not part of the system
+#pragma unroll
+        for (int rr = 0; rr < P; ++rr) {
+#pragma unroll
+            for (int c = 0; c < P; ++c) {
+                if (i > 0) ab[band_index<P>(i, rr, -1, c)] = A.a[rr * P + c];
+                ab[band_index<P>(i, rr, 0, c)] = Bm.a[rr * P + c];
+                if (i + 1 < Nx) ab[band_index<P>(i, rr, 1, c)] = C.a[rr * P + c];
+            }
+            rhs[i * P + rr] = d.a[rr];
+        }
+    }
+};
+
+// band complete -> solve (thread 0) -> h of this thread's rows; releases the slot
+template <int P, int R, int TT>
+SB_D void piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P]) {
+    double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
+    double* rhs = ab + (size_t)pd.Nx * P * BandShape<P>::ldab;
+    group_sync<TT>();
+    if (t == 0) {
+        const int info = banded_lu_solve<BandShape<P>::kl, BandShape<P>::ku, volatile double*>(ab, pd.Nx * P, rhs);
+        pd.status[k] = info ? 2 : 3;
+    }
+    group_sync<TT>();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int i = t * R + r;
+            h[r][p] = (i < pd.Nx) ? __ldcg(rhs + (size_t)i * P + p) : 0.0;
+        }
+    group_sync<TT>();
+    if (t == 0) piv_release(pd, s);
+}
+
+// the whole fallback for the fused kernels: assemble the rows again (from global memory: the staged copies may have
+// been refilled already), this time into the band.  Not inlined: a cold path with its own register allocation.
+template <class Fn, int R, int TT, bool SYM0, bool GLOB>
+__device__ __noinline__ void pivoted_newton_rows(ProbDev pd, MeshDev mesh, long long k, const double* ub, const double* bb,
+                                                 int t, int group, double tt, double inv_tau, volatile int* sh_slot,
+                                                 double (&h)[R][Fn::npde]) {
+    constexpr int P = Fn::npde;
+    const int s = piv_begin<P, TT>(pd, t, group, sh_slot);
+    double uc[R][P], bc[R][P];
+    load_chunk<P, R, TT>(ub, t, uc);
+    load_chunk<P, R, TT>(bb, t, bc);
+    double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
+    BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
+    assemble_chunk<Fn, R, TT, SYM0, true, GLOB>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
+                                               pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink);
+    piv_solve<P, R, TT>(pd, k, t, s, h);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3: residual + Jacobian to HBM (JAC) / assemble! value into F (!JAC)
 // ---------------------------------------------------------------------------------------------
 template <int P, int TT>
@@ -918,7 +1063,28 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_solve(ProbDev pd, double tol, int slot, i
         if (update) load_chunk<P, R, TT>(pd.u + (size_t)k * pd.L * P, t, uc);
     }
     Vec<P> h[R];
-    th.template finish<TT>(h, sm, t);
+    if (th.template finish<TT>(h, sm, t)) {   // pivot growth: the same system again, with row interchanges
+        volatile int* sh_slot = reinterpret_cast<volatile int*>(sm + ChunkThomas<P, R>::template smem_doubles<TT>());
+        const int s = piv_begin<P, TT>(pd, t, (int)k, sh_slot);
+        double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
+        BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const size_t o = (size_t)k * pd.L + (size_t)r * TT + t;
+            Mat<P> A, Bm, C; Vec<P> d;
+#pragma unroll
+            for (int i = 0; i < P * P; ++i) { A.a[i] = pd.Jl[o * P * P + i]; Bm.a[i] = pd.Jd[o * P * P + i]; C.a[i] = pd.Ju[o * P * P + i]; }
+#pragma unroll
+            for (int i = 0; i < P; ++i) d.a[i] = pd.F[o * P + i];
+            sink.row(r, A, Bm, C, d);
+        }
+        double hp[R][P];
+        piv_solve<P, R, TT>(pd, k, t, s, hp);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < P; ++p) h[r].a[p] = hp[r][p];
+    }
     if (update) {
         update_and_test<P, R, TT>(pd, k, t, uc, h, tol, slot, sm);
     } else {  // debug: leave x in F
@@ -949,7 +1115,15 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_newton_fused(ProbDev pd, double tt, doubl
     assemble_chunk<Fn, R, TT, SYM0, true>(pd, pd.mesh, pd.u + (size_t)k * pd.L * P, pd.b + (size_t)k * pd.L * P,
                                           pd.mass + (size_t)k * 4 * P, t, tt, inv_tau, pd.prm + (size_t)k * pd.nprm_s, uc, bc, th);
     Vec<P> h[R];
-    th.template finish<TT>(h, sm, t);
+    if (th.template finish<TT>(h, sm, t)) {   // pivot growth: assemble again into a band, solve with row interchanges
+        double hp[R][P];
+        pivoted_newton_rows<Fn, R, TT, SYM0, true>(pd, pd.mesh, k, pd.u + (size_t)k * pd.L * P, pd.b + (size_t)k * pd.L * P, t, (int)k, tt,
+                                                   inv_tau, reinterpret_cast<volatile int*>(sm + ChunkThomas<P, R>::template smem_doubles<TT>()), hp);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < P; ++p) h[r].a[p] = hp[r][p];
+    }
     update_and_test<P, R, TT>(pd, k, t, uc, h, tol, slot, sm);
 }
 
@@ -1010,7 +1184,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr int scratch = 2 * ChunkThomas<P, R>::template exch_doubles<TT>();   // exchange region of finish(), double-buffered
     // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], mass flags kept [4P], instance index [2]
     static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
-                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 2;
+                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 3;   // oK: instance index [2], fallback slot [2 ints]
     static constexpr int bar_doubles = 2 * G + 2;  // mbarriers (8 bytes): S per group (2 reserved) + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
@@ -1211,10 +1385,11 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, us, bs, mass, t, tt, inv_tau, prm, uc, bc, th);
         Vec<P> h[R];
         double* exch = scratch + (it & 1) * (LY::scratch / 2);
+        bool suspect;
         if constexpr (TT == 32) {
             __syncwarp();  // every lane is done with the staged inputs
-            if constexpr (S == 2) th.template finish<TT>(h, exch, t);
-            else th.template finish<TT>(h, exch, t, prefetch);
+            if constexpr (S == 2) suspect = th.template finish<TT>(h, exch, t);
+            else suspect = th.template finish<TT>(h, exch, t, prefetch);
         } else {
             // behind the barrier inside finish(): every thread has consumed the staged inputs (S == 1: refill them) and
             // every warp has parked its partial sum of the previous instance (settle it)
@@ -1222,7 +1397,17 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
                 if constexpr (S == 1) prefetch();
                 if (it > 0) settle_prev(it - 1);
             };
-            th.template finish<TT>(h, exch, t, hook);
+            suspect = th.template finish<TT>(h, exch, t, hook);
+        }
+        if (suspect) {   // pivot growth (same verdict in every thread of the group): solve again with row interchanges
+            const double* bg = pd.b + (size_t)k * L * P;
+            double hp[R][P];
+            pivoted_newton_rows<Fn, R, TT, SYM0, false>(pd, mesh, k, from_b ? bg : pd.u + (size_t)k * L * P, bg, t, blockIdx.x * G + g, tt,
+                                                        inv_tau, reinterpret_cast<volatile int*>(kslot) + 4 + (it & 1), hp);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < P; ++p) h[r].a[p] = hp[r][p];
         }
 
         // update, ||h||^2 of the system

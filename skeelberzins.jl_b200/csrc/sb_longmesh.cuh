@@ -17,6 +17,7 @@
 // one write of u per Newton iteration.  Scalar PDEs (npde = 1) only.
 #pragma once
 #include "sb_kernels.cuh"
+#include "sb_resident.cuh"
 
 namespace sb {
 

@@ -24,6 +24,7 @@ typedef void (*AssembleKernel)(ProbDev, double, double, int);
 typedef void (*FusedKernel)(ProbDev, double, double, double, int);
 typedef void (*FusedPKernel)(ProbDev, double, double, double, int, int, int);
 typedef void (*SolveKernel)(ProbDev, double, int, int);
+typedef void (*ResidentKernel)(ProbDev, ResidentArgs);
 typedef void (*MassKernel)(ProbDev, double, double*, int);
 typedef void (*LongChunkKernel)(ProbDev, double, double, LevelDev);
 typedef void (*LongBackKernel)(ProbDev, double, double, LevelDev, double*);
@@ -36,6 +37,8 @@ struct FunctorEntry {
     FusedKernel fused[kNumDecomp][2];
     FusedPKernel fused_p[kNumDecomp][2];      // persistent TMA-prefetch variant
     size_t fused_p_smem[kNumDecomp][2];       // its dynamic shared memory (bytes)
+    ResidentKernel resident[kNumDecomp][2];   // whole solve in one launch (sb_resident.cuh)
+    size_t resident_smem[kNumDecomp][2];
     MassKernel mass;
     // long-mesh path (scalar PDEs): [SYM0]
     LongChunkKernel long_chunk[2];
@@ -58,10 +61,14 @@ void fill_one(FunctorEntry& e) {
         e.fused_p[D][1] = k_newton_fused_p<Fn, R, TT, true>;
         e.fused_p_smem[D][0] = FusedPLayout<Fn, R, TT, false>::bytes;
         e.fused_p_smem[D][1] = FusedPLayout<Fn, R, TT, true>::bytes;
+        e.resident[D][0] = k_solve_resident<Fn, R, TT, false>;
+        e.resident[D][1] = k_solve_resident<Fn, R, TT, true>;
+        e.resident_smem[D][0] = ResidentLayout<Fn, R, TT, false>::bytes;
+        e.resident_smem[D][1] = ResidentLayout<Fn, R, TT, true>::bytes;
     } else {
         for (int s = 0; s < 2; ++s) {
             e.assemble_jac[D][s] = nullptr; e.assemble_val[D][s] = nullptr; e.fused[D][s] = nullptr;
-            e.fused_p[D][s] = nullptr; e.fused_p_smem[D][s] = 0;
+            e.fused_p[D][s] = nullptr; e.fused_p_smem[D][s] = 0; e.resident[D][s] = nullptr; e.resident_smem[D][s] = 0;
         }
     }
 }
@@ -102,7 +109,8 @@ inline size_t solve_smem_bytes(int P, int d) {
     const int TT = kDecomp[d].TT;
     if (TT == 32) return 0;
     return (P == 1 ? ChunkThomas<1, 1>::template smem_doubles<256>() * (size_t)TT / 256
-                   : ChunkThomas<2, 1>::template smem_doubles<256>() * (size_t)TT / 256) * sizeof(double);   // same for every R; linear in TT
+                   : ChunkThomas<2, 1>::template smem_doubles<256>() * (size_t)TT / 256) * sizeof(double)   // same for every R; linear in TT
+           + sizeof(double);                                                                                 // + the fallback's slot word
 }
 
 // defined in the per-functor translation units

@@ -52,7 +52,7 @@ static void run(int N, int flavour) {
         }
     for (int i = 0; i < n; ++i) b[i] = urand();
     std::vector<double> x = b, xd;
-    const int info = banded_lu_solve<BandShape<P>::kl, BandShape<P>::ku>(ab.data(), n, x.data());
+    const int info = banded_lu_solve<BandShape<P>::kl, BandShape<P>::ku, double*>(ab.data(), n, x.data());
     dense_solve(A, b, n, xd);
     double res = 0.0, scale = 0.0, err = 0.0, xs = 0.0;
     for (int i = 0; i < n; ++i) {

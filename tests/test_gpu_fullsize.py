@@ -129,7 +129,8 @@ def test_full_size_every_instance_against_the_oracle(ctx, oracle, cfg):
     assert (r["status"] == 0).all()
     assert r["iters"].max() <= hist_cap
 
-    # host-owned loops (src/pdepe.jl:90-108, src/utils.jl:311-336): per-step iteration counts of every instance
+    # host-owned loops (src/pdepe.jl:90-108, src/utils.jl:311-336; one C call per Newton iteration): per-step iteration
+    # counts of every instance from the device counters
     fn = sb.Functor(c.functor, c.params)
     dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn)
     try:
@@ -139,18 +140,20 @@ def test_full_size_every_instance_against_the_oracle(ctx, oracle, cfg):
         for i in range(nsteps):
             tau_i = tau if tau is not None else tg[i + 1] - tg[i]
             dev.begin_step(tg[i + 1], 1.0 / tau_i)
-            dev.newton_solve(tol, maxit)
+            sb.api._newton_loop(dev, tol, maxit)
             it_gpu[:, i] = dev.step_iters()
         u = dev.download().copy()
         assert (dev.status() == 0).all()
         tot = dev.total_iters()
-        # the C time loop with device-side stepping (what bench.py times) must do exactly the same work
+        # the whole solve in one launch (what bench.py times) must do exactly the same work, instance by instance
         dev.upload(c.initial())
         dev.mass_flags(tg[0])
-        dev.solve_steps(tg, tau, tol, maxit)
+        it_one = dev.solve_steps_opt(tg, tau, tol, maxit, step_iters=True)
         u2 = dev.download().copy()
         assert np.array_equal(u, u2)
+        assert np.array_equal(it_one, it_gpu)
         assert np.array_equal(dev.total_iters(), tot)
+        assert (dev.status() == 0).all()
     finally:
         dev.close()
 

@@ -24,12 +24,12 @@ from skeelberzins_jl_b200 import examples as ex                     # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="2")
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=0, help="0: 1 for the resident design, 2 otherwise")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--time-steps", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--tag", default="")
-    ap.add_argument("--design", default="fused_tma")
+    ap.add_argument("--design", default="resident")
     ap.add_argument("--check", action="store_true", help="compare a sample of instances with the CPU oracle")
     a = ap.parse_args()
     c = ex.baseline_case(a.config, B=a.batch or None)
@@ -42,7 +42,7 @@ def main():
         if a.time_steps:
             tg = tg[:a.time_steps + 1]
     tol, maxit = 1e-10, 100
-    n_str = 1 if stationary else max(1, a.streams)
+    n_str = 1 if stationary else (a.streams or (1 if a.design == "resident" else 2))
     ctxs = [sb.Context(0) for _ in range(n_str)]
     bounds = [int(round(i * B / n_str)) for i in range(n_str + 1)]
     u0 = c.initial()
@@ -110,10 +110,13 @@ def main():
     d.rollback()
     d.mass_flags(tg[0], stationary=stationary)
     d.profile_begin()
-    for i in range(tg.size - 1):
-        tau_i = tau if tau is not None else tg[i + 1] - tg[i]
-        d.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
-        d.newton_solve(tol, maxit)
+    if a.design == "resident" and not stationary:
+        d.solve_steps(tg, tau, tol, maxit)
+    else:
+        for i in range(tg.size - 1):
+            tau_i = tau if tau is not None else tg[i + 1] - tg[i]
+            d.begin_step(tg[i + 1], 0.0 if np.isinf(tau_i) else 1.0 / tau_i)
+            d.newton_solve(tol, maxit)
     prof = d.profile_end()
     nl = max(prof["launches"], 1)
     us = 1e3 * (prof["ms_solve"] + prof["ms_assemble"]) / nl
