@@ -5,7 +5,10 @@
 # (src/utils.jl:311-336) exactly as the reference does and calls one C entry point per Newton iteration; all the
 # arithmetic runs in hand-written sm_100a CUDA kernels.  No CUDA.jl, no CPU fallback.
 #
-# NOTE: `julia` is not installed in the build image, so this file has never been executed there; the Python host
+# STATUS: EXPERIMENTAL, NEVER EXECUTED.  `julia` is not installed in the build image or on the GPU box, so nothing in
+# this file has run.  What is checked (tests/test_c_abi.py): every ccall names an exported symbol and passes the number
+# and kind of arguments the header declares.  What is NOT checked: array layouts as Julia sees them (column-major views
+# of the C arrays), finalizers calling CUDA from the GC thread, keyword merging.  The Python host
 # (skeelberzins.jl_b200/api.py) drives the identical sequence of C calls and is what the tests and the bench run.
 #
 # pdefun / bdfun must be registry functors (device-compiled restatements of the example callbacks, see
@@ -13,14 +16,15 @@
 # as in the reference (src/utils.jl:629-632).
 module SkeelBerzinsB200
 
-export pdepe, Params, ProblemDefinition, SkeelBerzinsDiscretization, Functor, assemble!, mass_matrix
+export pdepe, Params, ProblemDefinition, SkeelBerzinsDiscretization, Functor, assemble!, mass_matrix, DiffEqArray,
+       interpolate_sol_time, interpolate_sol_space, pdeval, ode_operator
 
 const libsb = get(ENV, "SKEELBERZINS_B200_LIB", "libskeelberzins_b200.so")
 
 # registry ids (enum sb_functor_id)
 const LIN_DIFF, NONLIN_DIFF, LIN_DIFF_CYL, POISSON, STAT_NONLIN, REACT_DIFF = 0, 1, 2, 3, 4, 5
 const LIN_DIFF_SPH, CONV_DIFF, LIN_REACT, GENERIC_SCALAR = 6, 7, 8, 9
-const DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA = 0, 1, 2
+const DESIGN_SPLIT, DESIGN_FUSED, DESIGN_FUSED_TMA, DESIGN_RESIDENT = 0, 1, 2, 3
 
 struct SBError <: Exception
     code::Cint
@@ -91,7 +95,7 @@ end
 const SkeelBerzinsDiscretization = ProblemDefinition
 Base.length(pb::ProblemDefinition) = pb.nb_design_var          # src/utils.jl:665
 
-function problem_init(m, xmesh, tspan, pdefun::Functor, icfun, bdfun, params; ctx = Context(0), design = DESIGN_FUSED_TMA)
+function problem_init(m, xmesh, tspan, pdefun::Functor, icfun, bdfun, params; ctx = Context(0), design = DESIGN_RESIDENT)
     x = collect(Float64, xmesh)
     Nx = length(x); B = batch(pdefun)
     npde, nprm, _ = functor_info(pdefun.id)
@@ -184,11 +188,61 @@ function register_user_functor(cuda_source::AbstractString, struct_name::Abstrac
     Int(id[])
 end
 
+"""Result of the transient solve with the two fields the reference's `RecursiveArrayTools.DiffEqArray` result is used
+through (src/pdepe.jl:110): `sol.u[k]` = states `[npde*Nx, B]` at `sol.t[k]`; `sol(t)` interpolates in time
+(src/utils.jl:597), `sol(x_eval, t, pb)` in time and space (src/utils.jl:561)."""
+struct DiffEqArray
+    u::Vector{Matrix{Float64}}
+    t::Vector{Float64}
+end
+Base.length(s::DiffEqArray) = length(s.u)
+Base.getindex(s::DiffEqArray, i) = s.u[i]
+Base.lastindex(s::DiffEqArray) = lastindex(s.u)
+(s::DiffEqArray)(t::Real) = interpolate_sol_time(s, t)
+(s::DiffEqArray)(x_eval, t, pb::ProblemDefinition; val = true, deriv = true) = interpolate_sol_space(s, x_eval, t, pb; val = val, deriv = deriv)
+
+"""interpolate_sol_time(u_approx, t) (src/utils.jl:575-595): linear interpolation between stored time steps."""
+function interpolate_sol_time(u_approx::DiffEqArray, t)
+    ts = u_approx.t
+    (t == ts[1] || abs(t - ts[1]) ≤ 1.0e-10 * abs(ts[2] - ts[1])) && return u_approx.u[1]
+    idx = searchsortedfirst(ts, t)
+    (idx == 1 || idx > length(u_approx)) && error("The chosen time is not within the interval.")
+    dt = ts[idx] - ts[idx - 1]
+    ((ts[idx] - t) / dt) .* u_approx.u[idx - 1] .+ ((t - ts[idx - 1]) / dt) .* u_approx.u[idx]
+end
+
+"""interpolate_sol_space(u_approx, x_eval, times, pb; val, deriv) (src/utils.jl:460-559), evaluated on the GPU."""
+function interpolate_sol_space(u_approx::DiffEqArray, x_eval, times, pb::ProblemDefinition; val = true, deriv = true)
+    res = [pdeval(pb.m, pb.xmesh, interpolate_sol_time(u_approx, t), x_eval, pb) for t in (times isa Number ? [times] : times)]
+    us = [r[1] for r in res]; dus = [r[2] for r in res]
+    times isa Number && ((us, dus) = (us[1], dus[1]))
+    val && !deriv && return us
+    deriv && !val && return dus
+    us, dus
+end
+
+"""assemble! on DEVICE memory (sb_assemble_device): `d_u`, `d_du` are device pointers (e.g. `pointer(::CuArray)` reinterpreted
+to `Ptr{Float64}`) to `[npde*Nx, B]` arrays; asynchronous on the context's stream."""
+function assemble_device!(d_du::Ptr{Float64}, d_u::Ptr{Float64}, pb::ProblemDefinition, t)
+    check(ccall((:sb_assemble_device, libsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cdouble, Ptr{Float64}), pb.handle, d_u, t, d_du))
+    d_du
+end
+
+"""DiffEq-facing operator (src/diffEq.jl:18-43): `(f!, M, tspan)` with `f!(du, u, p, t) = assemble!(du, u, pb, t)` on the
+GPU and `M` the diagonal of the mass matrix (`nothing` for a pure ODE system); pass them on as
+`ODEFunction(f!; mass_matrix = Diagonal(vec(M)))` / `ODEProblem(..., vec(pb.inival), tspan)`."""
+function ode_operator(pb::ProblemDefinition)
+    M, flag_dae = mass_matrix(pb)
+    f!(du, u, p, t) = assemble!(du, u, pb, t)
+    f!, (flag_dae ? M : nothing), pb.tspan
+end
+
 _merge(params, kwargs) = Params(; (f => get(kwargs, f, getfield(params, f)) for f in fieldnames(Params))...)
 
-"""Transient pdepe (src/pdepe.jl:42-128) for the batch.  Returns `(u = Vector of [npde*Nx, B] states, t = grid)`
-and, as in the reference, `pb` / `storage` when `data` / `hist` are set."""
-function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params(), ctx = Context(0), kwargs...)
+"""Transient pdepe (src/pdepe.jl:42-128) for the batch.  Returns a `DiffEqArray` (`sol.u[k]` = `[npde*Nx, B]` states at
+`sol.t[k]`, `sol(t)`, `sol(x_eval, t, pb)`) and, as in the reference, `pb` / `storage` when `data` / `hist` are set.
+`c_loop = true` hands the time loop and the Newton loop to C (one kernel launch for the whole solve)."""
+function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params(), ctx = Context(0), c_loop = false, kwargs...)
     params = _merge(params, kwargs)
     @assert m == 0 || m == 1 || m == 2 "Parameter m invalid"
     @assert m == 0 || m > 0 && xmesh[1] ≥ 0 "Non-conforming mesh"
@@ -201,6 +255,21 @@ function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params()
                                     (params.tstep, diff(params.tstep))          # src/pdepe.jl:82-85
     upload!(pb, inival)
     check(ccall((:sb_mass_flags, libsb), Cint, (Ptr{Cvoid}, Cdouble, Cint), pb.handle, timeSteps[1], 0))
+    if c_loop && !params.hist
+        # the time loop and the Newton loop in C: with the resident design the whole solve is one kernel launch
+        # (sb_solve_steps_opt) that also writes every state, streamed out while later instances compute
+        nsteps = length(timeSteps) - 1
+        snaps = Array{Float64, 3}(undef, npde * Nx, batch(pdefun), nsteps + 1)      # C layout [nsteps+1][B][Nx][npde]
+        done = Ref{Cint}(0)
+        rc = ccall((:sb_solve_steps_opt, libsb), Cint,
+                   (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Ptr{Int32}, Ptr{Float64}, Ref{Cint}),
+                   pb.handle, nsteps, collect(Float64, timeSteps), C_NULL, flag_tstep ? Float64(tstep) : -1.0, params.tol,
+                   params.maxit, C_NULL, snaps, done)
+        rc == -4 && throw("convergence failed")                                       # src/utils.jl:336
+        check(rc)
+        sol = DiffEqArray([snaps[:, :, k] for k in 1:(nsteps + 1)], collect(Float64, timeSteps))
+        return params.data ? (sol, pb) : sol
+    end
     results = [copy(inival)]
     storage = []
     for i in eachindex(timeSteps[1:(end - 1)])                                     # src/pdepe.jl:90
@@ -208,7 +277,7 @@ function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params()
         params.hist && push!(storage, history(pb, params.maxit))
         push!(results, download(pb))
     end
-    sol = (u = results, t = timeSteps)
+    sol = DiffEqArray(results, collect(Float64, timeSteps))                        # src/pdepe.jl:110
     params.hist && params.data && return sol, pb, storage
     params.hist && return sol, storage
     params.data && return sol, pb

@@ -1184,7 +1184,8 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr int scratch = 2 * ChunkThomas<P, R>::template exch_doubles<TT>();   // exchange region of finish(), double-buffered
     // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], mass flags kept [4P], instance index [2]
     static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
-                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 3;   // oK: instance index [2], fallback slot [2 ints]
+                         oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 4;   // oK: instance index [2], fallback slot [2 ints], pad
+    static_assert(group_doubles % 2 == 0 && oB % 2 == 0 && oPrm % 2 == 0 && oMass % 2 == 0, "bulk copies need 16-byte aligned destinations");
     static constexpr int bar_doubles = 2 * G + 2;  // mbarriers (8 bytes): S per group (2 reserved) + one for the mesh weights
     static constexpr size_t bytes = sizeof(double) * (size_t)(bar_doubles + mesh_doubles + G * group_doubles);
 };
