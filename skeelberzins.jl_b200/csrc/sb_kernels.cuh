@@ -218,10 +218,10 @@ struct ChunkThomas {
     }
 
     // shared memory of finish<TT>() in doubles: the exchange region (two equations per warp) ...
-#ifdef SB_FINISH_SERIAL   // tuning builds: the round-1 second level (warp 0 solves the separators alone), for A/B runs
-    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT; }
-#else
+#ifdef SB_FINISH_PARALLEL   // tuning builds: every warp reduces its own separators (see finish_parallel)
     template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + 1) * (TT / 32); }
+#else                       // default: warp 0 solves the TT separators (finish_serial): first rows | reduced rows | unknowns | monitor words
+    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT + TT / 32 + 1; }
 #endif
     // ... followed by one partial sum per warp for system_sum()
     template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : exch_doubles<TT>() + TT / 32; }
@@ -284,86 +284,116 @@ struct ChunkThomas {
     SB_D bool finish(Vec<P> (&x)[R], double* sm, int t) { return finish<TT>(x, sm, t, NoHook()); }
 
     // Solve.  x[r] = unknowns of the thread's rows, t = thread index inside the system, sm = exch_doubles<TT>() doubles.
+    // hook(): called by every thread right after the first synchronisation point (TT == 32: after the first shuffle),
+    // when all threads of the system have finished reading their inputs, e.g. to start the prefetch of the next instance.
+    // Returns true (the same value in every thread of the system) when the pivot-growth monitor tripped anywhere in
+    // the system: x is then not to be trusted and the caller solves the instance again with row interchanges.
     //
-    // Three levels, every warp busy at every level and ONE CTA barrier:
-    //  1. thread: the R-1 interior rows were eliminated against the separator by row(); to_explicit() turns the
-    //     factors into x_r = y_r - v_r*x_prevsep - w_r*x_sep.
-    //  2. warp: the 32 separators of a warp form a tridiagonal system whose two outer couplings reach into the
+    // Level 1 (thread): the R-1 interior rows were eliminated against the separator by row(); to_explicit() turns the
+    // factors into x_r = y_r - v_r*x_prevsep - w_r*x_sep.  The TT separators form a reduced block-tridiagonal system.
+    // TT == 32: parallel cyclic reduction with shuffles (finish_parallel).  TT > 32, two variants, both measured:
+    //  * finish_serial (default): the reduced rows go to shared memory and warp 0 solves them alone -- TT/32 rows per
+    //    lane by the same partition, then the 32-row shuffle PCR -- while the other warps wait at a barrier.  Fewest
+    //    instructions (739 per warp and system at (8,128)); the idle warps' issue slots go to the other CTAs of the SM.
+    //  * finish_parallel (-DSB_FINISH_PARALLEL): every warp runs the shuffle PCR on its own 32 separators with the
+    //    couplings to the neighbouring warps carried along as spikes, then one exchange of two equations per warp and
+    //    a redundant elimination through the TT/32 warps: one barrier instead of three, no idle warp, but 914
+    //    instructions.  Per-iteration launches (k_newton_fused_p): same speed (35.5 vs 35.1 us per cfg2 launch, barrier
+    //    stall 1.4 vs 3.7 per issue).  Whole-solve kernel: 13.5 ms vs 11.8 ms per cfg2 solve -- instructions win.
+    template <int TT, class Hook>
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+#ifndef SB_FINISH_PARALLEL
+        if constexpr (TT > 32) return finish_serial<TT>(x, sm, t, hook);
+        else
+#endif
+        return finish_parallel<TT>(x, sm, t, hook);
+    }
+
+    template <int TT, class Hook>
+    SB_D bool finish_serial(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+        constexpr int W = TT / 32;
+        Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
+        if constexpr (R == 1) summary(y0, v0, w0, yL, vL, wL);
+        else { to_explicit(); y0 = dt[0]; v0 = vt[0]; w0 = ct[0]; yL = dt[R - 2]; vL = vt[R - 2]; wL = ct[R - 2]; }
+        double mine[NW], nb[NW];
+        pack(mine, v0, w0, y0);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
+        __syncthreads();
+        hook();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
+        Mat<P> v0n, w0n; Vec<P> y0n;
+        unpack(nb, v0n, w0n, y0n);
+        Mat<P> an, cn; Vec<P> dn;
+        reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
+        watch(an); watch(cn);
+        constexpr int Q = TT / 32;  // reduced rows per lane of warp 0
+        double* red = sm + NW * TT;
+        double* xsm = sm + 2 * NW * TT;
+        unsigned* monw = reinterpret_cast<unsigned*>(sm + (2 * NW + P) * TT);   // [W] per-warp monitors, [2W] the verdict
+        pack(mine, an, cn, dn);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) red[w * TT + t] = mine[w];
+#ifndef SB_NO_PIVOT_MONITOR
+        {
+            const unsigned g = __reduce_max_sync(0xffffffffu, mon);
+            if ((t & 31) == 0) monw[t >> 5] = g;
+        }
+#endif
+        __syncthreads();
+        if (t < 32) {
+            ChunkThomas<P, Q> lvl2;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                double rw[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + t * Q + q];
+                Mat<P> a, c; Vec<P> d;
+                unpack(rw, a, c, d);
+                lvl2.row(q, a, mat_identity<P>(), c, d);
+            }
+            Vec<P> y[Q];
+            const bool bad2 = lvl2.template finish_parallel<32>(y, nullptr, t, NoHook());
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int i = 0; i < P; ++i) xsm[i * TT + t * Q + q] = y[q].a[i];
+            if (t == 0) {
+                unsigned g = bad2 ? 0x7ff00000u : 0u;
+#pragma unroll
+                for (int w = 0; w < W; ++w) g = max(g, monw[w]);
+                monw[2 * W] = g;
+            }
+        }
+        __syncthreads();
+        Vec<P> xs, xp;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            xs.a[i] = xsm[i * TT + t];
+            xp.a[i] = (t > 0) ? xsm[i * TT + t - 1] : 0.0;
+        }
+        if constexpr (R == 1) x[0] = xs;
+        else explicit_rows(x, xp, xs);
+#ifndef SB_NO_PIVOT_MONITOR
+        return monw[2 * W] > kGrowthHi;
+#else
+        return false;
+#endif
+    }
+
+    // The all-warps variant (and the solver of one warp's worth of rows: TT == 32, and level 2 of finish_serial):
+    //  warp: the 32 separators of a warp form a tridiagonal system whose two outer couplings reach into the
     //     neighbouring warps: lane 0 to X_prev (the previous warp's last separator), lane 31 to X_next (the FIRST
     //     ROW of the next warp's first chunk, kept as an unknown instead of being eliminated, so nothing has to cross
     //     the warp boundary beforehand).  Parallel cyclic reduction with shuffles; an elimination step that would
     //     reach outside the warp is skipped, which leaves the coefficient of X_prev / X_next in the a / c slot
     //     ("spikes" at no cost).  After 5 steps  x_sep(lane) = d - a*X_prev - c*X_next.
-    //  3. CTA: per warp two equations in (X_prev, own first row F, own last separator L, X_next) go to shared memory;
+    //  CTA: per warp two equations in (X_prev, own first row F, own last separator L, X_next) go to shared memory;
     //     after the barrier every thread eliminates through the TT/32 warps (a few dozen flops) and keeps the two
     //     values its own warp needs.
-    // hook(): called by every thread right after the barrier (TT == 32: after the first shuffle), when all threads
-    // of the system have finished reading their inputs, e.g. to start the prefetch of the next instance.
-    // Returns true (the same value in every thread of the system) when the pivot-growth monitor tripped anywhere in
-    // the system: x is then not to be trusted and the caller solves the instance again with row interchanges.
-#ifdef SB_FINISH_SERIAL
-    template <int TT, class Hook>
-    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
-        if constexpr (TT == 32) return finish_parallel<TT>(x, sm, t, hook);
-        else {
-            Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
-            if constexpr (R == 1) summary(y0, v0, w0, yL, vL, wL);
-            else { to_explicit(); y0 = dt[0]; v0 = vt[0]; w0 = ct[0]; yL = dt[R - 2]; vL = vt[R - 2]; wL = ct[R - 2]; }
-            double mine[NW], nb[NW];
-            pack(mine, v0, w0, y0);
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
-            __syncthreads();
-            hook();
-#pragma unroll
-            for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
-            Mat<P> v0n, w0n; Vec<P> y0n;
-            unpack(nb, v0n, w0n, y0n);
-            Mat<P> an, cn; Vec<P> dn;
-            reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
-            constexpr int Q = TT / 32;  // reduced rows per lane of warp 0
-            double* red = sm + NW * TT;
-            double* xsm = sm + 2 * NW * TT;
-            pack(mine, an, cn, dn);
-#pragma unroll
-            for (int w = 0; w < NW; ++w) red[w * TT + t] = mine[w];
-            __syncthreads();
-            if (t < 32) {
-                ChunkThomas<P, Q> lvl2;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    double rw[NW];
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + t * Q + q];
-                    Mat<P> a, c; Vec<P> d;
-                    unpack(rw, a, c, d);
-                    lvl2.row(q, a, mat_identity<P>(), c, d);
-                }
-                Vec<P> y[Q];
-                lvl2.template finish_parallel<32>(y, nullptr, t, NoHook());
-#pragma unroll
-                for (int q = 0; q < Q; ++q)
-#pragma unroll
-                    for (int i = 0; i < P; ++i) xsm[i * TT + t * Q + q] = y[q].a[i];
-            }
-            __syncthreads();
-            Vec<P> xs, xp;
-#pragma unroll
-            for (int i = 0; i < P; ++i) {
-                xs.a[i] = xsm[i * TT + t];
-                xp.a[i] = (t > 0) ? xsm[i * TT + t - 1] : 0.0;
-            }
-            if constexpr (R == 1) x[0] = xs;
-            else explicit_rows(x, xp, xs);
-            return false;
-        }
-    }
     template <int TT, class Hook>
     SB_D bool finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
-#else
-    template <int TT, class Hook>
-    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
-#endif
         constexpr int W = TT / 32;
         const int lane = t & 31;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
@@ -720,6 +750,7 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
         boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
     }
 
+    const bool tail = i0 + R - 1 >= Nx - 1;   // this thread owns the last mesh node or padding
     double un[P];  // first node of the next chunk
     IntervalRes<P, ND> Lr, Rr;
     if (i0 >= 1 && i0 - 1 <= Nx - 2) {
@@ -797,11 +828,15 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
             for (int p = 0; p < P; ++p) b0[p] = JAC ? bc[0][p] : 0.0;
             boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
         }
-        if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
-            if (i == Nx - 1) row = rowN;
-            else {
-                row.A = mat_zero<P>(); row.C = mat_zero<P>(); row.d = vec_zero<P>();
-                row.Bm = JAC ? mat_identity<P>() : mat_zero<P>();
+        if (tail) {  // the thread(s) at the end of the mesh only.  The empty asm keeps this a real branch: predicated
+                     // into selects it would cost every row of every thread 16 instructions, as a branch it costs two
+            asm volatile("");
+            if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
+                if (i == Nx - 1) row = rowN;
+                else {
+                    row.A = mat_zero<P>(); row.C = mat_zero<P>(); row.d = vec_zero<P>();
+                    row.Bm = JAC ? mat_identity<P>() : mat_zero<P>();
+                }
             }
         }
         if constexpr (JAC) sink.row(r, row.A, row.Bm, row.C, row.d);
@@ -941,15 +976,17 @@ struct BandSink {   // row sink of assemble_chunk: block rows into LAPACK band s
 
 // band complete -> solve (thread 0) -> h of this thread's rows; releases the slot
 template <int P, int R, int TT>
-SB_D void piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P]) {
+SB_D bool piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P]) {
     double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
     double* rhs = ab + (size_t)pd.Nx * P * BandShape<P>::ldab;
     group_sync<TT>();
     if (t == 0) {
         const int info = banded_lu_solve<BandShape<P>::kl, BandShape<P>::ku, volatile double*>(ab, pd.Nx * P, rhs);
-        pd.status[k] = info ? 2 : 3;
+        if (info) rhs[0] = __longlong_as_double(0x7ff8000000000000LL);   // singular even with pivoting: a NaN everybody sees
+        if (info || pd.status[k] != 2) pd.status[k] = info ? 2 : 3;
     }
     group_sync<TT>();
+    const bool singular = !(__ldcg(rhs) == __ldcg(rhs));
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -959,12 +996,13 @@ SB_D void piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P
         }
     group_sync<TT>();
     if (t == 0) piv_release(pd, s);
+    return singular;
 }
 
 // the whole fallback for the fused kernels: assemble the rows again (from global memory: the staged copies may have
 // been refilled already), this time into the band.  Not inlined: a cold path with its own register allocation.
 template <class Fn, int R, int TT, bool SYM0, bool GLOB>
-__device__ __noinline__ void pivoted_newton_rows(ProbDev pd, MeshDev mesh, long long k, const double* ub, const double* bb,
+__device__ __noinline__ bool pivoted_newton_rows(ProbDev pd, MeshDev mesh, long long k, const double* ub, const double* bb,
                                                  int t, int group, double tt, double inv_tau, volatile int* sh_slot,
                                                  double (&h)[R][Fn::npde]) {
     constexpr int P = Fn::npde;
@@ -976,7 +1014,7 @@ __device__ __noinline__ void pivoted_newton_rows(ProbDev pd, MeshDev mesh, long 
     BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
     assemble_chunk<Fn, R, TT, SYM0, true, GLOB>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
                                                pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink);
-    piv_solve<P, R, TT>(pd, k, t, s, h);
+    return piv_solve<P, R, TT>(pd, k, t, s, h);
 }
 
 // ---------------------------------------------------------------------------------------------

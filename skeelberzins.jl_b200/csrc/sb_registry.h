@@ -108,9 +108,13 @@ void fill_solve(SolveKernel (&tab)[kNumDecomp], std::integer_sequence<int, D...>
 inline size_t solve_smem_bytes(int P, int d) {
     const int TT = kDecomp[d].TT;
     if (TT == 32) return 0;
-    return (P == 1 ? ChunkThomas<1, 1>::template smem_doubles<256>() * (size_t)TT / 256
-                   : ChunkThomas<2, 1>::template smem_doubles<256>() * (size_t)TT / 256) * sizeof(double)   // same for every R; linear in TT
-           + sizeof(double);                                                                                 // + the fallback's slot word
+    const int NW = 2 * P * P + P, W = TT / 32;
+#ifdef SB_FINISH_PARALLEL
+    const int exch = (2 * NW + 1) * W;
+#else
+    const int exch = (2 * NW + P) * TT + W + 1;
+#endif
+    return (size_t)(exch + W /* partial sums */ + 1 /* the fallback's slot word */) * sizeof(double);   // ChunkThomas::smem_doubles<TT>() + 1
 }
 
 // defined in the per-functor translation units

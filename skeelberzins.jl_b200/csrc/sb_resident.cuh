@@ -156,7 +156,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                     }
                     nm = ::sqrt(ss);
                     if (t == 0 && pd.hist && it - 1 < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it - 1] = nm;
-                    if (!(nm == nm) || nm > 1.0e300) { status = 2; break; }
+                    if (!(nm == nm) || nm > 1.0e300) status = 2;                       // goes on to maxit like the reference
                     if (nm < ra.tol) { conv = true; break; }                                 // src/utils.jl:329-333
                     if (it >= ra.maxit) break;                                          // src/utils.jl:336
                 }
@@ -171,12 +171,13 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 const bool suspect = th.template finish<TT>(h, scratch + (it & 1) * LY::exch, t);   // (B) inside
                 if (suspect) {          // pivot growth: the same rows into a band, solved with row interchanges
                     double hp[R][P];
-                    pivoted_newton_rows<Fn, R, TT, SYM0, false>(pd, mesh, k, utile, btile, t, blockIdx.x * G + g, tt, inv_tau, sh_slot, hp);
+                    const bool singular = pivoted_newton_rows<Fn, R, TT, SYM0, false>(pd, mesh, k, utile, btile, t, blockIdx.x * G + g, tt,
+                                                                                      inv_tau, sh_slot, hp);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
                         for (int p = 0; p < P; ++p) h[r].a[p] = hp[r][p];
-                    status = 3;
+                    if (status != 2) status = singular ? 2 : 3;
                 }
                 // ---- u -= h (src/utils.jl:321); every thread is past its reads of the old iterate (barrier B) ----
                 ss = 0.0;

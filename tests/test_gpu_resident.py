@@ -133,19 +133,22 @@ def _zero_diagonal_case(B, Nx):
 
 
 @pytest.mark.parametrize("design", ["resident", "fused_tma", "fused", "split"])
-@pytest.mark.parametrize("Nx", [64, 200, 1024])
-def test_pivoted_fallback_on_a_zero_diagonal(ctx, oracle, design, Nx):
+@pytest.mark.parametrize("Nx,tol", [(64, 1e-10), (200, 1e-10), (1024, 1e-7), (2048, 1e-6)])
+def test_pivoted_fallback_on_a_zero_diagonal(ctx, oracle, design, Nx, tol):
+    """Warp-per-system (Nx <= 256) and CTA-per-system decompositions.  The matrix has condition number ~ Nx and the
+    solution grows with Nx, so the rounding floor of ||h||_2 reaches 1e-10 near Nx = 1000: the long meshes use a
+    tolerance above it (the same for the oracle)."""
     B = 6
     x, tau, prm, u0 = _zero_diagonal_case(B, Nx)
     tg = np.array([0.0, tau, 2 * tau, 3 * tau])
     fn = sb.Functor(ex.GENERIC_SCALAR, prm)
     for c_loop in (False, True):
         sol, dev = sb.pdepe(0, fn, u0, fn, x, (tg[0], tg[-1]), ctx=ctx, tstep=tg, squeeze=False, save="last", design=design,
-                            c_loop=c_loop, return_device=True)
+                            c_loop=c_loop, return_device=True, tol=tol)
         try:
-            r = oracle.pdepe_transient(ex.GENERIC_SCALAR, 0, x, prm, u0, tg, None)
+            r = oracle.pdepe_transient(ex.GENERIC_SCALAR, 0, x, prm, u0, tg, None, tol=tol)
             assert (r["status"] == 0).all()
-            assert _relerr(np.asarray(sol.u[-1]), r["u"][:, :, 0]) < 1e-9     # cond(J) ~ Nx^2 here
+            assert _relerr(np.asarray(sol.u[-1]), r["u"][:, :, 0]) < 1e-9 * max(1.0, Nx / 200)   # cond(J) ~ Nx here
             assert np.array_equal(dev.total_iters(), r["iters"].sum(axis=1))
             assert (dev.status() == 3).all()               # solved, by the pivoted fallback
         finally:
@@ -185,7 +188,9 @@ def test_block_tridiagonal_solve_without_dominance(ctx, oracle, P, Nx):
     # and against the oracle's pivoted LU where the system is not hopelessly conditioned
     err = np.abs(xg - xo).reshape(B, -1).max(axis=1) / np.abs(xo).reshape(B, -1).max(axis=1)
     assert np.median(err) < 1e-8
-    assert (st[B // 2:] == 3).all()                        # zeros on the diagonal: cannot pass without interchanges
+    if P == 1:
+        assert (st[B // 2:] == 3).all()                    # zeros on the diagonal: cannot pass without interchanges
+    # (P = 2: the pivoting INSIDE the 2x2 blocks already copes with a zero diagonal entry)
 
 
 def test_convection_dominated_problem(ctx, oracle):
