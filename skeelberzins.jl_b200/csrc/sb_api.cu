@@ -636,7 +636,7 @@ int longmesh_setup(sb_problem* pb) {
 
 template <int RT>
 void launch_top(sb_problem* pb, const LevelDev& top, const LevelDev& below) {
-    const size_t smem = (size_t)(2 * 3 + 1) * kLongTT * sizeof(double);
+    const size_t smem = (size_t)ChunkThomas<1, RT>::template smem_doubles<kLongTT>() * sizeof(double);
     launch_pdl((const void*)k6_top<RT, kLongTT>, dim3((unsigned)pb->pd.B), dim3(kLongTT), smem, pb->ctx->stream, top, below,
                (const int*)pb->d_active);
 }

@@ -750,7 +750,6 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
         boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
     }
 
-    const bool tail = i0 + R - 1 >= Nx - 1;   // this thread owns the last mesh node or padding
     double un[P];  // first node of the next chunk
     IntervalRes<P, ND> Lr, Rr;
     if (i0 >= 1 && i0 - 1 <= Nx - 2) {
@@ -828,15 +827,11 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
             for (int p = 0; p < P; ++p) b0[p] = JAC ? bc[0][p] : 0.0;
             boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
         }
-        if (tail) {  // the thread(s) at the end of the mesh only.  The empty asm keeps this a real branch: predicated
-                     // into selects it would cost every row of every thread 16 instructions, as a branch it costs two
-            asm volatile("");
-            if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
-                if (i == Nx - 1) row = rowN;
-                else {
-                    row.A = mat_zero<P>(); row.C = mat_zero<P>(); row.d = vec_zero<P>();
-                    row.Bm = JAC ? mat_identity<P>() : mat_zero<P>();
-                }
+        if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
+            if (i == Nx - 1) row = rowN;
+            else {
+                row.A = mat_zero<P>(); row.C = mat_zero<P>(); row.d = vec_zero<P>();
+                row.Bm = JAC ? mat_identity<P>() : mat_zero<P>();
             }
         }
         if constexpr (JAC) sink.row(r, row.A, row.Bm, row.C, row.d);
