@@ -494,6 +494,7 @@ def run_ours(args):
         barrier()
         s0.record(stream)
         for _ in range(n_sa):
+            sol_all = None                                     # hand the pinned snapshot buffer back before asking for it again
             sol_all = solve_all()
         s1.record(stream)
         barrier()

@@ -81,7 +81,9 @@ enum sb_functor_id {
     SB_USER_FUNCTOR_BASE = 1000
 };
 
-#define SB_MAX_NPDE 2
+/* registry functors have npde <= 2; user functors (plugin slot) up to 4: npde = 3 on meshes up to 1024 nodes, npde = 4 up
+ * to 512 (the factors of a block row are 2*npde^2 + npde doubles per thread: rows per thread 16 / 8 / 4 / 2 for npde 1..4) */
+#define SB_MAX_NPDE 4
 #define SB_GENERIC_SCALAR_NPARAMS 19
 
 typedef struct sb_ctx sb_ctx;

@@ -59,10 +59,12 @@ enum {
     LIN_DIFF = 0, NONLIN_DIFF = 1, LIN_DIFF_CYL = 2, POISSON = 3, STAT_NONLIN = 4, REACT_DIFF = 5,
     LIN_DIFF_SPH = 6, CONV_DIFF = 7, LIN_REACT = 8, GENERIC_SCALAR = 9,
     EXP_DIFF = 10,  // not in the product registry: checker for run-time compiled user functors (tests/test_gpu_plugin.py)
-    NUM_FUNCTORS = 11
+    CHAIN3 = 11,    // likewise: three species, A -> B -> C with a quadratic first step (npde = 3)
+    CHAIN4 = 12,    // four species, A -> B -> C -> D, second species with a u-dependent capacity (npde = 4)
+    NUM_FUNCTORS = 13
 };
-static const int k_npde[NUM_FUNCTORS] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1};
-static const int k_nprm[NUM_FUNCTORS] = {1, 1, 3, 3, 3, 3, 1, 3, 2, 19, 3};
+static const int k_npde[NUM_FUNCTORS] = {1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1, 3, 4};
+static const int k_nprm[NUM_FUNCTORS] = {1, 1, 3, 3, 3, 3, 1, 3, 2, 19, 3, 5, 7};
 
 // pdefun(x,t,u,dudx) -> (c,f,s)     docs/src/solvers.md:9-24
 template <class T>
@@ -94,6 +96,16 @@ static void pdefun(int id, const double* p, double x, double t, const T* u, cons
         s[0] = p[4] + p[5] * u[0] + p[6] * ux[0]; break;
     case EXP_DIFF:      // c = 1, f = p0*exp(u)*ux, s = -p1*u^2 + x
         c[0] = T(1.0); f[0] = p[0] * exp(u[0]) * ux[0]; s[0] = -(p[1] * u[0] * u[0]) + x; break;
+    case CHAIN3: {      // prm = {D1, D2, D3, k1, k2}: A -> B (rate k1*A^2), B -> C (rate k2*B)
+        c[0] = T(1.0); c[1] = T(1.0); c[2] = T(1.0);
+        f[0] = p[0] * ux[0]; f[1] = p[1] * ux[1]; f[2] = p[2] * ux[2];
+        T r1 = p[3] * u[0] * u[0], r2 = p[4] * u[1];
+        s[0] = -r1; s[1] = r1 - r2; s[2] = r2; break; }
+    case CHAIN4: {      // prm = {D1..D4, k1, k2, k3}: linear chain; species 2 has capacity 1 + u2 and its flux feels u1
+        c[0] = T(1.0); c[1] = 1.0 + u[1]; c[2] = T(1.0); c[3] = T(1.0);
+        f[0] = p[0] * ux[0]; f[1] = p[1] * (1.0 + u[0]) * ux[1]; f[2] = p[2] * ux[2]; f[3] = p[3] * ux[3];
+        T r1 = p[4] * u[0], r2 = p[5] * u[1], r3 = p[6] * u[2];
+        s[0] = -r1; s[1] = r1 - r2; s[2] = r2 - r3; s[3] = r3; break; }
     }
 }
 
@@ -127,6 +139,14 @@ static void bdfun(int id, const double* p, double xl, const T* ul, double xr, co
         pr[0] = p[13] * ur[0] - (p[14] + p[15] * t + p[16] * std::exp(-p[17] * t)); qr[0] = T(p[18]); break;
     case EXP_DIFF:      // left Dirichlet u = p2*(1+t), right homogeneous Neumann
         pl[0] = ul[0] - p[2] * (1.0 + t); ql[0] = T(0.0); pr[0] = T(0.0); qr[0] = T(1.0); break;
+    case CHAIN3:        // A held at 1 on the left, everything else zero flux; C absorbed (Dirichlet 0) on the right
+        pl[0] = ul[0] - 1.0; ql[0] = T(0.0); pl[1] = T(0.0); ql[1] = T(1.0); pl[2] = T(0.0); ql[2] = T(1.0);
+        pr[0] = T(0.0); qr[0] = T(1.0); pr[1] = T(0.0); qr[1] = T(1.0); pr[2] = ur[2]; qr[2] = T(0.0); break;
+    case CHAIN4:        // A held at 1 + t/10 on the left; D absorbed on the right; the rest zero flux
+        pl[0] = ul[0] - (1.0 + 0.1 * t); ql[0] = T(0.0);
+        for (int j = 1; j < 4; ++j) { pl[j] = T(0.0); ql[j] = T(1.0); }
+        for (int j = 0; j < 3; ++j) { pr[j] = T(0.0); qr[j] = T(1.0); }
+        pr[3] = ur[3]; qr[3] = T(0.0); break;
     }
 }
 
@@ -504,8 +524,12 @@ int sbo_residual_jacobian(int functor, int m, int Nx, const double* xmesh, int64
     for (int64_t k = 0; k < B; ++k) {
         Problem pb; problem_init(pb, m, Nx, xmesh, functor, prm + k * k_nprm[functor]);
         const double* mk = mass ? mass + k * n : nullptr;
-        if (P == 1) residual_jacobian<1>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P);
-        else        residual_jacobian<2>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P);
+        switch (P) {
+        case 1: residual_jacobian<1>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P); break;
+        case 2: residual_jacobian<2>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P); break;
+        case 3: residual_jacobian<3>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P); break;
+        default: residual_jacobian<4>(pb, u + k * n, b + k * n, tau, mk, t, F + k * n, Jl + k * n * P, Jd + k * n * P, Ju + k * n * P); break;
+        }
     }
     return 0;
 }
@@ -581,7 +605,9 @@ int sbo_pdepe_transient(int functor, int m, int Nx, const double* xmesh, int64_t
         double* hk = hist ? hist + (size_t)k * (nt - 1) * hist_cap : nullptr;
         double* sk = snapshots ? snapshots + (size_t)k * nt * n : nullptr;
         int rc = (P == 1) ? solve_transient<1>(pb, u + k * n, nt, tgrid, tau_scalar, tol, maxit, itk, hk, hist_cap, sk)
-                          : solve_transient<2>(pb, u + k * n, nt, tgrid, tau_scalar, tol, maxit, itk, hk, hist_cap, sk);
+               : (P == 2) ? solve_transient<2>(pb, u + k * n, nt, tgrid, tau_scalar, tol, maxit, itk, hk, hist_cap, sk)
+               : (P == 3) ? solve_transient<3>(pb, u + k * n, nt, tgrid, tau_scalar, tol, maxit, itk, hk, hist_cap, sk)
+                          : solve_transient<4>(pb, u + k * n, nt, tgrid, tau_scalar, tol, maxit, itk, hk, hist_cap, sk);
         if (status) status[k] = rc;
     }
     return 0;
@@ -601,7 +627,9 @@ int sbo_pdepe_stationary(int functor, int m, int Nx, const double* xmesh, int64_
     for (int64_t k = 0; k < B; ++k) {
         Problem pb; problem_init(pb, m, Nx, xmesh, functor, prm + k * k_nprm[functor]);
         int rc = (P == 1) ? solve_stationary<1>(pb, u + k * n, tol, maxit, iters ? iters + k : nullptr, hist ? hist + (size_t)k * maxit : nullptr)
-                          : solve_stationary<2>(pb, u + k * n, tol, maxit, iters ? iters + k : nullptr, hist ? hist + (size_t)k * maxit : nullptr);
+               : (P == 2) ? solve_stationary<2>(pb, u + k * n, tol, maxit, iters ? iters + k : nullptr, hist ? hist + (size_t)k * maxit : nullptr)
+               : (P == 3) ? solve_stationary<3>(pb, u + k * n, tol, maxit, iters ? iters + k : nullptr, hist ? hist + (size_t)k * maxit : nullptr)
+                          : solve_stationary<4>(pb, u + k * n, tol, maxit, iters ? iters + k : nullptr, hist ? hist + (size_t)k * maxit : nullptr);
         if (status) status[k] = rc;
     }
     return 0;

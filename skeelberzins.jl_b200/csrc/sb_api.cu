@@ -16,6 +16,7 @@
 #include <cstring>
 #include <atomic>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -60,10 +61,10 @@ std::atomic<long long> g_launches{0};  // kernels launched by this library (all 
 // cudaKernel_t handles of kernels compiled at run time (NVRTC) for a user functor.  Both launch through
 // cudaLaunchKernel.
 struct KernelSet {
-    const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr, *resident = nullptr;
+    const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr, *resident = nullptr, *solve = nullptr;
     const void *long_chunk = nullptr, *long_back = nullptr, *long_assemble_jac = nullptr, *long_assemble_val = nullptr;
     size_t fused_p_smem = 0, long_smem = 0, resident_smem = 0;
-    bool long_configured = false;
+    bool long_configured = false, small_configured = false;
     cudaLibrary_t lib = nullptr;  // owner of the run-time compiled kernels (user functors)
 };
 
@@ -112,6 +113,10 @@ const UserFunctor* user_functor(int functor_id) {
 }
 int add_user_functor(const UserFunctor& uf) {
     std::lock_guard<std::mutex> lk(g_uf_mu);
+    std::deque<UserFunctor>& v = user_functors_unlocked();
+    for (size_t i = 0; i < v.size(); ++i)   // registering the same source again returns the same id (and its compiled kernels)
+        if (v[i].npde == uf.npde && v[i].nparams == uf.nparams && v[i].name == uf.name && v[i].source == uf.source)
+            return SB_USER_FUNCTOR_BASE + (int)i;
     user_functors_unlocked().push_back(uf);
     return SB_USER_FUNCTOR_BASE + (int)user_functors_unlocked().size() - 1;
 }
@@ -200,14 +205,14 @@ const FunctorEntry* registry() {
     return table;
 }
 
-SolveKernel solve_kernel(int P, int dec) {
+SolveKernel solve_kernel(int P, int dec) {   // registry functors: npde <= 2 (wider systems come through the plugin, NVRTC)
     static SolveKernel t1[kNumDecomp], t2[kNumDecomp];
     static std::once_flag once;
     std::call_once(once, [] {
         fill_solve<1>(t1, std::make_integer_sequence<int, kNumDecomp>{});
         fill_solve<2>(t2, std::make_integer_sequence<int, kNumDecomp>{});
     });
-    return P == 1 ? t1[dec] : t2[dec];
+    return P == 1 ? t1[dec] : P == 2 ? t2[dec] : nullptr;
 }
 
 inline double ipow(double x, int n) {
@@ -383,6 +388,18 @@ int ensure_jacobian(sb_problem* pb) {
     return SB_OK;
 }
 
+// the one-CTA-per-system kernels of wide systems (npde >= 3) exchange more than the default 48 KB of shared memory
+int configure_small_kernels(sb_problem* pb) {
+    if (pb->ks.small_configured) return SB_OK;
+    const size_t smem = pb->warp ? 0 : solve_smem_bytes(pb->P, pb->dec);
+    if (smem > 48 * 1024) {
+        if (pb->ks.solve) CU(cudaFuncSetAttribute(pb->ks.solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (pb->ks.fused) CU(cudaFuncSetAttribute(pb->ks.fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    pb->ks.small_configured = true;
+    return SB_OK;
+}
+
 void launch_geometry(const sb_problem* pb, dim3& grid, dim3& block, size_t& smem) {
     if (pb->warp) {
         block = dim3(kWarpBlockThreads);
@@ -438,7 +455,9 @@ int download_nodes(sb_problem* pb, const double* src, double* host, int W) {
 // decomposition that covers the mesh with R <= Rpref rows per thread, else the CTA-per-system one with
 // the preferred R and the fewest threads.  SB_ROWS_PER_THREAD / SB_THREADS_PER_SYSTEM override (tuning).
 int pick_decomposition(int Nx, int P) {
-    const int Rpref = 8;  // measured: (8, 32) beats (4, 64) for npde = 2 at Nx = 256; (8, 128) is best for npde = 1 at Nx = 1024
+    // measured: (8, 32) beats (4, 64) for npde = 2 at Nx = 256; (8, 128) is best for npde = 1 at Nx = 1024; npde = 3, 4: what
+    // the register file allows (max_rows_per_thread)
+    const int Rpref = std::min(8, max_rows_per_thread(P));
     int want_R = 0, want_T = 0;
     if (const char* e = getenv("SB_ROWS_PER_THREAD")) want_R = atoi(e);
     if (const char* e = getenv("SB_THREADS_PER_SYSTEM")) want_T = atoi(e);
@@ -513,6 +532,7 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     name("sb::k_newton_fused<%s, %d, %d, %s>");
     name("sb::k_newton_fused_p<%s, %d, %d, %s>");
     name("sb::k_solve_resident<%s, %d, %d, %s>");
+    snprintf(buf, sizeof buf, "sb::k_solve<%d, %d, %d>", uf.npde, R, TT); names.push_back(buf);
     if (longmesh) {
         name("sb::k6_chunk_asm<%s, %d, %d, %s>");
         name("sb::k6_back_asm<%s, %d, %d, %s>");
@@ -553,15 +573,32 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
 }
 
 // Compile the kernels this problem needs (its decomposition, its coordinate symmetry) for a user functor and load them.
+struct CompiledShape { std::vector<char> cubin; std::vector<std::string> lowered; };
+std::mutex g_cubin_mu;
+std::map<std::string, CompiledShape>& cubin_cache() { static std::map<std::string, CompiledShape> m; return m; }
+
 int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
+    // one NVRTC run per (functor, problem shape); later problems of the same shape load the cached CUBIN
+    char key[512];
+    snprintf(key, sizeof key, "%p|%s|%d|%d|%d|%d", (const void*)&uf, uf.name.c_str(), pb->pd.R, pb->pd.T, pb->sym0, (int)pb->longmesh);
     std::vector<char> cubin;
     std::vector<std::string> lowered;
-    int rc = nvrtc_user_kernels(uf, pb->pd.R, pb->pd.T, pb->sym0 != 0, pb->longmesh, cubin, lowered);
-    if (rc != SB_OK) return rc;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lk(g_cubin_mu);
+        auto it = cubin_cache().find(key);
+        if (it != cubin_cache().end()) { cubin = it->second.cubin; lowered = it->second.lowered; hit = true; }
+    }
+    if (!hit) {
+        int rc = nvrtc_user_kernels(uf, pb->pd.R, pb->pd.T, pb->sym0 != 0, pb->longmesh, cubin, lowered);
+        if (rc != SB_OK) return rc;
+        std::lock_guard<std::mutex> lk(g_cubin_mu);
+        cubin_cache()[key] = CompiledShape{cubin, lowered};
+    }
     KernelSet& ks = pb->ks;
     cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
-    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p, &ks.resident,
+    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p, &ks.resident, &ks.solve,
                             &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
     for (size_t i = 0; i < lowered.size(); ++i) {
         cudaKernel_t kern;
@@ -842,7 +879,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
             ctx->refs--;
             delete pb;
             return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) for npde = %d; the long-mesh "
-                        "path handles scalar PDEs only", Nx, kMaxBlockT * 8, f_npde);
+                        "path handles scalar PDEs only", Nx, kMaxBlockT * std::min(8, max_rows_per_thread(f_npde)), f_npde);
         }
         pb->longmesh = true;
         R = kLongR; T = kLongT0;
@@ -920,7 +957,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     TRY(dev_alloc(&pb->d_count, (size_t)2 * kSlots));  // active counts [kSlots] + done tickets [kSlots]
     TRY(dev_alloc(&pb->d_list, (size_t)2 * B));
     constexpr int kPivSlots = 64;   // concurrent pivoted fallback solves (a group that finds none free waits for one)
-    const size_t piv_stride = (size_t)Nx * pb->P * ((pb->P == 1 ? BandShape<1>::ldab : BandShape<2>::ldab) + 1);
+    const size_t piv_stride = (size_t)Nx * pb->P * ((size_t)(6 * pb->P - 2) + 1);   // BandShape<P>::ldab = 3*(2P-1) + 1 band rows + the rhs
     if (!pb->longmesh) {
         TRY(dev_alloc(&pb->d_piv, kPivSlots * piv_stride));
         TRY(dev_alloc(&pb->d_piv_lock, (size_t)kPivSlots));
@@ -978,6 +1015,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         ks.fused_p = (const void*)fe->fused_p[pb->dec][pb->sym0];
         ks.fused_p_smem = fe->fused_p_smem[pb->dec][pb->sym0];
         ks.resident = (const void*)fe->resident[pb->dec][pb->sym0];
+        ks.solve = (const void*)solve_kernel(pb->P, pb->dec);
         ks.resident_smem = fe->resident_smem[pb->dec][pb->sym0];
         ks.long_chunk = (const void*)fe->long_chunk[pb->sym0];
         ks.long_back = (const void*)fe->long_back[pb->sym0];
@@ -1166,8 +1204,7 @@ static int run_begin_step_kernel(sb_problem* pb) {
     const size_t total = (size_t)pb->pd.B * pb->pd.L;
     const int bs = 256;
     cudaStream_t st = pb->ctx->stream;
-    if (pb->P == 1) k_begin_step<1><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
-    else k_begin_step<2><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd);
+    k_begin_step<0><<<(unsigned)((total + bs - 1) / bs), bs, 0, st>>>(pb->pd, pb->P);
     ++g_launches;
     CU(cudaGetLastError());
     return SB_OK;
@@ -1353,8 +1390,8 @@ int sb_solve_update_norm(sb_problem* pb, double tol) {
     if ((rc = prepare_slot(pb, &slot))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    solve_kernel(pb->P, pb->dec)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, tol, slot, 1);
-    ++g_launches;
+    if ((rc = configure_small_kernels(pb))) return rc;
+    CU(launch_any(pb->ks.solve, grid, block, smem, pb->ctx->stream, pb->pd, tol, slot, 1));
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evB[slot], pb->ctx->stream));
     return finish_slot(pb, slot);
@@ -1411,6 +1448,7 @@ int sb_newton_iteration(sb_problem* pb, double tol) {
         return finish_slot(pb, slot);
     }
     pb->step_all_tma = false;
+    if ((rc = configure_small_kernels(pb))) return rc;
     if (pb->prof) CU(cudaEventRecord(pb->evA[slot], pb->ctx->stream));
     CU(launch_any(pb->ks.fused, grid, block, smem, pb->ctx->stream, pb->pd, pb->t_next, pb->inv_tau, tol, slot));
     CU(cudaGetLastError());
@@ -1869,8 +1907,8 @@ int sb_debug_solve(sb_problem* pb, const double* Jl, const double* Jd, const dou
     if ((rc = upload_nodes(pb, F, pb->d_F, pb->P, 0))) return rc;
     dim3 grid, block; size_t smem;
     launch_geometry(pb, grid, block, smem);
-    solve_kernel(pb->P, pb->dec)<<<grid, block, smem, pb->ctx->stream>>>(pb->pd, 0.0, 0, 0);
-    ++g_launches;
+    if ((rc = configure_small_kernels(pb))) return rc;
+    CU(launch_any(pb->ks.solve, grid, block, smem, pb->ctx->stream, pb->pd, 0.0, 0, 0));
     CU(cudaGetLastError());
     return download_nodes(pb, pb->d_F, x, pb->P);
 }

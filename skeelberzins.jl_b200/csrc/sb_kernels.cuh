@@ -223,6 +223,13 @@ struct ChunkThomas {
 #else                       // default: warp 0 solves the TT separators (finish_serial): first rows | reduced rows | unknowns | monitor words
     template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT + TT / 32 + 1; }
 #endif
+    // the all-warps variant reuses its exchange region while slow warps may still read it: two buffers; the serial one
+    // has a barrier between every write and the reads it could disturb: one
+#ifdef SB_FINISH_PARALLEL
+    static constexpr int exch_buffers = 2;
+#else
+    static constexpr int exch_buffers = 1;
+#endif
     // ... followed by one partial sum per warp for system_sum()
     template <int TT> static __host__ __device__ constexpr int smem_doubles() { return TT == 32 ? 0 : exch_doubles<TT>() + TT / 32; }
 
@@ -1012,6 +1019,25 @@ __device__ __noinline__ bool pivoted_newton_rows(ProbDev pd, MeshDev mesh, long 
     return piv_solve<P, R, TT>(pd, k, t, s, h);
 }
 
+// the fallback for the split design: the rows are already in HBM (Jl, Jd, Ju, F)
+template <int P, int R, int TT>
+__device__ __noinline__ bool pivoted_stored_rows(ProbDev pd, long long k, int t, volatile int* sh_slot, double (&h)[R][P]) {
+    const int s = piv_begin<P, TT>(pd, t, (int)k, sh_slot);
+    double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
+    BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const size_t o = (size_t)k * pd.L + (size_t)r * TT + t;
+        Mat<P> A, Bm, C; Vec<P> d;
+#pragma unroll
+        for (int i = 0; i < P * P; ++i) { A.a[i] = pd.Jl[o * P * P + i]; Bm.a[i] = pd.Jd[o * P * P + i]; C.a[i] = pd.Ju[o * P * P + i]; }
+#pragma unroll
+        for (int i = 0; i < P; ++i) d.a[i] = pd.F[o * P + i];
+        sink.row(r, A, Bm, C, d);
+    }
+    return piv_solve<P, R, TT>(pd, k, t, s, h);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: residual + Jacobian to HBM (JAC) / assemble! value into F (!JAC)
 // ---------------------------------------------------------------------------------------------
@@ -1097,22 +1123,8 @@ __global__ void SB_LAUNCH_BOUNDS(TT) k_solve(ProbDev pd, double tol, int slot, i
     }
     Vec<P> h[R];
     if (th.template finish<TT>(h, sm, t)) {   // pivot growth: the same system again, with row interchanges
-        volatile int* sh_slot = reinterpret_cast<volatile int*>(sm + ChunkThomas<P, R>::template smem_doubles<TT>());
-        const int s = piv_begin<P, TT>(pd, t, (int)k, sh_slot);
-        double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
-        BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const size_t o = (size_t)k * pd.L + (size_t)r * TT + t;
-            Mat<P> A, Bm, C; Vec<P> d;
-#pragma unroll
-            for (int i = 0; i < P * P; ++i) { A.a[i] = pd.Jl[o * P * P + i]; Bm.a[i] = pd.Jd[o * P * P + i]; C.a[i] = pd.Ju[o * P * P + i]; }
-#pragma unroll
-            for (int i = 0; i < P; ++i) d.a[i] = pd.F[o * P + i];
-            sink.row(r, A, Bm, C, d);
-        }
         double hp[R][P];
-        piv_solve<P, R, TT>(pd, k, t, s, hp);
+        pivoted_stored_rows<P, R, TT>(pd, k, t, reinterpret_cast<volatile int*>(sm + ChunkThomas<P, R>::template smem_doubles<TT>()), hp);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -1214,7 +1226,8 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
     static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
     static constexpr int oGw = 0, oAB = oGw + nGw, oIvol = oAB + nAB, oFrac = oIvol + nIvol, mesh_doubles = oFrac + nFrac;
-    static constexpr int scratch = 2 * ChunkThomas<P, R>::template exch_doubles<TT>();   // exchange region of finish(), double-buffered
+    static constexpr int exch = ChunkThomas<P, R>::template exch_doubles<TT>(), nexch = ChunkThomas<P, R>::exch_buffers;
+    static constexpr int scratch = nexch * exch + (nexch * exch) % 2;   // exchange region(s) of finish(), padded to 16 bytes
     // per group: u[S][L*P], b[S][L*P], prm[S][NPS], mass[S][4P], scratch, partial sums [2][8], mass flags kept [4P], instance index [2]
     static constexpr int oU = 0, oB = oU + S * L * P, oPrm = oB + S * L * P, oMass = oPrm + S * NPS, oScr = oMass + S * 4 * P,
                          oSum = oScr + scratch, oKeep = oSum + 16, oK = oKeep + 4 * P, group_doubles = oK + 4;   // oK: instance index [2], fallback slot [2 ints], pad
@@ -1227,7 +1240,7 @@ struct FusedPLayout {  // shared-memory carve-up (offsets in doubles)
 // thread; 2x2 block arithmetic needs about twice that, so it is given half the warps instead of spilling
 __host__ __device__ constexpr int persistent_min_blocks(int TT, int P) {
     const int threads = (TT == 32) ? kWarpBlockThreads : TT;
-    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_P2;
+    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_P2;   // P > 2: as P = 2 (255 registers)
     return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;
 }
 template <class Fn, int R, int TT, bool SYM0>
@@ -1418,7 +1431,7 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
         ChunkThomas<P, R> th;
         assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, us, bs, mass, t, tt, inv_tau, prm, uc, bc, th);
         Vec<P> h[R];
-        double* exch = scratch + (it & 1) * (LY::scratch / 2);
+        double* exch = scratch + (it % LY::nexch) * LY::exch;
         bool suspect;
         if constexpr (TT == 32) {
             __syncwarp();  // every lane is done with the staged inputs
@@ -1518,8 +1531,8 @@ __global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary
 }
 
 // b = M .* u_n ; u <- b ; active, counters (src/pdepe.jl:94, src/utils.jl:309)
-template <int P>
-__global__ void k_begin_step(ProbDev pd) {
+template <int UNUSED = 0>   // (a template only so that the header can be included from several translation units)
+__global__ void k_begin_step(ProbDev pd, int P) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*L node slots
     const size_t total = (size_t)pd.B * pd.L;
     if (idx >= total) return;
@@ -1531,7 +1544,6 @@ __global__ void k_begin_step(ProbDev pd) {
     if (s == 0) { pd.active[k] = 1; pd.iters[k] = 0; }
     const double* mass = pd.mass + (size_t)k * 4 * P;
     const int cls = (i == 0) ? 0 : ((i == pd.Nx - 1) ? 2 : 1);
-#pragma unroll
     for (int p = 0; p < P; ++p) {
         const double mv = mass[cls * P + p];
         const double v = (i < pd.Nx) ? mv * pd.u[idx * P + p] : 0.0;

@@ -11,14 +11,19 @@ namespace sb {
 // Thread decompositions the kernels are compiled for: R rows per thread x TT threads per system.
 // TT == 32: one warp per system (shuffles only); TT > 32: one CTA per system.
 struct Decomp { int R, TT; };
-constexpr int kNumDecomp = 13;
+constexpr int kNumDecomp = 16;
 constexpr Decomp kDecomp[kNumDecomp] = {
     {1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32},   // warp per system: Nx <= 32 .. 512
     {4, 64}, {8, 64}, {16, 64},                     // CTA per system
     {4, 128}, {8, 128},
     {4, 256}, {8, 256}, {16, 256},
+    {2, 64}, {2, 128}, {2, 256},                    // npde = 4 only (two rows per thread is all its registers hold)
 };
-constexpr bool decomp_ok(int P, int d) { return P == 1 || kDecomp[d].R <= 8; }  // R = 16 only for scalar PDEs
+// rows per thread the register file allows: the factors of a row are 2*P*P + P doubles (R = 16 only for scalar PDEs)
+constexpr int max_rows_per_thread(int P) { return P == 1 ? 16 : P == 2 ? 8 : P == 3 ? 4 : 2; }
+constexpr bool decomp_ok(int P, int d) {
+    return kDecomp[d].R <= max_rows_per_thread(P) && (P == 4 || !(kDecomp[d].R == 2 && kDecomp[d].TT > 32));
+}
 
 typedef void (*AssembleKernel)(ProbDev, double, double, int);
 typedef void (*FusedKernel)(ProbDev, double, double, double, int);

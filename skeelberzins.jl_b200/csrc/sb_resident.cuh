@@ -44,10 +44,12 @@ struct ResidentLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
     static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
     static constexpr int oGw = 0, oAB = oGw + nGw, oIvol = oAB + nAB, oFrac = oIvol + nIvol, mesh_doubles = oFrac + nFrac;
-    static constexpr int exch = ChunkThomas<P, R>::template exch_doubles<TT>();
-    // per group: u[L*P] (+2 so that slot -1 and slot L exist), b[L*P], prm[NPS], mass[4P], exchange x2, sums [2][8], slot word
+    static constexpr int exch = ChunkThomas<P, R>::template exch_doubles<TT>(), nexch = ChunkThomas<P, R>::exch_buffers;
+    static constexpr int scr = nexch * exch + (nexch * exch) % 2;
+    // per group: u[L*P] (+2 so that slot -1 and slot L exist), b[L*P], prm[NPS], mass[4P], exchange region(s), sums [2][8], slot word
     static constexpr int oU = 2, oB = oU + L * P + 2, oPrm = oB + L * P, oMass = oPrm + NPS, oScr = oMass + 4 * P,
-                         oSum = oScr + 2 * exch, oSlot = oSum + 16, group_doubles = oSlot + 2;
+                         oSum = oScr + scr, oSlot = oSum + 16, group_doubles = oSlot + 2;
+    static_assert(group_doubles % 2 == 0 && mesh_doubles % 2 == 0, "double2 accesses need 16-byte aligned groups");
     static constexpr size_t bytes = sizeof(double) * (size_t)(mesh_doubles + G * group_doubles);
 };
 
@@ -168,7 +170,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 ChunkThomas<P, R> th;
                 assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, utile, btile, mbuf, t, tt, inv_tau, pbuf, uc, bc, th);
                 Vec<P> h[R];
-                const bool suspect = th.template finish<TT>(h, scratch + (it & 1) * LY::exch, t);   // (B) inside
+                const bool suspect = th.template finish<TT>(h, scratch + (it % LY::nexch) * LY::exch, t);   // (B) inside
                 if (suspect) {          // pivot growth: the same rows into a band, solved with row interchanges
                     double hp[R][P];
                     const bool singular = pivoted_newton_rows<Fn, R, TT, SYM0, false>(pd, mesh, k, utile, btile, t, blockIdx.x * G + g, tt,

@@ -95,3 +95,96 @@ def test_user_functor_long_mesh(ctx, oracle):
     sol = sb.pdepe(0, fn, ic, fn, x, (0.0, 0.03), ctx=ctx, tstep=1e-2, squeeze=False, save="last")
     r = oracle.pdepe_transient(ORACLE_EXP_DIFF, 0, x, prm, ic[None, :, None], sb.julia_range(0.0, 1e-2, 0.03), 1e-2)
     assert np.abs(sol.u[-1] - r["u"][:, :, 0]).max() < 1e-10 * np.abs(r["u"]).max()
+
+
+# ---- npde = 3 and 4: reference src/utils.jl:67-104, :725-759 are generic in npde; here wide systems come through the plugin
+CHAIN3_SRC = r"""
+struct Chain3 {   // A -> B (rate k1*A^2), B -> C (rate k2*B); prm = {D1, D2, D3, k1, k2}
+    static constexpr int npde = 3, nparams = 5;
+    static constexpr bool c_unit = true, s_zero = false;
+    template <class S> static __device__ void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
+        c[0] = S(1.0); c[1] = S(1.0); c[2] = S(1.0);
+        f[0] = p[0] * ux[0]; f[1] = p[1] * ux[1]; f[2] = p[2] * ux[2];
+        const S r1 = p[3] * u[0] * u[0], r2 = p[4] * u[1];
+        s[0] = -r1; s[1] = r1 - r2; s[2] = r2;
+    }
+    template <class S> static __device__ void bc(double, const S* ul, double, const S* ur, double, const double*,
+                                                 S* pl, double* ql, S* pr, double* qr) {
+        pl[0] = ul[0] - 1.0; ql[0] = 0.0; pl[1] = S(0.0); ql[1] = 1.0; pl[2] = S(0.0); ql[2] = 1.0;
+        pr[0] = S(0.0); qr[0] = 1.0; pr[1] = S(0.0); qr[1] = 1.0; pr[2] = ur[2]; qr[2] = 0.0;
+    }
+};
+"""
+CHAIN4_SRC = r"""
+struct Chain4 {   // A -> B -> C -> D; species 2 has capacity 1 + u2 and a flux that feels u1; prm = {D1..D4, k1, k2, k3}
+    static constexpr int npde = 4, nparams = 7;
+    static constexpr bool c_unit = false, s_zero = false;
+    template <class S> static __device__ void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
+        c[0] = S(1.0); c[1] = 1.0 + u[1]; c[2] = S(1.0); c[3] = S(1.0);
+        f[0] = p[0] * ux[0]; f[1] = p[1] * (1.0 + u[0]) * ux[1]; f[2] = p[2] * ux[2]; f[3] = p[3] * ux[3];
+        const S r1 = p[4] * u[0], r2 = p[5] * u[1], r3 = p[6] * u[2];
+        s[0] = -r1; s[1] = r1 - r2; s[2] = r2 - r3; s[3] = r3;
+    }
+    template <class S> static __device__ void bc(double, const S* ul, double, const S* ur, double t, const double*,
+                                                 S* pl, double* ql, S* pr, double* qr) {
+        pl[0] = ul[0] - (1.0 + 0.1 * t); ql[0] = 0.0;
+        for (int j = 1; j < 4; ++j) { pl[j] = S(0.0); ql[j] = 1.0; }
+        for (int j = 0; j < 3; ++j) { pr[j] = S(0.0); qr[j] = 1.0; }
+        pr[3] = ur[3]; qr[3] = 0.0;
+    }
+};
+"""
+WIDE = {3: (CHAIN3_SRC, "Chain3", 11, [0.5, 0.2, 0.1, 2.0, 1.0]), 4: (CHAIN4_SRC, "Chain4", 12, [0.5, 0.2, 0.1, 0.05, 2.0, 1.0, 0.5])}
+
+
+@pytest.mark.parametrize("npde,Nx,design", [(3, 100, "resident"), (3, 100, "fused_tma"), (3, 100, "split"), (3, 1000, "resident"),
+                                            (3, 1000, "fused"), (4, 50, "resident"), (4, 50, "split"), (4, 500, "resident"),
+                                            (4, 500, "fused_tma")])
+def test_three_and_four_species_systems(ctx, oracle, npde, Nx, design):
+    """Wide systems through the plugin slot, every design, warp and CTA decompositions, against the oracle: final
+    state to 1e-10, the Newton iteration count of every instance in every step, residual and Jacobian blocks."""
+    src, name, oracle_id, base = WIDE[npde]
+    fid = sb.register_user_functor(src, name, npde, len(base))
+    B = 5
+    prm = np.tile(np.array(base), (B, 1)) * (1.0 + 0.1 * np.arange(B))[:, None]
+    x = ex.linspace(0, 1, Nx)
+    u0 = np.zeros((B, Nx, npde))
+    u0[:, :, 0] = np.exp(-5 * x)
+    tg = np.linspace(0.0, 0.3, 7)
+    fn = sb.Functor(fid, prm)
+    dev = sb.DeviceProblem(ctx, 0, x, fn, design=design)
+    try:
+        dev.upload(u0)
+        dev.mass_flags(tg[0])
+        M = dev.mass()
+        assert np.array_equal(M, oracle.mass(oracle_id, 0, x, prm, u0, tg[0]))
+        its = np.empty((B, tg.size - 1), dtype=np.int32)
+        for i in range(tg.size - 1):
+            dev.begin_step(tg[i + 1], 1.0 / (tg[i + 1] - tg[i]))
+            if i % 2:
+                dev.newton_solve(1e-10, 100)
+            else:
+                sb.api._newton_loop(dev, 1e-10, 100)
+            its[:, i] = dev.step_iters()
+        u = dev.download().copy()
+        r = oracle.pdepe_transient(oracle_id, 0, x, prm, u0, tg, None)
+        assert np.abs(u - r["u"]).max() < 1e-10 * np.abs(r["u"]).max()
+        assert np.array_equal(its, r["iters"])
+        assert (dev.status() == 0).all()
+        if design == "split":                                # F and the block-tridiagonal Jacobian entry by entry
+            dev.begin_step(0.4, 10.0)
+            b = M * u
+            dev.residual_jacobian()
+            F, Jl, Jd, Ju = dev.debug_system()
+            Fo, Jlo, Jdo, Juo = oracle.residual_jacobian(oracle_id, 0, x, prm, b, b, 0.1, M, 0.4)
+            scale = np.abs(Jdo).max()
+            assert np.abs(F - Fo).max() <= 1e-12 * max(np.abs(Fo).max(), 1.0)
+            for A, Ao in ((Jl, Jlo), (Jd, Jdo), (Ju, Juo)):
+                assert np.abs(A - Ao).max() <= 1e-12 * scale
+        if design == "resident":                             # the whole solve in one launch, same answer
+            dev.upload(u0)
+            dev.mass_flags(tg[0])
+            it1 = dev.solve_steps_opt(tg, None, 1e-10, 100, step_iters=True)
+            assert np.array_equal(dev.download(), u) and np.array_equal(it1, its)
+    finally:
+        dev.close()
