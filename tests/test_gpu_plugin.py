@@ -185,6 +185,8 @@ def test_three_and_four_species_systems(ctx, oracle, npde, Nx, design):
             dev.upload(u0)
             dev.mass_flags(tg[0])
             it1 = dev.solve_steps_opt(tg, None, 1e-10, 100, step_iters=True)
-            assert np.array_equal(dev.download(), u) and np.array_equal(it1, its)
+            # (bit-identical for npde <= 2, tests/test_gpu_resident.py; the generic Gauss-Jordan block inverse of wider
+            # systems is contracted into FMAs differently in the two kernels: agreement to rounding)
+            assert np.abs(dev.download() - u).max() < 1e-13 * np.abs(u).max() and np.array_equal(it1, its)
     finally:
         dev.close()
