@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's B instances PER GPU (default, what the driver's 1..8 sweep runs); "
                          "strong: the config's B instances in total, B/N per GPU (SURVEY 8(e): 512 per GPU at N = 8)")
+    ap.add_argument("--shard", default="strided", choices=["strided", "contiguous"],
+                    help="which instances of the job a rank solves: every N-th (default: the same mix of the sweep on every GPU) "
+                         "or a contiguous block by instance index")
     ap.add_argument("--no-extras", action="store_true", help="skip the host-owned-loop and out-of-L2 corroboration legs")
     return ap.parse_args()
 
@@ -256,8 +259,9 @@ def run_ours(args):
     case, Bp, Nx = make_case(args, world)
     tg, tau = time_grid_of(case, args)
     P = case.npde
-    lo, hi = rank * Bp, (rank + 1) * Bp                       # shard by instance index, no collective on the path
-    prm = np.ascontiguousarray(case.params[lo:hi])
+    # shard by instance index, no collective on the path: strided (rank, rank + N, ...) or a contiguous block
+    mine = np.arange(rank, Bp * world, world) if args.shard == "strided" else np.arange(rank * Bp, (rank + 1) * Bp)
+    prm = np.ascontiguousarray(case.params[mine])
     u0_t = torch.empty((Bp, Nx, P), dtype=torch.float64).pin_memory()
     u0 = u0_t.numpy()
     u0[:] = np.asarray(case.icfun(case.xmesh), dtype=np.float64).reshape(1, Nx, P)
@@ -607,7 +611,8 @@ def run_ours(args):
                                      "all Newton iterations of all time steps (no lock step between instances)" if args.design == "resident" else
                                      "C sb_solve_steps: time loop and Newton loop in C, device-side stepping (a launch that finds "
                                      "every instance converged starts the next time step itself)"),
-                       "scaling_mode": "%s: %d instances per GPU, %d in total" % (args.scaling, Bp, Bp * world),
+                       "scaling_mode": "%s: %d instances per GPU, %d in total; %s shards by instance index, no collective on the data path"
+                                       % (args.scaling, Bp, Bp * world, args.shard),
                        "per_rank_ms_per_step": {"min": min(per_rank_ms), "median": float(np.median(per_rank_ms)),
                                                 "max": max(per_rank_ms), "all": per_rank_ms},
                        "host_cores_per_rank": pinned_cores,

@@ -836,23 +836,25 @@ def _pdepe_devices(devices, m, pdefun, icfun, bdfun, x, tspan, kw):
     (sharding.shard_range), one host thread and one context per GPU, no exchange between the shards (the instances are
     independent); the results are put together in instance order."""
     import threading
-    from .sharding import shard_range
+    from .sharding import shard_indices
     B, Nx, npde = pdefun.batch, x.size, pdefun.npde
     u0 = None if callable(icfun) else np.asarray(icfun, dtype=np.float64)
     per_inst_ic = u0 is not None and u0.size == B * Nx * npde and B > 1
     tstep = kw.get("tstep", None)
     parts, errors = [None] * len(devices), []
 
+    shards = [shard_indices(B, len(devices), r) for r in range(len(devices))]   # strided: every GPU gets the same mix
+
     def work(r, d):
-        lo, hi = shard_range(B, len(devices), r)
-        if hi <= lo:
+        idx = shards[r]
+        if idx.size == 0:
             return
         try:
-            fn = Functor(pdefun.id, pdefun.params[lo:hi])
-            ic = u0.reshape(B, Nx, npde)[lo:hi] if per_inst_ic else icfun
+            fn = Functor(pdefun.id, pdefun.params[idx])
+            ic = u0.reshape(B, Nx, npde)[idx] if per_inst_ic else icfun
             kw_r = dict(kw)
             if tstep is not None and np.ndim(tstep) == 2:
-                kw_r["tstep"] = np.asarray(tstep)[lo:hi]
+                kw_r["tstep"] = np.asarray(tstep)[idx]
             parts[r] = pdepe(m, fn, ic, fn, x, tspan, ctx=default_context(int(d)), squeeze=False, **kw_r)
         except Exception as e:          # re-raised on the calling thread
             errors.append(e)
@@ -864,11 +866,20 @@ def _pdepe_devices(devices, m, pdefun, icfun, bdfun, x, tspan, kw):
         t_.join()
     if errors:
         raise errors[0]
-    parts = [p for p in parts if p is not None]
+    live = [(shards[r], p) for r, p in enumerate(parts) if p is not None]
+
+    def gather(pieces):                  # back into instance order
+        first = np.asarray(pieces[0])
+        out = np.empty((B,) + first.shape[1:], dtype=first.dtype)
+        for (idx, _), a in zip(live, pieces):
+            out[idx] = a
+        return out
+
     if tspan is None:
-        return np.concatenate(parts, axis=0)
-    us = [np.concatenate([p.u[i] for p in parts], axis=0) for i in range(len(parts[0].u))]
-    ts = parts[0].t if np.ndim(parts[0].t) == 1 else np.concatenate([p.t for p in parts], axis=0)
+        return gather([p for _, p in live])
+    p0 = live[0][1]
+    us = [gather([p.u[i] for _, p in live]) for i in range(len(p0.u))]
+    ts = p0.t if np.ndim(p0.t) == 1 else gather([p.t for _, p in live])
     return DiffEqArray(us, ts)
 
 

@@ -220,8 +220,8 @@ struct ChunkThomas {
     // shared memory of finish<TT>() in doubles: the exchange region (two equations per warp) ...
 #ifdef SB_FINISH_PARALLEL   // tuning builds: every warp reduces its own separators (see finish_parallel)
     template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + 1) * (TT / 32); }
-#else                       // default: warp 0 solves the TT separators (finish_serial): first rows | reduced rows | unknowns | monitor words
-    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (2 * NW + P) * TT + TT / 32 + 1; }
+#else                       // default: warp 0 solves the TT separators (finish_serial): warps' first rows | reduced rows | unknowns | monitor words
+    template <int TT> static __host__ __device__ constexpr int exch_doubles() { return TT == 32 ? 0 : (NW + P) * TT + (NW + 1) * (TT / 32) + 1; }
 #endif
     // the all-warps variant reuses its exchange region while slow warps may still read it: two buffers; the serial one
     // has a barrier between every write and the reads it could disturb: one
@@ -319,45 +319,65 @@ struct ChunkThomas {
     template <int TT, class Hook>
     SB_D bool finish_serial(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
         constexpr int W = TT / 32;
+        const int lane = t & 31, wi = t >> 5;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
         if constexpr (R == 1) summary(y0, v0, w0, yL, vL, wL);
         else { to_explicit(); y0 = dt[0]; v0 = vt[0]; w0 = ct[0]; yL = dt[R - 2]; vL = vt[R - 2]; wL = ct[R - 2]; }
+        // first-row representation of thread t+1: by shuffle inside the warp.  At a warp's last lane the first row of the
+        // next warp stays in the reduced row as an unknown (coefficient c) -- warp 0 eliminates it below with the
+        // representation that warp's lane 0 leaves in shared memory -- so no barrier is needed before the reduced rows.
         double mine[NW], nb[NW];
         pack(mine, v0, w0, y0);
+        double* frow = sm;                       // [W][NW] first-row representations of the warps' first threads
+        double* red = sm + NW * W;               // [NW][TT] reduced rows
+        double* xsm = red + NW * TT;             // [P][TT] separator unknowns
+        unsigned* monw = reinterpret_cast<unsigned*>(xsm + P * TT);   // [W] per-warp monitors, [2W] the verdict
 #pragma unroll
-        for (int w = 0; w < NW; ++w) sm[w * TT + t] = mine[w];
-        __syncthreads();
-        hook();
-#pragma unroll
-        for (int w = 0; w < NW; ++w) nb[w] = (t + 1 < TT) ? sm[w * TT + t + 1] : 0.0;
+        for (int w = 0; w < NW; ++w) {
+            const double v = __shfl_down_sync(0xffffffffu, mine[w], 1);
+            const bool wdiag = (w >= P * P) && (w < 2 * P * P) && ((w - P * P) / P == (w - P * P) % P);
+            nb[w] = (lane < 31) ? v : ((wdiag && t != TT - 1) ? -1.0 : 0.0);
+            if (lane == 0) frow[wi * NW + w] = mine[w];
+        }
         Mat<P> v0n, w0n; Vec<P> y0n;
         unpack(nb, v0n, w0n, y0n);
         Mat<P> an, cn; Vec<P> dn;
         reduced_row(As, Bs, Cs, ds, yL, vL, wL, v0n, w0n, y0n, an, cn, dn);
         watch(an); watch(cn);
         constexpr int Q = TT / 32;  // reduced rows per lane of warp 0
-        double* red = sm + NW * TT;
-        double* xsm = sm + 2 * NW * TT;
-        unsigned* monw = reinterpret_cast<unsigned*>(sm + (2 * NW + P) * TT);   // [W] per-warp monitors, [2W] the verdict
         pack(mine, an, cn, dn);
 #pragma unroll
         for (int w = 0; w < NW; ++w) red[w * TT + t] = mine[w];
 #ifndef SB_NO_PIVOT_MONITOR
         {
             const unsigned g = __reduce_max_sync(0xffffffffu, mon);
-            if ((t & 31) == 0) monw[t >> 5] = g;
+            if (lane == 0) monw[wi] = g;
         }
 #endif
         __syncthreads();
+        hook();
         if (t < 32) {
             ChunkThomas<P, Q> lvl2;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
+                const int j = t * Q + q;                       // reduced row = separator of thread j
                 double rw[NW];
 #pragma unroll
-                for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + t * Q + q];
+                for (int w = 0; w < NW; ++w) rw[w] = red[w * TT + j];
                 Mat<P> a, c; Vec<P> d;
                 unpack(rw, a, c, d);
+                if ((j & 31) == 31 && j != TT - 1) {           // last thread of a warp: x_j + a x_{j-1} + c F = d with
+                    double fw[NW];                             // F = y0' - v0' x_j - w0' x_{j+1} the next warp's first row
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) fw[w] = frow[((j >> 5) + 1) * NW + w];
+                    Mat<P> v0f, w0f; Vec<P> y0f;
+                    unpack(fw, v0f, w0f, y0f);
+                    const Mat<P> inv = inverse_fast(sub_mul(mat_identity<P>(), c, v0f));
+                    d = mul(inv, sub_mul(d, c, y0f));
+                    a = mul(inv, a);
+                    c = neg(mul(inv, mul(c, w0f)));
+                    lvl2.watch(a); lvl2.watch(c);
+                }
                 lvl2.row(q, a, mat_identity<P>(), c, d);
             }
             Vec<P> y[Q];

@@ -117,7 +117,7 @@ inline size_t solve_smem_bytes(int P, int d) {
 #ifdef SB_FINISH_PARALLEL
     const int exch = (2 * NW + 1) * W;
 #else
-    const int exch = (2 * NW + P) * TT + W + 1;
+    const int exch = (NW + P) * TT + (NW + 1) * W + 1;
 #endif
     return (size_t)(exch + W /* partial sums */ + 1 /* the fallback's slot word */) * sizeof(double);   // ChunkThomas::smem_doubles<TT>() + 1
 }

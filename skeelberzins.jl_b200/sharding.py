@@ -18,6 +18,16 @@ def shard_range(B, world_size, rank):
     return lo, min(B, lo + per)
 
 
+def shard_indices(B, world_size, rank, mode="strided"):
+    """Instance indices of rank `rank`.  "strided": rank, rank + world, rank + 2*world, ... -- every rank gets the same
+    mix of a sweep, so ranks finish together (a monotone parameter sweep cut into contiguous blocks is not balanced:
+    cfg2 on 8 GPUs, slowest rank 13.0 ms against a median of 12.3).  "contiguous": the block of shard_range."""
+    if mode == "contiguous":
+        lo, hi = shard_range(B, world_size, rank)
+        return np.arange(lo, hi)
+    return np.arange(int(rank), int(B), int(world_size))
+
+
 def env_rank():
     """(rank, world_size, local_rank) from the torchrun environment (defaults: single process)."""
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),

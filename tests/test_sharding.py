@@ -70,3 +70,19 @@ def test_shard_ranges_partition_the_batch():
             assert r[0][0] == 0 and r[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert max(hi - lo for lo, hi in r) == -(-B // W)
+
+
+def test_strided_shards_partition_the_batch_and_balance_a_sweep():
+    """shard_indices: every instance belongs to exactly one rank, and a monotone per-instance cost (a parameter sweep) is
+    spread evenly -- which contiguous blocks do not do."""
+    import numpy as np
+    from skeelberzins_jl_b200.sharding import shard_indices
+    for B in (1, 7, 64, 4096, 4099):
+        for W in (1, 2, 3, 8):
+            for mode in ("strided", "contiguous"):
+                idx = np.concatenate([shard_indices(B, W, k, mode) for k in range(W)])
+                assert sorted(idx.tolist()) == list(range(B)), (B, W, mode)
+    cost = 500.0 + 100.0 * np.arange(4096) / 4096          # cfg2: 503..604 Newton iterations across the sweep
+    load = lambda mode: np.array([cost[shard_indices(4096, 8, k, mode)].sum() for k in range(8)])
+    assert load("strided").max() / load("strided").mean() < 1.001
+    assert load("contiguous").max() / load("contiguous").mean() > 1.05
