@@ -544,12 +544,13 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
         return fail(SB_ERR_PLUGIN, "nvrtcCreateProgram failed");
     for (const std::string& n : names) nvrtcAddNameExpression(prog, n.c_str());
     const std::string inc = "-I" + csrc_dir();
-    char d1[64], d2[64], d3[64];
+    char d1[64], d2[64], d3[64], d4[64];
     snprintf(d1, sizeof d1, "-DSB_TMA_STAGES=%d", (int)SB_TMA_STAGES);
     snprintf(d2, sizeof d2, "-DSB_PERSISTENT_WARPS_PER_SM=%d", (int)SB_PERSISTENT_WARPS_PER_SM);
     snprintf(d3, sizeof d3, "-DSB_PERSISTENT_WARPS_P2=%d", (int)SB_PERSISTENT_WARPS_P2);
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), d1, d2, d3};
-    const nvrtcResult r = nvrtcCompileProgram(prog, 7, opts);
+    snprintf(d4, sizeof d4, "-DSB_LONG_T0=%d", (int)SB_LONG_T0);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), d1, d2, d3, d4};
+    const nvrtcResult r = nvrtcCompileProgram(prog, 8, opts);
     if (r != NVRTC_SUCCESS) {
         size_t ls = 0;
         nvrtcGetProgramLogSize(prog, &ls);
@@ -632,17 +633,23 @@ int longmesh_setup(sb_problem* pb) {
     const int64_t B = pb->pd.B;
     std::vector<LevelDev> lv;
     int n = pb->pd.Nx;
+    int top_rows = kLongTopRows;
+    if (const char* e = getenv("SB_LONG_TOP_ROWS")) {   // testing: stored levels on meshes of moderate length
+        top_rows = std::max(kLongTT, std::min(kLongTopRows, atoi(e)));
+    }
     for (int l = 0;; ++l) {
         LevelDev L;
         memset(&L, 0, sizeof L);
         L.n = n;
-        const bool top = (l > 0 && n <= kLongTopRows);
+        const bool top = (l > 0 && n <= top_rows);
         if (top) { L.R = 1; while (L.R * kLongTT < n) L.R *= 2; }
         else L.R = (l == 0) ? kLongR : kLongRS;
         const int tt = (l == 0) ? kLongT0 : kLongTT;
         L.ntiles = (n + L.R * tt - 1) / (L.R * tt);
         L.stride = (size_t)L.ntiles * L.R * tt;
-        L.nchunks = L.ntiles * tt;                   // every chunk (padding chunks included) is a row of the next level
+        // rows of the next level: level 0 reduces every tile to one row inside its CTA; a stored level keeps one row
+        // per thread chunk (padding chunks included)
+        L.nchunks = (l == 0) ? L.ntiles : L.ntiles * tt;
         lv.push_back(L);
         if (top) break;
         n = L.nchunks;
@@ -916,10 +923,14 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     // per-interval interpolation weights (src/utils.jl:18-48) and flux weights, per-node volume weights
     // (src/assembler.jl:36,68-69,74,84,98), written straight in the [r][t] device layout
     const size_t L = pd.L;
-    // device image: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L] | ivol[L]
-    std::vector<double> mesh(9 * L, 0.0);
+    // device image: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L] | ivol[L] | xs[L]
+    std::vector<double> mesh(10 * L, 0.0);
     double *h_xi = &mesh[0], *h_awbw = &mesh[L], *h_gwwf = &mesh[3 * L], *h_frac = &mesh[5 * L], *h_gw = &mesh[7 * L],
-           *h_ivol = &mesh[8 * L];
+           *h_ivol = &mesh[8 * L], *h_xs = &mesh[9 * L];
+    for (size_t i = 0; i < L; ++i) {   // the mesh points themselves (padding: the mesh continued with its last spacing)
+        const size_t s = (i / (R * T)) * (R * T) + ((i % (R * T)) % R) * T + (i % (R * T)) / R;
+        h_xs[s] = (i < (size_t)Nx) ? xmesh[i] : xmesh[Nx - 1] + (double)(i - (Nx - 1)) * (xmesh[Nx - 1] - xmesh[Nx - 2]);
+    }
     for (int i = 0; i < Nx; ++i) {
         const size_t s = (size_t)(i / (R * T)) * (R * T) + (size_t)((i % (R * T)) % R) * T + (i % (R * T)) / R;
         double fR = 0.0, fL = 0.0;
@@ -943,7 +954,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     int rc = SB_OK;
     const size_t n = (size_t)B * L * pb->P;
 #define TRY(x) do { if (rc == SB_OK) rc = (x); } while (0)
-    TRY(dev_alloc(&pb->d_mesh, 9 * L));
+    TRY(dev_alloc(&pb->d_mesh, 10 * L));
     TRY(dev_alloc(&pb->d_prm, (size_t)B * std::max(pd.nprm_s, 2)));
     TRY(dev_alloc(&pb->d_u, n));
     TRY(dev_alloc(&pb->d_b, n));
@@ -971,7 +982,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
     for (int i = 0; i < 3 * kSlots; ++i) pb->h_count[i] = 0;
     cudaStream_t st = ctx->stream;
-    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 9 * L * sizeof(double), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 10 * L * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && f_nparams > 0)
         e = cudaMemcpy2DAsync(pb->d_prm, pd.nprm_s * sizeof(double), params, f_nparams * sizeof(double),
                               f_nparams * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, st);
@@ -999,6 +1010,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     pd.mesh.frac = reinterpret_cast<const double2*>(pb->d_mesh + 5 * L);
     pd.mesh.gw = pb->d_mesh + 7 * L;
     pd.mesh.ivol = pb->d_mesh + 8 * L;
+    pd.mesh.xs = pb->d_mesh + 9 * L;
     pd.prm = pb->d_prm; pd.u = pb->d_u; pd.b = pb->d_b; pd.F = pb->d_F; pd.mass = pb->d_mass;
     pd.active = pb->d_active; pd.iters = pb->d_iters; pd.total_iters = pb->d_total; pd.norm = pb->d_norm;
     pd.status = pb->d_status; pd.hist = nullptr; pd.hist_cap = 0; pd.active_count = pb->d_count;

@@ -33,6 +33,8 @@ struct MeshDev {           // [R][TT] each; interval j = (node j, node j+1) is s
                            // .y = (x_i^(m+1) - zeta_{i-1}^(m+1))/(m+1)  frac2, src/assembler.jl:69 (:98 for i=N-1)
     const double* gw;      // copy of gwwf.x (the only interval weight needed when m == 0)
     const double* ivol;    // 1/(frac1 + frac2): reciprocal control-volume weight of interior nodes (c == 1 functors)
+    const double* xs;      // the mesh points themselves in the same [r][t] layout (long-mesh path, m == 0: every weight
+                           // above is a few flops away from x, so the level-0 sweeps read 8 instead of 32 bytes per node)
 };
 
 // weight loads: through the read-only data path when the arrays are in global memory (GLOB), plain loads
@@ -590,13 +592,21 @@ struct IntervalRes {  // (c,f,s) of one interval; partials w.r.t. (u_left[0..P),
     double wf;
 };
 
-template <class Fn, int ND, bool SYM0, bool GLOB = true>
+// XW (m == 0 only): the interval's weights come from its two mesh points xl, xr instead of the weight arrays -- the
+// same expressions as the host set-up (sb_problem_create); the reciprocals are fast_rcp's (within an ulp of the host's
+// divisions; __drcp_rn would agree bit for bit at twice the instructions, measured 44 vs 35 us per cfg5 sweep).
+template <class Fn, int ND, bool SYM0, bool GLOB = true, bool XW = false>
 SB_D void eval_interval(const MeshDev& mesh, int slot, const double* ul, const double* ur, double tt, const double* prm,
-                        IntervalRes<Fn::npde, ND>& out) {
+                        IntervalRes<Fn::npde, ND>& out, double xl = 0.0, double xr = 0.0) {
     constexpr int P = Fn::npde;
-    const double xi = __ldg(mesh.xi + slot);  // always global; dead (and removed) when the functor ignores x
+    static_assert(!XW || SYM0, "weights from x: m == 0 only");
+    double xi;
+    if constexpr (XW) xi = (xl + xr) / 2;
+    else xi = __ldg(mesh.xi + slot);  // always global; dead (and removed) when the functor ignores x
     double aw, bw, gw;
-    if constexpr (SYM0) {  // m == 0: xi is the midpoint, linear interpolation, unit flux weight
+    if constexpr (XW) {
+        aw = 0.5; bw = 0.5; gw = fast_rcp(xr - xl); out.wf = 1.0;
+    } else if constexpr (SYM0) {  // m == 0: xi is the midpoint, linear interpolation, unit flux weight
         aw = 0.5; bw = 0.5; gw = ldw<GLOB>(mesh.gw, slot); out.wf = 1.0;
     } else {
         const double2 ab = ldw<GLOB>(mesh.awbw, slot), gf = ldw<GLOB>(mesh.gwwf, slot);
@@ -621,10 +631,11 @@ struct RowOut { Mat<P> A, Bm, C; Vec<P> d; };
 // Boundary rows (src/assembler.jl:36-57 left, :98-122 right).  side = 0: node 0 with I = interval 0;
 // side = 1: node Nx-1 with I = interval Nx-2.  ui/bi: u and b at the boundary node.
 // JAC: out = (Jl, Jd, Ju, F); !JAC: out.d = du.
-template <class Fn, bool JAC, int ND, bool GFRAC = true>
+// XW: the node's volume weight (frac1 at the left end, frac2 at the right end) is handed in as xfrac.
+template <class Fn, bool JAC, int ND, bool GFRAC = true, bool XW = false>
 SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* u0p, const double* uNp, const double* mass,
                        int side, double tt, double inv_tau, const double* prm, const IntervalRes<Fn::npde, ND>& I,
-                       const double* ui, const double* bi, int slot, RowOut<Fn::npde>& out) {
+                       const double* ui, const double* bi, int slot, RowOut<Fn::npde>& out, double xfrac = 0.0) {
     constexpr int P = Fn::npde;
     constexpr int PO = JAC ? P : 0;
     Dual<PO> ul_[P], ur_[P], pl[P], pr[P];
@@ -644,7 +655,8 @@ SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* u0p
         for (int q = 0; q < P; ++q) { dm[j][q] = 0.0; dc[j][q] = 0.0; dp[j][q] = 0.0; }
     }
     if (side == 0) {
-        const double frac = ldw<GFRAC>(mesh.frac, slot).x;
+        double frac;
+        if constexpr (XW) frac = xfrac; else frac = ldw<GFRAC>(mesh.frac, slot).x;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             mss[j] = mass[j];
@@ -688,7 +700,8 @@ SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* u0p
             }
         }
     } else {  // src/assembler.jl:98-122
-        const double frac = ldw<GFRAC>(mesh.frac, slot).y;
+        double frac;
+        if constexpr (XW) frac = xfrac; else frac = ldw<GFRAC>(mesh.frac, slot).y;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             mss[j] = mass[2 * P + j];
@@ -738,9 +751,11 @@ SB_D void boundary_row(const ProbDev& pd, const MeshDev& mesh, const double* u0p
 }
 
 // Sink concept: row(r, Jl, Jd, Ju, F) when JAC, value(r, du) otherwise.
-template <class Fn, int R, int TT, bool SYM0, bool JAC, bool GLOB = true, class Sink>
 // mesh: weight arrays (global or shared memory); ub/bb: this instance's u and b in device layout (global or
 // shared memory); mass: its 3*P mass flags; prm: its functor parameters.
+// XW (long-mesh path, m == 0): mesh.xs is the tile of mesh points (slots -1 .. R*TT valid where the mesh goes on) and
+// replaces gw, ivol and frac.
+template <class Fn, int R, int TT, bool SYM0, bool JAC, bool GLOB = true, bool XW = false, class Sink>
 SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* ub, const double* bb, const double* mass,
                          int t, double tt, double inv_tau, const double* prm, const double (&uc)[R][Fn::npde],
                          const double (&bc)[R][Fn::npde], Sink& sink, int i_base = 0, const double* u0p = nullptr,
@@ -773,18 +788,24 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
             bN[p] = JAC ? bb[(size_t)sN * P + p] : 0.0;
         }
         IntervalRes<P, ND> IN;
-        eval_interval<Fn, ND, SYM0, GLOB>(mesh, sM, uM, uN, tt, prm, IN);
-        boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN);
+        double xM = 0.0, xN = 0.0;
+        if constexpr (XW) { xM = mesh.xs[sM]; xN = mesh.xs[sN]; }
+        eval_interval<Fn, ND, SYM0, GLOB, XW>(mesh, sM, uM, uN, tt, prm, IN, xM, xN);
+        boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero)), XW>(pd, mesh, u0p, uNp, mass, 1, tt, inv_tau, prm, IN, uN, bN, sN, rowN,
+                                                                            xN - (xM + xN) / 2);
     }
 
     double un[P];  // first node of the next chunk
     IntervalRes<P, ND> Lr, Rr;
+    double x_prev = 0.0, x_cur = 0.0, x_next = 0.0;  // XW: mesh points around the current row
+    if constexpr (XW) x_cur = mesh.xs[t];
     if (i0 >= 1 && i0 - 1 <= Nx - 2) {
         double ul[P];
         const int slot = (t > 0) ? (R - 1) * TT + t - 1 : -1;  // t == 0: last node of the previous tile
 #pragma unroll
         for (int p = 0; p < P; ++p) ul[p] = ub[(ptrdiff_t)slot * P + p];
-        eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, ul, uc[0], tt, prm, Lr);
+        if constexpr (XW) x_prev = mesh.xs[slot];
+        eval_interval<Fn, ND, SYM0, GLOB, XW>(mesh, slot, ul, uc[0], tt, prm, Lr, x_prev, x_cur);
     } else {
 #pragma unroll
         for (int p = 0; p < P; ++p) { Lr.c[p] = Dual<ND>(1.0); Lr.f[p] = Dual<ND>(0.0); Lr.s[p] = Dual<ND>(0.0); }
@@ -800,14 +821,20 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
         const int i = i0 + r;
         const int slot = r * TT + t;
         // evaluated for every row: for i > Nx-2 the slot is padding (zeros) and the result is never used
-        eval_interval<Fn, ND, SYM0, GLOB>(mesh, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr);
+        if constexpr (XW) x_next = mesh.xs[(r + 1 < R) ? (r + 1) * TT + t : ((t + 1 < TT) ? t + 1 : R * TT)];
+        eval_interval<Fn, ND, SYM0, GLOB, XW>(mesh, slot, uc[r], (r + 1 < R) ? uc[r + 1] : un, tt, prm, Rr, x_cur, x_next);
         const double wR = SYM0 ? 1.0 : Rr.wf, wL = SYM0 ? 1.0 : Lr.wf;  // m == 0: unit flux weights, folded away
 
         // interior node, src/assembler.jl:60-95 (computed for every row; boundary / padding rows are replaced below)
         double frR = 0.0, frL = 0.0;
-        if constexpr (!(Fn::c_unit && Fn::s_zero)) { const double2 fr = ldw<GLOB>(mesh.frac, slot); frR = fr.x; frL = fr.y; }
         double ivol = 0.0;
-        if constexpr (Fn::c_unit) ivol = ldw<GLOB>(mesh.ivol, slot);
+        if constexpr (XW) {   // zeta = interval midpoints: frac1 = zeta_i - x_i, frac2 = x_i - zeta_{i-1} (m + 1 = 1)
+            frR = (x_cur + x_next) / 2 - x_cur; frL = x_cur - (x_prev + x_cur) / 2;
+            if constexpr (Fn::c_unit) ivol = fast_rcp(frR + frL);
+        } else {
+            if constexpr (!(Fn::c_unit && Fn::s_zero)) { const double2 fr = ldw<GLOB>(mesh.frac, slot); frR = fr.x; frL = fr.y; }
+            if constexpr (Fn::c_unit) ivol = ldw<GLOB>(mesh.ivol, slot);
+        }
         RowOut<P> row;
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -852,7 +879,8 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
             double b0[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) b0[p] = JAC ? bc[0][p] : 0.0;
-            boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero))>(pd, mesh, u0p, uNp, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row);
+            boundary_row<Fn, JAC, ND, (GLOB || (Fn::c_unit && Fn::s_zero)), XW>(pd, mesh, u0p, uNp, mass, 0, tt, inv_tau, prm, Rr, uc[0], b0, slot, row,
+                                                                                frR);
         }
         if (i >= Nx - 1) {  // right boundary node (prepared above) or padding (identity row)
             if (i == Nx - 1) row = rowN;
@@ -864,6 +892,7 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
         if constexpr (JAC) sink.row(r, row.A, row.Bm, row.C, row.d);
         else sink.value(r, row.d);
         Lr = Rr;
+        if constexpr (XW) { x_prev = x_cur; x_cur = x_next; }
     }
 }
 

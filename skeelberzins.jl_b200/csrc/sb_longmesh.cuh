@@ -21,7 +21,11 @@
 
 namespace sb {
 
-constexpr int kLongR = 8, kLongT0 = 64;   // level 0: rows per thread / threads per tile (tile = 512 mesh nodes; measured: 128 -> 137 us, 64 -> 134 us, 32 -> 136 us per cfg5 iteration)
+#ifndef SB_LONG_T0
+#define SB_LONG_T0 256
+#endif
+constexpr int kLongR = 8, kLongT0 = SB_LONG_T0;   // level 0: rows per thread / threads per tile (tile = 2048 mesh nodes = one row of the level above)
+constexpr int kLongCtasPerSM = 512 / kLongT0;     // level-0 kernels are compiled for 16 warps per SM (128 registers)
 constexpr int kLongTT = 256;              // stored levels and the top level: threads per tile
 constexpr int kLongRS = 16;               // stored levels (1 .. top-1): rows per thread = reduction factor per level
 
@@ -100,36 +104,95 @@ SB_D void form_rows(const LevelDev& below, int64_t k, int tile, int t, double (&
 // mesh weight pointers of one tile
 SB_D MeshDev mesh_of_tile(const MeshDev& m, size_t off) {
     MeshDev r = m;
-    r.xi += off; r.awbw += off; r.gwwf += off; r.frac += off; r.gw += off; r.ivol += off;
+    r.xi += off; r.awbw += off; r.gwwf += off; r.frac += off; r.gw += off; r.ivol += off; r.xs += off;
     return r;
 }
 
-// Shared-memory staging of one tile for the m == 0 kernels: u (with the edge nodes of the neighbouring tiles), b and
-// the mesh weights arrive by bulk copies behind one mbarrier, so a sweep pays the DRAM latency once instead of once
-// per row.  (m >= 1 needs 9 instead of 6 arrays per tile, which would leave one CTA per SM: those kernels keep
-// reading global memory directly.)
+// ---------------------------------------------------------------------------------------------------------------------
+// Open reduction of a group of N <= 32 consecutive chunks held one per lane (every lane of the warp calls; lanes >= N
+// carry nothing).  A chunk is known by its first-row representation and its separator row with the interior eliminated:
+//     x_first(l) = y0 - v0*s_{l-1} - w0*s_l            ar*s_{l-1} + bp*s_l + cs*x_first(l+1) = dp
+// (s_l = unknown of the chunk's last row; s_{-1} = S_prev, the separator of whatever precedes the group).  The group's
+// last separator S_last = s_{N-1} stays an unknown: rows 0 .. N-2 are reduced by parallel cyclic reduction in which an
+// elimination step that would reach outside the group is skipped, so the coefficient that is left multiplies S_prev /
+// S_last ("spikes" at no cost).  Afterwards
+//     s_l = dn - an*S_prev - cn*S_last                                                      (lanes l <= N-2)
+// and the group as a whole is a chunk of the same form -- (Y0, V0, W0) valid in lane 0, (AR, BP, DP) in lane N-1, cs
+// unchanged -- which is what the next level up consumes.  The backward sweep runs the same reduction again and turns
+// (S_prev, S_last) into the s_l.  Scalar rows (npde = 1).
+// ---------------------------------------------------------------------------------------------------------------------
+struct OpenRows { double an, cn, dn; };
+
+template <int N>
+SB_D OpenRows open_reduce(int lane, double y0, double v0, double w0, double ar, double bp, double cs, double dp,
+                          double& Y0, double& V0, double& W0, double& AR, double& BP, double& DP) {
+    constexpr unsigned FULL = 0xffffffffu;
+    double an = 0.0, cn = 0.0, dn = 0.0;
+    if constexpr (N > 1) {
+        // reduced row of lane l < N-1: the first row of chunk l+1 is eliminated with that chunk's representation
+        const double y0n = __shfl_down_sync(FULL, y0, 1), v0n = __shfl_down_sync(FULL, v0, 1), w0n = __shfl_down_sync(FULL, w0, 1);
+        if (lane < N - 1) {
+            const double binv = fast_rcp(fma(-cs, v0n, bp));
+            an = binv * ar; cn = -(binv * (cs * w0n)); dn = binv * fma(-cs, y0n, dp);
+        }
+#pragma unroll
+        for (int s = 1; s < N - 1; s <<= 1) {
+            const double am = __shfl_up_sync(FULL, an, s), cm = __shfl_up_sync(FULL, cn, s), dm = __shfl_up_sync(FULL, dn, s);
+            const double ap = __shfl_down_sync(FULL, an, s), cp = __shfl_down_sync(FULL, cn, s), dq = __shfl_down_sync(FULL, dn, s);
+            const bool hu = lane >= s, hd = lane + s <= N - 2;   // the partner row exists inside the group
+            const double anm = hu ? an : 0.0, cnp = hd ? cn : 0.0;
+            const double b2 = fma(-cnp, ap, fma(-anm, cm, 1.0));
+            const double d2 = fma(-cnp, dq, fma(-anm, dm, dn));
+            const double a2 = hu ? -(an * am) : an, c2 = hd ? -(cn * cp) : cn;
+            const double inv = fast_rcp(b2);
+            an = inv * a2; cn = inv * c2; dn = inv * d2;     // (lanes >= N-1 compute on, nobody reads them)
+        }
+    }
+    // the group as one chunk
+    Y0 = fma(-w0, dn, y0); V0 = fma(-w0, an, v0); W0 = -(w0 * cn);
+    if constexpr (N > 1) {
+        const double al = __shfl_up_sync(FULL, an, 1), cl = __shfl_up_sync(FULL, cn, 1), dl = __shfl_up_sync(FULL, dn, 1);
+        AR = -(ar * al); BP = fma(-ar, cl, bp); DP = fma(-ar, dl, dp);
+    } else {
+        Y0 = y0; V0 = v0; W0 = w0; AR = ar; BP = bp; DP = dp;
+    }
+    OpenRows o; o.an = an; o.cn = cn; o.dn = dn;
+    return o;
+}
+
+// separator of lane l (and of lane l-1) from the group's outer values
+template <int N>
+SB_D void open_back(int lane, const OpenRows& o, double S_prev, double S_last, double& xp, double& xs) {
+    xs = (lane < N - 1) ? fma(-o.cn, S_last, fma(-o.an, S_prev, o.dn)) : S_last;
+    const double up = __shfl_up_sync(0xffffffffu, xs, 1);
+    xp = (lane > 0) ? up : S_prev;
+}
+
+// Shared memory of the level-0 kernels.  m == 0: u (with the edge nodes of the neighbouring tiles), b and the mesh
+// points x of the tile arrive by bulk copies behind mbarriers, so a sweep pays the DRAM latency once instead of once per
+// row, and gw / ivol / frac are computed from x (8 instead of 32 bytes per node and sweep).  m >= 1 needs logarithms and
+// cube roots for that: those kernels keep reading the weight arrays from global memory and stage u only.
 template <class Fn, int R, int TT, bool SYM0>
 struct LongStage {
     static constexpr bool on = SYM0;
-    static constexpr int L = R * TT;
-    static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
-    static constexpr int oU = 2;                                  // [L + 4]: node slot s at oU + 2 + s, s = -2 .. L+1
+    static constexpr int L = R * TT, W = TT / 32;
+    static constexpr int oBar = 0;                                // two mbarriers (weights | state)
+    static constexpr int oRed = 2;                                // [W][8] warp summaries / [W + 2] separators on the way back
+    static constexpr int oU = oRed + 8 * W;                       // [L + 4]: node slot s at oU + 2 + s, s = -2 .. L+1
     static constexpr int oB = oU + L + 4;                         // [L]
-    static constexpr int oGw = oB + L;                            // [L + 2]: interval slot s at oGw + 2 + s, s = -2 .. L-1
-    static constexpr int oIvol = oGw + L + 2;                     // [L]   (c == 1 functors)
-    static constexpr int oFrac = oIvol + (Fn::c_unit ? L : 0);    // [2L]  (functors with c or s)
-    static constexpr int doubles = oFrac + (kFrac ? 2 * L : 0);
-    static constexpr size_t bytes = (on ? doubles : oB) * sizeof(double);   // m >= 1: the backward sweep stages u only
+    static constexpr int oX = oB + L;                             // [L + 4]: mesh point of slot s at oX + 2 + s
+    static constexpr int doubles = oX + L + 4;
+    static_assert(oU % 2 == 0 && oB % 2 == 0 && oX % 2 == 0, "bulk copies need 16-byte aligned destinations");
+    static constexpr size_t bytes = (on ? doubles : oB) * sizeof(double);   // m >= 1: u only
 };
 
-// Part 1, before pdl_wait(): barriers and the mesh weights, which no kernel ever writes -- this overlaps the tail of
+// Part 1, before pdl_wait(): barriers and the mesh points, which no kernel ever writes -- this overlaps the tail of
 // the previous kernel in the stream.  Part 2, after it: u and b of the tile.
 template <class Fn, int R, int TT>
-SB_D void long_stage_weights(const ProbDev& pd, int tile, double* sm, MeshDev& mesh) {
+SB_D void long_stage_mesh(const ProbDev& pd, int tile, double* sm, MeshDev& mesh) {
     using LS = LongStage<Fn, R, TT, true>;
     constexpr int L = LS::L;
-    constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // bar[0]: weights, bar[1]: state
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + LS::oBar);   // bar[0]: mesh points, bar[1]: state
     const size_t toff = (size_t)tile * L;
     if (threadIdx.x == 0) {
         mbar_init(bar + 0, 1);
@@ -139,22 +202,16 @@ SB_D void long_stage_weights(const ProbDev& pd, int tile, double* sm, MeshDev& m
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int lo = (tile > 0) ? 2 : 0;  // halo towards an existing neighbour
-        uint32_t bytes = (uint32_t)((L + lo) * sizeof(double));
-        if (Fn::c_unit) bytes += LB;
-        if (LS::kFrac) bytes += 2 * LB;
+        const int lo = (tile > 0) ? 2 : 0, hi = (tile + 1 < pd.ntiles) ? 2 : 0;  // halo towards an existing neighbour
+        const uint32_t bytes = (uint32_t)((L + lo + hi) * sizeof(double));
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(sm + LS::oGw + 2 - lo, pd.mesh.gw + toff - lo, (uint32_t)((L + lo) * sizeof(double)), bar);
-        if constexpr (Fn::c_unit) bulk_g2s(sm + LS::oIvol, pd.mesh.ivol + toff, LB, bar);
-        if constexpr (LS::kFrac) bulk_g2s(sm + LS::oFrac, pd.mesh.frac + toff, 2 * LB, bar);
+        bulk_g2s(sm + LS::oX + 2 - lo, pd.mesh.xs + toff - lo, bytes, bar);
     }
-    mesh = mesh_of_tile(pd.mesh, toff);  // xi (read only by functors that use x) stays in global memory
-    mesh.gw = sm + LS::oGw + 2;
-    if constexpr (Fn::c_unit) mesh.ivol = sm + LS::oIvol;
-    if constexpr (LS::kFrac) mesh.frac = reinterpret_cast<const double2*>(sm + LS::oFrac);
+    mesh = mesh_of_tile(pd.mesh, toff);  // (the weight arrays are not read by the m == 0 kernels)
+    mesh.xs = sm + LS::oX + 2;
 }
 
-// a CTA that turns out to have nothing to do must not exit with the weight copies in flight
+// a CTA that turns out to have nothing to do must not exit with the copy in flight
 SB_D void long_stage_drain(double* sm) {
     if (threadIdx.x == 0) mbar_wait(reinterpret_cast<uint64_t*>(sm), 0);
 }
@@ -165,7 +222,7 @@ SB_D void long_stage_state(const ProbDev& pd, int64_t k, int tile, bool use_b, b
     using LS = LongStage<Fn, R, TT, true>;
     constexpr int L = LS::L;
     constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + LS::oBar);
     const size_t toff = (size_t)tile * L;
     if (threadIdx.x == 0) {
         const int ulo = (halo_u && tile > 0) ? 2 : 0, uhi = (halo_u && tile + 1 < pd.ntiles) ? 2 : 0;
@@ -180,17 +237,75 @@ SB_D void long_stage_state(const ProbDev& pd, int64_t k, int tile, bool use_b, b
     mbar_wait(bar + 0, 0);
 }
 
-// level 0, forward: assemble + eliminate the chunk, store its summary
+// thread level -> the chunk's 7 numbers (what store_summary writes for the stored levels)
+template <int R>
+SB_D void chunk_numbers(const ChunkThomas<1, R>& th, double& y0, double& v0, double& w0, double& ar, double& bp, double& cs, double& dp) {
+    Vec<1> y0v, yL; Mat<1> v0m, w0m, vL, wL;
+    th.summary(y0v, v0m, w0m, yL, vL, wL);
+    const double As = th.As.a[0];
+    y0 = y0v.a[0]; v0 = v0m.a[0]; w0 = w0m.a[0];
+    ar = -(As * vL.a[0]); bp = fma(-As, wL.a[0], th.Bs.a[0]); cs = th.Cs.a[0]; dp = fma(-As, yL.a[0], th.ds.a[0]);
+}
+
+// Reduction of the TT chunks of a tile inside its CTA.  Every thread leaves its chunk's 7 numbers in shared memory; warp 0
+// alone turns them into reduced rows (as form_rows does for a stored level), TT/32 per lane, eliminates those with the
+// same partition (lvl2) and finishes with the open reduction across its 32 lanes.  The other warps wait at the barrier
+// -- their issue slots go to the other CTAs of the SM; an all-warps variant (open_reduce in every warp, then across the
+// warps) was measured at 44 / 50 us per cfg5 sweep.
+template <int TT>
+struct TileScratch {
+    static constexpr int Q = TT / 32;
+    static constexpr int S = TT + TT / 8 + 2;      // record j at pos(j) = j + j/8: lane q reads 8q+i -> stride 9, no bank conflicts
+    double rec[7][S];                              // y0, v0, w0, ar, bp, cs, dp
+    double sep[S];                                 // backward: [0] the separator before the tile, [pos(j) + 1] thread j's
+    static SB_D int pos(int j) { return j + (j >> 3); }
+};
+
+template <int TT>
+SB_D OpenRows tile_reduce_warp0(const TileScratch<TT>& ts, int lane, ChunkThomas<1, TT / 32>& lvl2, double& Y0, double& V0,
+                                double& W0, double& AR, double& BP, double& CS, double& DP) {
+    using TS = TileScratch<TT>;
+    constexpr int Q = TS::Q;
+    static_assert(Q >= 2, "tiles of at least 64 threads");
+    const int j0 = lane * Q;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int p = TS::pos(j0 + i), pn = TS::pos(j0 + i + 1);
+        const double ar = ts.rec[3][p], bp = ts.rec[4][p], cs = ts.rec[5][p], dp = ts.rec[6][p];
+        const double y0n = ts.rec[0][pn], v0n = ts.rec[1][pn], w0n = ts.rec[2][pn];   // chunk j+1: its first row is eliminated
+        const double binv = fast_rcp(fma(-cs, v0n, bp));
+        Mat<1> A, Bm, C; Vec<1> d;
+        A.a[0] = binv * ar; Bm.a[0] = 1.0; C.a[0] = -(binv * (cs * w0n)); d.a[0] = binv * fma(-cs, y0n, dp);
+        if (i == Q - 1 && lane == 31) {            // the tile's last chunk: its successor lives in the next tile
+            A.a[0] = ar; Bm.a[0] = bp; C.a[0] = cs; d.a[0] = dp;
+        }
+        lvl2.row(i, A, Bm, C, d);
+    }
+    double y0, v0, w0, ar, bp, cs, dp, Y1, V1, W1;
+    chunk_numbers<Q>(lvl2, y0, v0, w0, ar, bp, cs, dp);
+    const OpenRows rows = open_reduce<32>(lane, y0, v0, w0, ar, bp, cs, dp, Y1, V1, W1, AR, BP, DP);
+    CS = cs;
+    // lane 0: (Y1, V1, W1) represent the tile's first separator; the tile's first mesh row follows with thread 0's numbers
+    const double ty0 = ts.rec[0][0], tv0 = ts.rec[1][0], tw0 = ts.rec[2][0];
+    Y0 = fma(-tw0, Y1, ty0); V0 = fma(-tw0, V1, tv0); W0 = -(tw0 * W1);
+    return rows;
+}
+
+// level 0, forward: assemble + eliminate the chunk (thread), reduce the 32 chunks of a warp and the TT/32 warps of the
+// CTA to ONE summary per tile of R*TT mesh nodes: the level above has Nx / (R*TT) rows
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__(TT) k6_chunk_asm(ProbDev pd, double tt, double inv_tau, LevelDev lv) {
+__global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_chunk_asm(ProbDev pd, double tt, double inv_tau, LevelDev lv) {
     static_assert(Fn::npde == 1, "long-mesh path: scalar PDEs only");
+    using LS = LongStage<Fn, R, TT, SYM0>;
+    using TS = TileScratch<TT>;
     extern __shared__ __align__(16) double k6sm[];
-    const int tile = blockIdx.x, t = threadIdx.x;
+    __shared__ TS ts;
+    const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, wi = t >> 5;
     const int64_t k = blockIdx.y;
     const size_t toff = (size_t)tile * R * TT;
     MeshDev mesh;
     pdl_release();
-    if constexpr (SYM0) long_stage_weights<Fn, R, TT>(pd, tile, k6sm, mesh);
+    if constexpr (SYM0) long_stage_mesh<Fn, R, TT>(pd, tile, k6sm, mesh);
     else mesh = mesh_of_tile(pd.mesh, toff);
     pdl_wait();
     if (!pd.active[k]) {
@@ -216,10 +331,25 @@ __global__ void __launch_bounds__(TT) k6_chunk_asm(ProbDev pd, double tt, double
             if (i0 + r == pd.Nx - 1) e[2 * pd.ntiles + 1] = uc[r][0];
     }
     ChunkThomas<1, R> th;
-    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
-                                                 pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui,
-                                                 ui + tiled_pos(pd.Nx - 1, R, TT));
-    store_summary<R>(th, lv, k, tile * TT + t);
+    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
+                                                       pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui,
+                                                       ui + tiled_pos(pd.Nx - 1, R, TT));
+    double y0, v0, w0, ar, bp, cs, dp;
+    chunk_numbers<R>(th, y0, v0, w0, ar, bp, cs, dp);
+    {
+        const int p = TS::pos(t);
+        ts.rec[0][p] = y0; ts.rec[1][p] = v0; ts.rec[2][p] = w0; ts.rec[3][p] = ar; ts.rec[4][p] = bp; ts.rec[5][p] = cs; ts.rec[6][p] = dp;
+    }
+    __syncthreads();
+    if (wi == 0) {
+        ChunkThomas<1, TS::Q> lvl2;
+        double Y0, V0, W0, AR, BP, CS, DP;
+        tile_reduce_warp0<TT>(ts, lane, lvl2, Y0, V0, W0, AR, BP, CS, DP);
+        // one 64-byte record per tile, at the position of the row it becomes in the level above
+        double* S = reinterpret_cast<double*>(lv.sum + ((size_t)k * lv.up_stride + tiled_pos(tile, lv.up_R, kLongTT)) * 4);
+        if (lane == 0) { S[0] = Y0; S[1] = V0; S[2] = W0; }
+        if (lane == 31) { S[3] = AR; S[4] = BP; S[5] = CS; S[6] = DP; S[7] = 0.0; }
+    }
 }
 
 // level l >= 1, forward: form the level's rows, keep them, eliminate, store the chunk summary
@@ -302,18 +432,22 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
     for (int r = 0; r < R; ++r) lv.x[base + (size_t)r * TT + t] = x[r].a[0];
 }
 
-// level 0, backward: recompute, back-substitute, update u, per-tile sum of h^2
+// level 0, backward: recompute assembly, elimination and both reductions, pick up the tile's two outer separators from
+// the level above, back-substitute, u -= h in place, per-tile sum of h^2
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
-    __shared__ double red[TT / 32];
+__global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
+    using LS = LongStage<Fn, R, TT, SYM0>;
+    using TS = TileScratch<TT>;
+    constexpr int W = TT / 32;
+    __shared__ double red[W];
+    __shared__ TS ts;
     extern __shared__ __align__(16) double k6sm[];
-    const int tile = blockIdx.x, t = threadIdx.x;
+    const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, wi = t >> 5;
     const int64_t k = blockIdx.y;
     const size_t toff = (size_t)tile * R * TT;
-    using LS = LongStage<Fn, R, TT, SYM0>;
     MeshDev mesh;
     pdl_release();
-    if constexpr (SYM0) long_stage_weights<Fn, R, TT>(pd, tile, k6sm, mesh);
+    if constexpr (SYM0) long_stage_mesh<Fn, R, TT>(pd, tile, k6sm, mesh);
     else mesh = mesh_of_tile(pd.mesh, toff);
     pdl_wait();
     if (!pd.active[k]) {
@@ -338,15 +472,36 @@ __global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double 
     }
     if (t == 0 && tile > 0) k6sm[LS::oU + 1] = e[2 * (tile - 1) + 1];
     if (t == TT - 1 && tile + 1 < pd.ntiles) k6sm[LS::oU + 2 + R * TT] = e[2 * (tile + 1)];
-    if constexpr (!SYM0) __syncthreads();
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; ++r) { uc[r][0] = ub[r * TT + t]; bc[r][0] = use_b ? bb[r * TT + t] : 0.0; }
     ChunkThomas<1, R> th;
-    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
-                                                 pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff,
-                                                 e + 2 * pd.ntiles, e + 2 * pd.ntiles + 1);
+    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
+                                                       pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff,
+                                                       e + 2 * pd.ntiles, e + 2 * pd.ntiles + 1);
+    double y0, v0, w0, ar, bp, cs, dp;
+    chunk_numbers<R>(th, y0, v0, w0, ar, bp, cs, dp);
+    {
+        const int p = TS::pos(t);
+        ts.rec[0][p] = y0; ts.rec[1][p] = v0; ts.rec[2][p] = w0; ts.rec[3][p] = ar; ts.rec[4][p] = bp; ts.rec[5][p] = cs; ts.rec[6][p] = dp;
+    }
+    __syncthreads();
+    if (wi == 0) {
+        ChunkThomas<1, TS::Q> lvl2;
+        double Y0, V0, W0, AR, BP, CS, DP;
+        const OpenRows rows = tile_reduce_warp0<TT>(ts, lane, lvl2, Y0, V0, W0, AR, BP, CS, DP);
+        Vec<1> Sp, Ss, x2p, x2s, x2[TS::Q];
+        separators(up, k, tile, Sp, Ss);
+        open_back<32>(lane, rows, Sp.a[0], Ss.a[0], x2p.a[0], x2s.a[0]);
+        lvl2.back(x2, x2p, x2s);
+#pragma unroll
+        for (int i = 0; i < TS::Q; ++i) ts.sep[TS::pos(lane * TS::Q + i) + 1] = x2[i].a[0];
+        if (lane == 0) ts.sep[0] = Sp.a[0];
+    }
+    __syncthreads();
     Vec<1> xp, xs, h[R];
-    separators(up, k, tile * TT + t, xp, xs);
+    xs.a[0] = ts.sep[TS::pos(t) + 1];
+    xp.a[0] = (t > 0) ? ts.sep[TS::pos(t - 1) + 1] : ts.sep[0];
     th.back(h, xp, xs);
     double ss = 0.0;
 #pragma unroll
@@ -357,11 +512,11 @@ __global__ void __launch_bounds__(TT) k6_back_asm(ProbDev pd, double tt, double 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
-    if ((t & 31) == 0) red[t >> 5] = ss;
+    if (lane == 0) red[wi] = ss;
     __syncthreads();
     if (t == 0) {
 #pragma unroll
-        for (int w = 1; w < TT / 32; ++w) ss += red[w];
+        for (int w = 1; w < W; ++w) ss += red[w];
         partial[(size_t)k * pd.ntiles + tile] = ss;
     }
 }
