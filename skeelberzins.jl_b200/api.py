@@ -225,8 +225,9 @@ class DeviceProblem:
         self._h = h
         self.B, self.Nx, self.npde = functor.batch, x.size, functor.npde
         self.nparams, self.functor_id, self.m = functor.nparams, int(functor.id), int(m)
-        self._mesh_key = _mesh_fingerprint(x)
         self._mesh_copy = x.copy()
+        self._mesh_sample = _mesh_sample(self._mesh_copy).copy()
+        self._mesh_key = _mesh_fingerprint(x, self._mesh_sample)
         self.set_design(design)
 
     def close(self):
@@ -465,32 +466,35 @@ _MESH_EXACT_MAX = 1 << 16     # meshes up to this size are compared node by node
 
 
 def _mesh_sample(x):
-    """Evenly strided sample of a long mesh (64k points plus both ends): what pooled problems are matched on when an
-    exact comparison would cost more than the solve (a 2^22-node mesh: 5 ms for two passes, the solve takes 1 ms)."""
+    """Evenly strided sample of a long mesh (16k points plus 1024 at both ends): what pooled problems are matched on
+    when an exact comparison would cost more than the solve (a 2^22-node mesh: 5 ms for two passes over it, the solve
+    takes 0.6 ms).  A caller who changes a long mesh between the sampled points must not rely on the pool: pass
+    `return_device=True` / hold the DeviceProblem, or call clear_pool()."""
     if x.size <= _MESH_EXACT_MAX:
         return x
-    step = x.size // _MESH_EXACT_MAX
+    step = x.size // (1 << 14)
     return np.concatenate([x[:1024], x[::step], x[-1024:]])
 
 
-def _mesh_fingerprint(x):
+def _mesh_fingerprint(x, sample=None):
     """Cheap key of a mesh for the problem pool; a pooled problem is only reused after a comparison with its own copy
-    of the mesh (exact up to 65536 nodes, on a 64k-point sample beyond)."""
-    xs = _mesh_sample(x)
+    of the mesh (exact up to 65536 nodes, on the sample beyond)."""
+    xs = _mesh_sample(x) if sample is None else sample
     return (x.size, float(x[0]), float(x[-1]), float(xs.sum()), float(np.dot(xs, xs)))
 
 
-def _same_mesh(a, b):
-    return a.size == b.size and np.array_equal(_mesh_sample(a), _mesh_sample(b))
+def _same_mesh(dev, x, sample):
+    return dev._mesh_copy.size == x.size and np.array_equal(dev._mesh_sample, sample)
 
 
-def _pool_key(ctx, m, x, functor):
-    return (id(ctx), int(m), int(functor.id), functor.batch, _mesh_fingerprint(x))
+def _pool_key(ctx, m, x, functor, sample=None):
+    return (id(ctx), int(m), int(functor.id), functor.batch, _mesh_fingerprint(x, sample))
 
 
 def _acquire(ctx, m, x, functor, design):
-    lst = _pool.get(_pool_key(ctx, m, x, functor))
-    if lst and _same_mesh(lst[-1]._mesh_copy, x):
+    sample = _mesh_sample(x)                     # taken once per call: key and comparison both use it
+    lst = _pool.get(_pool_key(ctx, m, x, functor, sample))
+    if lst and _same_mesh(lst[-1], x, sample):
         dev = lst.pop()
         dev.set_params(functor.params)
         dev.set_design(design)

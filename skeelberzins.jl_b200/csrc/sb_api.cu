@@ -671,8 +671,10 @@ int longmesh_setup(sb_problem* pb) {
         }
         if (l + 1 < lv.size()) { lv[l].sum = reinterpret_cast<double2*>(p); p += 8 * lv[l].up_stride * B; }
     }
-    CU(guarded_malloc((void**)&pb->d_partial, (size_t)B * (3 * pb->pd.ntiles + 2) * sizeof(double)));  // per-tile sums | edge copies
+    // per-tile sums | edge copies | the chunks' separator coefficients
+    CU(guarded_malloc((void**)&pb->d_partial, (size_t)B * ((3 + 3 * kLongT0) * (size_t)pb->pd.ntiles + 2) * sizeof(double)));
     lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;
+    lv[0].coef = lv[1].coef = pb->d_partial + (size_t)B * (3 * (size_t)pb->pd.ntiles + 2);
     pb->lv = lv;
     pb->top_R = lv.back().R;
     return SB_OK;
@@ -692,11 +694,9 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
     std::vector<LevelDev>& lv = pb->lv;
     const int top = (int)lv.size() - 1;
     const size_t smem = pb->ks.long_smem;
-    if (!pb->ks.long_configured) {  // one-time opt-in to the staged tiles' shared memory
-        if (smem > 48 * 1024) {
-            CU(cudaFuncSetAttribute(pb->ks.long_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(pb->ks.long_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+    if (!pb->ks.long_configured) {  // one-time opt-in to the staged tiles' shared memory (static + dynamic may exceed 48 KB)
+        CU(cudaFuncSetAttribute(pb->ks.long_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64)));
+        CU(cudaFuncSetAttribute(pb->ks.long_back, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64)));
         pb->ks.long_configured = true;
     }
     // every kernel of the sequence is launched with programmatic stream serialization: launch latency and the

@@ -22,9 +22,9 @@
 namespace sb {
 
 #ifndef SB_LONG_T0
-#define SB_LONG_T0 256
+#define SB_LONG_T0 128
 #endif
-constexpr int kLongR = 8, kLongT0 = SB_LONG_T0;   // level 0: rows per thread / threads per tile (tile = 2048 mesh nodes = one row of the level above)
+constexpr int kLongR = 8, kLongT0 = SB_LONG_T0;   // level 0: rows per thread / threads per tile (tile = 1024 mesh nodes = one row of the level above; measured: 256 threads 87 us, 128 threads 80 us per cfg5 iteration)
 constexpr int kLongCtasPerSM = 512 / kLongT0;     // level-0 kernels are compiled for 16 warps per SM (128 registers)
 constexpr int kLongTT = 256;              // stored levels and the top level: threads per tile
 constexpr int kLongRS = 16;               // stored levels (1 .. top-1): rows per thread = reduction factor per level
@@ -43,6 +43,9 @@ struct LevelDev {      // one level of the recursive partition (level 0 has no s
                        // record per chunk (two full sectors), so the scattered positions cost no write amplification
     size_t up_stride;  // stride of the next level
     int up_R;          // R of the next level
+    double* coef;      // level 0 only: [B][ntiles][3][T0] every thread chunk's separator as a function of its tile's two
+                       // outer separators, s_j = D_j - A_j*S_prev - C_j*S_tile, left by the forward sweep so that the
+                       // backward sweep needs no reduction (and no barrier) of its own
     double* edge;      // levels 0 and 1 only: [B][2*ntiles0 + 2] iterate at the first / last node of every level-0 tile
                        // and at mesh nodes 0 and Nx-1, saved by the forward sweep so that the backward sweep can
                        // update u in place (a tile's neighbours may already hold the new iterate)
@@ -291,6 +294,32 @@ SB_D OpenRows tile_reduce_warp0(const TileScratch<TT>& ts, int lane, ChunkThomas
     return rows;
 }
 
+// Every chunk's separator in terms of the tile's outer separators: s_j = D_j - A_j*S_prev - C_j*S_tile, j = lane*Q + i.
+// (lvl2 in explicit form gives x_i = y_i - v_i*xp - w_i*xs inside the lane's chunk; xp, xs are the open rows of lanes
+// lane-1 and lane.)  cf: the tile's [3][TT] block of LevelDev::coef.
+template <int TT>
+SB_D void tile_coefficients(ChunkThomas<1, TT / 32>& lvl2, const OpenRows& rows, int lane, double* cf) {
+    constexpr int Q = TT / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    // xs = Xd - Xa*S_prev - Xc*S_tile (lane 31: S_tile itself), xp likewise from the lane before (lane 0: S_prev itself)
+    const double Xd = (lane < 31) ? rows.dn : 0.0, Xa = (lane < 31) ? rows.an : 0.0, Xc = (lane < 31) ? rows.cn : -1.0;
+    const double ud = __shfl_up_sync(FULL, Xd, 1), ua = __shfl_up_sync(FULL, Xa, 1), uc = __shfl_up_sync(FULL, Xc, 1);
+    const double Pd = (lane > 0) ? ud : 0.0, Pa = (lane > 0) ? ua : -1.0, Pc = (lane > 0) ? uc : 0.0;
+    lvl2.to_explicit();
+    const int j0 = lane * Q;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        double D = Xd, A = Xa, C = Xc;
+        if (i < Q - 1) {
+            const double y = lvl2.dt[i].a[0], v = lvl2.vt[i].a[0], w = lvl2.ct[i].a[0];
+            D = fma(-w, Xd, fma(-v, Pd, y));
+            A = -fma(w, Xa, v * Pa);
+            C = -fma(w, Xc, v * Pc);
+        }
+        cf[j0 + i] = D; cf[TT + j0 + i] = A; cf[2 * TT + j0 + i] = C;
+    }
+}
+
 // level 0, forward: assemble + eliminate the chunk (thread), reduce the 32 chunks of a warp and the TT/32 warps of the
 // CTA to ONE summary per tile of R*TT mesh nodes: the level above has Nx / (R*TT) rows
 template <class Fn, int R, int TT, bool SYM0>
@@ -344,11 +373,13 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_chunk_asm(ProbDev pd, d
     if (wi == 0) {
         ChunkThomas<1, TS::Q> lvl2;
         double Y0, V0, W0, AR, BP, CS, DP;
-        tile_reduce_warp0<TT>(ts, lane, lvl2, Y0, V0, W0, AR, BP, CS, DP);
+        const OpenRows rows = tile_reduce_warp0<TT>(ts, lane, lvl2, Y0, V0, W0, AR, BP, CS, DP);
         // one 64-byte record per tile, at the position of the row it becomes in the level above
         double* S = reinterpret_cast<double*>(lv.sum + ((size_t)k * lv.up_stride + tiled_pos(tile, lv.up_R, kLongTT)) * 4);
         if (lane == 0) { S[0] = Y0; S[1] = V0; S[2] = W0; }
         if (lane == 31) { S[3] = AR; S[4] = BP; S[5] = CS; S[6] = DP; S[7] = 0.0; }
+        // and, for the backward sweep, what every chunk's separator will be once the tile's outer separators are known
+        tile_coefficients<TT>(lvl2, rows, lane, lv.coef + ((size_t)k * pd.ntiles + tile) * 3 * TT);
     }
 }
 
@@ -432,15 +463,15 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
     for (int r = 0; r < R; ++r) lv.x[base + (size_t)r * TT + t] = x[r].a[0];
 }
 
-// level 0, backward: recompute assembly, elimination and both reductions, pick up the tile's two outer separators from
-// the level above, back-substitute, u -= h in place, per-tile sum of h^2
+// level 0, backward: recompute assembly and elimination of the chunk, take the chunk's separators from the coefficients
+// the forward sweep left and the tile's two outer separators from the level above, back-substitute, u -= h in place,
+// per-tile sum of h^2.  No reduction and no barrier between the assembly and the update.
 template <class Fn, int R, int TT, bool SYM0>
 __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
     using LS = LongStage<Fn, R, TT, SYM0>;
-    using TS = TileScratch<TT>;
     constexpr int W = TT / 32;
     __shared__ double red[W];
-    __shared__ TS ts;
+    __shared__ double outer[2];          // the separator before the tile, the tile's own
     extern __shared__ __align__(16) double k6sm[];
     const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, wi = t >> 5;
     const int64_t k = blockIdx.y;
@@ -462,6 +493,16 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, do
     // tile (the neighbours' edge nodes, both mesh ends for the boundary conditions) comes from the copy the
     // forward sweep saved in `edge`.
     const double* e = up.edge + (size_t)k * (2 * pd.ntiles + 2);
+    if (t == 32 % TT) {                  // (a thread that does not issue the copies)
+        Vec<1> Sp, Ss;
+        separators(up, k, tile, Sp, Ss);
+        outer[0] = Sp.a[0]; outer[1] = Ss.a[0];
+    }
+    // chunk t and chunk t-1: s = D - A*S_prev - C*S_tile (written by this iteration's forward sweep: L2, not the read-only path)
+    const double* cf = up.coef + ((size_t)k * pd.ntiles + tile) * 3 * TT;
+    const int tm = (t > 0) ? t - 1 : 0;
+    const double cD = __ldcg(cf + t), cA = __ldcg(cf + TT + t), cC = __ldcg(cf + 2 * TT + t);
+    const double pD = __ldcg(cf + tm), pA = __ldcg(cf + TT + tm), pC = __ldcg(cf + 2 * TT + tm);
     double uc[R][1], bc[R][1];
     if constexpr (SYM0) {
         long_stage_state<Fn, R, TT>(pd, k, tile, use_b, false, k6sm, ub, bb);
@@ -479,29 +520,10 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, do
     assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
                                                        pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff,
                                                        e + 2 * pd.ntiles, e + 2 * pd.ntiles + 1);
-    double y0, v0, w0, ar, bp, cs, dp;
-    chunk_numbers<R>(th, y0, v0, w0, ar, bp, cs, dp);
-    {
-        const int p = TS::pos(t);
-        ts.rec[0][p] = y0; ts.rec[1][p] = v0; ts.rec[2][p] = w0; ts.rec[3][p] = ar; ts.rec[4][p] = bp; ts.rec[5][p] = cs; ts.rec[6][p] = dp;
-    }
-    __syncthreads();
-    if (wi == 0) {
-        ChunkThomas<1, TS::Q> lvl2;
-        double Y0, V0, W0, AR, BP, CS, DP;
-        const OpenRows rows = tile_reduce_warp0<TT>(ts, lane, lvl2, Y0, V0, W0, AR, BP, CS, DP);
-        Vec<1> Sp, Ss, x2p, x2s, x2[TS::Q];
-        separators(up, k, tile, Sp, Ss);
-        open_back<32>(lane, rows, Sp.a[0], Ss.a[0], x2p.a[0], x2s.a[0]);
-        lvl2.back(x2, x2p, x2s);
-#pragma unroll
-        for (int i = 0; i < TS::Q; ++i) ts.sep[TS::pos(lane * TS::Q + i) + 1] = x2[i].a[0];
-        if (lane == 0) ts.sep[0] = Sp.a[0];
-    }
-    __syncthreads();
+    const double Sp = outer[0], St = outer[1];
     Vec<1> xp, xs, h[R];
-    xs.a[0] = ts.sep[TS::pos(t) + 1];
-    xp.a[0] = (t > 0) ? ts.sep[TS::pos(t - 1) + 1] : ts.sep[0];
+    xs.a[0] = fma(-cC, St, fma(-cA, Sp, cD));
+    xp.a[0] = (t > 0) ? fma(-pC, St, fma(-pA, Sp, pD)) : Sp;
     th.back(h, xp, xs);
     double ss = 0.0;
 #pragma unroll

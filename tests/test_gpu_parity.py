@@ -249,7 +249,7 @@ def test_frozen_instances_and_c_loop(ctx, oracle):
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Nx", [21, 2049, 5000, 70001])
 def test_longmesh_stationary_vs_oracle(ctx, oracle, monkeypatch, Nx):
-    """Example105 (stationary nonlinear diffusion) through the long-mesh kernels: 1, 2, 3 and 35 tiles of 2048 nodes
+    """Example105 (stationary nonlinear diffusion) through the long-mesh kernels: 1, 3, 5 and 69 tiles of 1024 nodes
     (forced onto the long path also where a single CTA would do); every tile is one row of the top level."""
     monkeypatch.setenv("SB_FORCE_LONGMESH", "1")
     c = ex.example105(Nx)
@@ -266,7 +266,7 @@ def test_longmesh_stored_levels(ctx, oracle, monkeypatch):
     """A mesh with more tiles than the top level takes rows (the limit is lowered from 4096 to 256 for the test): the
     tile summaries go through a stored level (k6_chunk_sys / k6_back_sys) before the top."""
     monkeypatch.setenv("SB_LONG_TOP_ROWS", "256")
-    Nx = 600001                                    # 293 tiles > 256
+    Nx = 600001                                    # 586 tiles > 256
     c = ex.example105(Nx)
     fn = sb.Functor(c.functor, c.params)
     u, hist = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, ctx=ctx, hist=True)
