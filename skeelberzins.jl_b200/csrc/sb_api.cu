@@ -1532,8 +1532,8 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
     const ProbDev& pd = pb->pd;
     const int64_t B = pd.B;
     const bool b_given = (tgrid == nullptr && inst_tgrid == nullptr);
-    const int G = pb->warp ? kWarpBlockThreads / 32 : 1;
-    const unsigned threads = pb->warp ? kWarpBlockThreads : (unsigned)pd.T;
+    const int G = resident_groups(pd.T);
+    const unsigned threads = (unsigned)(G * pd.T);
     if (pb->r_grid == 0) {
         CU(cudaFuncSetAttribute(pb->ks.resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->ks.resident_smem));
         int occ = 0, sms = 0;

@@ -153,6 +153,15 @@ template <int P> SB_D Mat<P> inverse_fast(const Mat<P>& A) {
     }
 }
 
+// Barrier of the TT threads that own a system: a warp (TT == 32), the whole CTA (bar == 0), or -- when a CTA holds
+// several systems of TT > 32 threads each (the whole-solve kernel at TT == 64) -- the named barrier `bar` (1 .. 15)
+// with TT participants.
+template <int TT> SB_D void group_sync(int bar = 0) {
+    if constexpr (TT == 32) __syncwarp();
+    else if (bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(TT) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Partitioned block-Thomas ("SPIKE"-type) elimination of one block-tridiagonal system.
 // Rows arrive one by one (row(r, A, B, C, d): A x_{i-1} + B x_i + C x_{i+1} = d).  The thread
@@ -290,7 +299,7 @@ struct ChunkThomas {
     struct NoHook { SB_D void operator()() const {} };
 
     template <int TT>
-    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t) { return finish<TT>(x, sm, t, NoHook()); }
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, int bar = 0) { return finish<TT>(x, sm, t, NoHook(), bar); }
 
     // Solve.  x[r] = unknowns of the thread's rows, t = thread index inside the system, sm = exch_doubles<TT>() doubles.
     // hook(): called by every thread right after the first synchronisation point (TT == 32: after the first shuffle),
@@ -309,17 +318,18 @@ struct ChunkThomas {
     //    a redundant elimination through the TT/32 warps: one barrier instead of three, no idle warp, but 914
     //    instructions.  Per-iteration launches (k_newton_fused_p): same speed (35.5 vs 35.1 us per cfg2 launch, barrier
     //    stall 1.4 vs 3.7 per issue).  Whole-solve kernel: 13.5 ms vs 11.8 ms per cfg2 solve -- instructions win.
+    // bar: the barrier of the system's threads (group_sync)
     template <int TT, class Hook>
-    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+    SB_D bool finish(Vec<P> (&x)[R], double* sm, int t, Hook hook, int bar = 0) {
 #ifndef SB_FINISH_PARALLEL
-        if constexpr (TT > 32) return finish_serial<TT>(x, sm, t, hook);
+        if constexpr (TT > 32) return finish_serial<TT>(x, sm, t, hook, bar);
         else
 #endif
-        return finish_parallel<TT>(x, sm, t, hook);
+        return finish_parallel<TT>(x, sm, t, hook, bar);
     }
 
     template <int TT, class Hook>
-    SB_D bool finish_serial(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+    SB_D bool finish_serial(Vec<P> (&x)[R], double* sm, int t, Hook hook, int bar = 0) {
         constexpr int W = TT / 32;
         const int lane = t & 31, wi = t >> 5;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
@@ -356,7 +366,7 @@ struct ChunkThomas {
             if (lane == 0) monw[wi] = g;
         }
 #endif
-        __syncthreads();
+        group_sync<TT>(bar);
         hook();
         if (t < 32) {
             ChunkThomas<P, Q> lvl2;
@@ -395,7 +405,7 @@ struct ChunkThomas {
                 monw[2 * W] = g;
             }
         }
-        __syncthreads();
+        group_sync<TT>(bar);
         Vec<P> xs, xp;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
@@ -422,7 +432,7 @@ struct ChunkThomas {
     //     after the barrier every thread eliminates through the TT/32 warps (a few dozen flops) and keeps the two
     //     values its own warp needs.
     template <int TT, class Hook>
-    SB_D bool finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook) {
+    SB_D bool finish_parallel(Vec<P> (&x)[R], double* sm, int t, Hook hook, int bar = 0) {
         constexpr int W = TT / 32;
         const int lane = t & 31;
         Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
@@ -503,7 +513,7 @@ struct ChunkThomas {
                 for (int w = 0; w < NW; ++w) eq[NW + w] = mine[w];
                 reinterpret_cast<unsigned*>(sm + 2 * NW * W)[2 * wi] = grow;
             }
-            __syncthreads();
+            group_sync<TT>(bar);
             hook();
 #pragma unroll
             for (int w = 0; w < W; ++w) grow = max(grow, reinterpret_cast<const unsigned*>(sm + 2 * NW * W)[2 * w]);
@@ -972,7 +982,6 @@ SB_D void update_and_test(const ProbDev& pd, int64_t k, int t, const double (&uc
 // right), every thread picks up the unknowns of its rows.  status[k] = 3 records that the fallback ran (2: the matrix
 // is singular even with pivoting).
 // ---------------------------------------------------------------------------------------------
-template <int TT> SB_D void group_sync() { if constexpr (TT == 32) __syncwarp(); else __syncthreads(); }
 
 SB_D int piv_acquire(const ProbDev& pd, int start) {
     int s = start % pd.piv_slots;
@@ -990,19 +999,19 @@ SB_D void piv_release(const ProbDev& pd, int s) {
 
 // slot for this thread group (taken by its thread 0, made known to all) and a zeroed band
 template <int P, int TT>
-SB_D int piv_begin(const ProbDev& pd, int t, int group, volatile int* sh_slot) {
+SB_D int piv_begin(const ProbDev& pd, int t, int group, volatile int* sh_slot, int bar = 0) {
     int s = 0;
     if (t == 0) s = piv_acquire(pd, group);
     if constexpr (TT == 32) s = __shfl_sync(0xffffffffu, s, 0);
     else {
         if (t == 0) *sh_slot = s;
-        __syncthreads();
+        group_sync<TT>(bar);
         s = *sh_slot;
     }
     double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
     const int n = pd.Nx * P * BandShape<P>::ldab;
     for (int i = t; i < n; i += TT) ab[i] = 0.0;
-    group_sync<TT>();
+    group_sync<TT>(bar);
     return s;
 }
 
@@ -1027,16 +1036,16 @@ struct BandSink {   // row sink of assemble_chunk: block rows into LAPACK band s
 
 // band complete -> solve (thread 0) -> h of this thread's rows; releases the slot
 template <int P, int R, int TT>
-SB_D bool piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P]) {
+SB_D bool piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P], int bar = 0) {
     double* ab = pd.piv_band + (size_t)s * pd.piv_stride;
     double* rhs = ab + (size_t)pd.Nx * P * BandShape<P>::ldab;
-    group_sync<TT>();
+    group_sync<TT>(bar);
     if (t == 0) {
         const int info = banded_lu_solve<BandShape<P>::kl, BandShape<P>::ku, volatile double*>(ab, pd.Nx * P, rhs);
         if (info) rhs[0] = __longlong_as_double(0x7ff8000000000000LL);   // singular even with pivoting: a NaN everybody sees
         if (info || pd.status[k] != 2) pd.status[k] = info ? 2 : 3;
     }
-    group_sync<TT>();
+    group_sync<TT>(bar);
     const bool singular = !(__ldcg(rhs) == __ldcg(rhs));
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -1045,7 +1054,7 @@ SB_D bool piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P
             const int i = t * R + r;
             h[r][p] = (i < pd.Nx) ? __ldcg(rhs + (size_t)i * P + p) : 0.0;
         }
-    group_sync<TT>();
+    group_sync<TT>(bar);
     if (t == 0) piv_release(pd, s);
     return singular;
 }
@@ -1055,9 +1064,9 @@ SB_D bool piv_solve(const ProbDev& pd, int64_t k, int t, int s, double (&h)[R][P
 template <class Fn, int R, int TT, bool SYM0, bool GLOB>
 __device__ __noinline__ bool pivoted_newton_rows(ProbDev pd, MeshDev mesh, long long k, const double* ub, const double* bb,
                                                  int t, int group, double tt, double inv_tau, volatile int* sh_slot,
-                                                 double (&h)[R][Fn::npde]) {
+                                                 double (&h)[R][Fn::npde], int bar = 0) {
     constexpr int P = Fn::npde;
-    const int s = piv_begin<P, TT>(pd, t, group, sh_slot);
+    const int s = piv_begin<P, TT>(pd, t, group, sh_slot, bar);
     double uc[R][P], bc[R][P];
     load_chunk<P, R, TT>(ub, t, uc);
     load_chunk<P, R, TT>(bb, t, bc);
@@ -1065,7 +1074,7 @@ __device__ __noinline__ bool pivoted_newton_rows(ProbDev pd, MeshDev mesh, long 
     BandSink<P> sink{ab, ab + (size_t)pd.Nx * P * BandShape<P>::ldab, t * R, pd.Nx};
     assemble_chunk<Fn, R, TT, SYM0, true, GLOB>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
                                                pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink);
-    return piv_solve<P, R, TT>(pd, k, t, s, h);
+    return piv_solve<P, R, TT>(pd, k, t, s, h, bar);
 }
 
 // the fallback for the split design: the rows are already in HBM (Jl, Jd, Ju, F)

@@ -214,14 +214,18 @@ SB_D void long_stage_mesh(const ProbDev& pd, int tile, double* sm, MeshDev& mesh
     mesh.xs = sm + LS::oX + 2;
 }
 
-// a CTA that turns out to have nothing to do must not exit with the copy in flight
+// a CTA that turns out to have nothing to do must not exit with its copies in flight
 SB_D void long_stage_drain(double* sm) {
-    if (threadIdx.x == 0) mbar_wait(reinterpret_cast<uint64_t*>(sm), 0);
+    if (threadIdx.x == 0) {
+        mbar_wait(reinterpret_cast<uint64_t*>(sm), 0);
+        mbar_wait(reinterpret_cast<uint64_t*>(sm) + 1, 0);
+    }
 }
 
+// u and b of the tile: issued right after pdl_wait(), before anything that depends on a global load, so that the
+// latencies of the copy and of the per-instance loads (active flag, parameters, mass flags) overlap
 template <class Fn, int R, int TT>
-SB_D void long_stage_state(const ProbDev& pd, int64_t k, int tile, bool use_b, bool halo_u, double* sm,
-                           const double*& ub, const double*& bb) {
+SB_D void long_stage_state_issue(const ProbDev& pd, int64_t k, int tile, bool use_b, bool halo_u, double* sm) {
     using LS = LongStage<Fn, R, TT, true>;
     constexpr int L = LS::L;
     constexpr uint32_t LB = (uint32_t)(L * sizeof(double));
@@ -234,11 +238,31 @@ SB_D void long_stage_state(const ProbDev& pd, int64_t k, int tile, bool use_b, b
         bulk_g2s(sm + LS::oU + 2 - ulo, pd.u + (size_t)k * pd.L + toff - ulo, ubytes, bar + 1);
         if (use_b) bulk_g2s(sm + LS::oB, pd.b + (size_t)k * pd.L + toff, LB, bar + 1);
     }
+}
+template <class Fn, int R, int TT>
+SB_D void long_stage_state_wait(bool use_b, double* sm, const double*& ub, const double*& bb) {
+    using LS = LongStage<Fn, R, TT, true>;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + LS::oBar);
     ub = sm + LS::oU + 2;
     bb = use_b ? sm + LS::oB : ub;       // tau = Inf: b is multiplied by 1/tau = 0 wherever it is still named
     mbar_wait(bar + 1, 0);
     mbar_wait(bar + 0, 0);
 }
+
+// parameters and mass flags of the instance -> registers (asked for early: see long_stage_state_issue)
+template <class Fn>
+struct InstanceRegs {
+    static constexpr int NP = Fn::nparams > 0 ? Fn::nparams : 1;
+    double prm[NP], mass[4];
+    int active;
+    SB_D void load(const ProbDev& pd, int64_t k) {
+        active = pd.active[k];
+#pragma unroll
+        for (int i = 0; i < Fn::nparams; ++i) prm[i] = pd.prm[(size_t)k * pd.nprm_s + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mass[i] = pd.mass[(size_t)k * 4 + i];
+    }
+};
 
 // thread level -> the chunk's 7 numbers (what store_summary writes for the stored levels)
 template <int R>
@@ -337,15 +361,18 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_chunk_asm(ProbDev pd, d
     if constexpr (SYM0) long_stage_mesh<Fn, R, TT>(pd, tile, k6sm, mesh);
     else mesh = mesh_of_tile(pd.mesh, toff);
     pdl_wait();
-    if (!pd.active[k]) {
+    const bool use_b = inv_tau != 0.0;  // stationary solves (tau = Inf) never look at b: rhs - b/tau = rhs
+    if constexpr (SYM0) long_stage_state_issue<Fn, R, TT>(pd, k, tile, use_b, true, k6sm);
+    InstanceRegs<Fn> in;
+    in.load(pd, k);
+    if (!in.active) {
         if constexpr (SYM0) long_stage_drain(k6sm);
         return;
     }
     const double* ui = pd.u + (size_t)k * pd.L;
     const double* ub = ui + toff;
     const double* bb = pd.b + (size_t)k * pd.L + toff;
-    const bool use_b = inv_tau != 0.0;  // stationary solves (tau = Inf) never look at b: rhs - b/tau = rhs
-    if constexpr (SYM0) long_stage_state<Fn, R, TT>(pd, k, tile, use_b, true, k6sm, ub, bb);
+    if constexpr (SYM0) long_stage_state_wait<Fn, R, TT>(use_b, k6sm, ub, bb);
     double uc[R][1], bc[R][1];
 #pragma unroll
     for (int r = 0; r < R; ++r) { uc[r][0] = ub[r * TT + t]; bc[r][0] = use_b ? bb[r * TT + t] : 0.0; }
@@ -360,8 +387,7 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_chunk_asm(ProbDev pd, d
             if (i0 + r == pd.Nx - 1) e[2 * pd.ntiles + 1] = uc[r][0];
     }
     ChunkThomas<1, R> th;
-    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
-                                                       pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui,
+    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, in.mass, t, tt, inv_tau, in.prm, uc, bc, th, (int)toff, ui,
                                                        ui + tiled_pos(pd.Nx - 1, R, TT));
     double y0, v0, w0, ar, bp, cs, dp;
     chunk_numbers<R>(th, y0, v0, w0, ar, bp, cs, dp);
@@ -481,14 +507,17 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, do
     if constexpr (SYM0) long_stage_mesh<Fn, R, TT>(pd, tile, k6sm, mesh);
     else mesh = mesh_of_tile(pd.mesh, toff);
     pdl_wait();
-    if (!pd.active[k]) {
+    const bool use_b = inv_tau != 0.0;  // stationary solves (tau = Inf) never look at b: rhs - b/tau = rhs
+    if constexpr (SYM0) long_stage_state_issue<Fn, R, TT>(pd, k, tile, use_b, false, k6sm);
+    InstanceRegs<Fn> in;
+    in.load(pd, k);
+    if (!in.active) {
         if constexpr (SYM0) long_stage_drain(k6sm);
         return;
     }
     double* ug = pd.u + (size_t)k * pd.L + toff;
     const double* ub = ug;
     const double* bb = pd.b + (size_t)k * pd.L + toff;
-    const bool use_b = inv_tau != 0.0;  // stationary solves (tau = Inf) never look at b: rhs - b/tau = rhs
     // u is updated in place while other tiles are still being read: everything this CTA needs from outside its own
     // tile (the neighbours' edge nodes, both mesh ends for the boundary conditions) comes from the copy the
     // forward sweep saved in `edge`.
@@ -505,7 +534,7 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, do
     const double pD = __ldcg(cf + tm), pA = __ldcg(cf + TT + tm), pC = __ldcg(cf + 2 * TT + tm);
     double uc[R][1], bc[R][1];
     if constexpr (SYM0) {
-        long_stage_state<Fn, R, TT>(pd, k, tile, use_b, false, k6sm, ub, bb);
+        long_stage_state_wait<Fn, R, TT>(use_b, k6sm, ub, bb);
     } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) k6sm[LS::oU + 2 + r * TT + t] = ug[r * TT + t];
@@ -517,8 +546,7 @@ __global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, do
 #pragma unroll
     for (int r = 0; r < R; ++r) { uc[r][0] = ub[r * TT + t]; bc[r][0] = use_b ? bb[r * TT + t] : 0.0; }
     ChunkThomas<1, R> th;
-    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
-                                                       pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff,
+    assemble_chunk<Fn, R, TT, SYM0, true, !SYM0, SYM0>(pd, mesh, ub, bb, in.mass, t, tt, inv_tau, in.prm, uc, bc, th, (int)toff,
                                                        e + 2 * pd.ntiles, e + 2 * pd.ntiles + 1);
     const double Sp = outer[0], St = outer[1];
     Vec<1> xp, xs, h[R];

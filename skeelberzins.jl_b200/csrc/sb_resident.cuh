@@ -37,9 +37,19 @@ struct ResidentArgs {
     unsigned long long* sum_iters;  // [1] Newton iterations summed over instances and steps (the work counter)
 };
 
+// Systems per CTA of the whole-solve kernel: four warps (TT == 32); two 64-thread groups with a named barrier each
+// (TT == 64: the CTA's copy of the mesh weights is the larger part of its shared memory, sharing it between two
+// systems lifts the resident warps per SM from 11 to 16 on cfg3); one otherwise.
+__host__ __device__ constexpr int resident_groups(int TT) { return TT == 32 ? kWarpBlockThreads / 32 : (TT == 64 ? 2 : 1); }
+__host__ __device__ constexpr int resident_min_blocks(int TT, int P) {
+    const int warps = (P == 1) ? SB_PERSISTENT_WARPS_PER_SM : SB_PERSISTENT_WARPS_P2;
+    const int threads = resident_groups(TT) * TT;
+    return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;
+}
+
 template <class Fn, int R, int TT, bool SYM0>
 struct ResidentLayout {  // shared-memory carve-up (offsets in doubles)
-    static constexpr int P = Fn::npde, L = R * TT, G = (TT == 32) ? kWarpBlockThreads / 32 : 1;
+    static constexpr int P = Fn::npde, L = R * TT, G = resident_groups(TT);
     static constexpr int NPS = (Fn::nparams + 1) / 2 * 2;
     static constexpr bool kFrac = !(Fn::c_unit && Fn::s_zero);
     static constexpr int nGw = SYM0 ? L : 0, nAB = SYM0 ? 0 : 4 * L, nIvol = Fn::c_unit ? L : 0, nFrac = kFrac ? 2 * L : 0;
@@ -54,14 +64,15 @@ struct ResidentLayout {  // shared-memory carve-up (offsets in doubles)
 };
 
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__((TT) == 32 ? kWarpBlockThreads : (TT), persistent_min_blocks(TT, Fn::npde))
+__global__ void __launch_bounds__(resident_groups(TT) * TT, resident_min_blocks(TT, Fn::npde))
 k_solve_resident(ProbDev pd, ResidentArgs ra) {
     using LY = ResidentLayout<Fn, R, TT, SYM0>;
     constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS;
     extern __shared__ __align__(16) double smr[];
     double* mesh_sm = smr;
-    const int g = (TT == 32) ? (threadIdx.x >> 5) : 0;
-    const int t = (TT == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int g = (G > 1) ? (int)threadIdx.x / TT : 0;
+    const int t = (G > 1) ? (int)threadIdx.x % TT : (int)threadIdx.x;
+    const int bar = (G > 1 && TT > 32) ? 1 + g : 0;   // barrier of this system's threads (group_sync)
     double* grp = mesh_sm + LY::mesh_doubles + (size_t)g * LY::group_doubles;
     double* utile = grp + LY::oU;     // [L*P] current iterate, device-layout slots (r*TT + t)
     double* btile = grp + LY::oB;     // [L*P] b = M .* u_n of the step
@@ -74,7 +85,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
     // mesh weights -> shared memory, once per CTA
     MeshDev mesh = pd.mesh;
     {
-        const int nthr = (TT == 32) ? kWarpBlockThreads : TT;
+        const int nthr = G * TT;
         if constexpr (SYM0) {
             for (int i = threadIdx.x; i < L; i += nthr) mesh_sm[LY::oGw + i] = pd.mesh.gw[i];
             mesh.gw = mesh_sm + LY::oGw;
@@ -117,7 +128,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 }
             }
         };
-        group_sync<TT>();               // parameters and mass flags visible
+        group_sync<TT>(bar);               // parameters and mass flags visible
         if (ra.snap && !ra.b_given) snapshot(0);
 
         long long total = 0;
@@ -148,7 +159,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
             bool conv = false;
             double ss = 0.0;
             while (true) {
-                group_sync<TT>();       // (A) the iterate of every thread and the partial sums of h^2 are visible
+                group_sync<TT>(bar);       // (A) the iterate of every thread and the partial sums of h^2 are visible
                 if (it > 0) {
                     if constexpr (TT > 32) {   // every thread forms the same total in the same order
                         const double* sl = sums + ((it - 1) & 1) * 8;
@@ -170,11 +181,11 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 ChunkThomas<P, R> th;
                 assemble_chunk<Fn, R, TT, SYM0, true, false>(pd, mesh, utile, btile, mbuf, t, tt, inv_tau, pbuf, uc, bc, th);
                 Vec<P> h[R];
-                const bool suspect = th.template finish<TT>(h, scratch + (it % LY::nexch) * LY::exch, t);   // (B) inside
+                const bool suspect = th.template finish<TT>(h, scratch + (it % LY::nexch) * LY::exch, t, bar);   // (B) inside
                 if (suspect) {          // pivot growth: the same rows into a band, solved with row interchanges
                     double hp[R][P];
                     const bool singular = pivoted_newton_rows<Fn, R, TT, SYM0, false>(pd, mesh, k, utile, btile, t, blockIdx.x * G + g, tt,
-                                                                                      inv_tau, sh_slot, hp);
+                                                                                      inv_tau, sh_slot, hp, bar);
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -237,7 +248,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 }
             }
         }
-        group_sync<TT>();               // the tiles, parameters and flags are rewritten by the next instance
+        group_sync<TT>(bar);               // the tiles, parameters and flags are rewritten by the next instance
     }
 }
 
