@@ -405,9 +405,10 @@ def run_ours(args):
     lay = dev.layout()
     longmesh = lay["R"] * lay["T"] < Nx
     if longmesh:
-        # K6: two sweeps that each read u (8 B), b (8 B, transient only) and the mesh weights (32 B for
-        # m = 0; one instance, so the mesh is not amortised), one in-place write of the new iterate (8 B)
-        bpu = {"fused": 2 * (8 + 32 + (0 if stationary else 8)) + 8}
+        # K6: two sweeps that each read u (8 B), b (8 B, transient only) and the mesh -- m = 0: the mesh points
+        # x (8 B), every weight is computed from them; m >= 1: the weight arrays (40 B); one instance, so the mesh is not
+        # amortised -- and one in-place write of the new iterate (8 B)
+        bpu = {"fused": 2 * (8 + (8 if case.m == 0 else 40) + (0 if stationary else 8)) + 8}
     peak, peak_kind = hbm_peak()
     kern = {}
     if args.design in ("resident", "fused", "fused_tma"):
@@ -428,7 +429,7 @@ def run_ours(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind if peak_kind == "measured" else "of fallback",
-        "kernel": "k6_chunk_asm .. k6_finalize (long-mesh Newton iteration, one launch = the whole kernel sequence)" if longmesh
+        "kernel": "k6_chunk_asm, k6_top, k6_back_asm, k6_finalize (long-mesh Newton iteration, one launch = the whole kernel sequence)" if longmesh
         else ("k_solve_resident (the whole solve: every Newton iteration of every time step of every instance in one launch)"
               if args.design == "resident" else "k_newton_fused_p" if args.design == "fused_tma" else "k_newton_fused") if dom == "fused" else "k_" + dom,
         "avg_launch_us": 1e3 * kern[dom] / n_launch, "launches_profiled": prof["launches"],

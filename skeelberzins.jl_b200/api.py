@@ -96,6 +96,7 @@ def register_user_functor(cuda_source, struct_name, npde, nparams):
         struct <struct_name> {
             static constexpr int npde = ..., nparams = ...;
             static constexpr bool c_unit = ..., s_zero = ...;    // c == 1 identically / s == 0 identically
+            static constexpr bool s_const = ...;                 // optional: s does not depend on u or dudx
             template <class S> static __device__ void pde(double x, double t, const S* u, const S* ux,
                                                           const double* prm, S* c, S* f, S* s);
             template <class S> static __device__ void bc(double xl, const S* ul, double xr, const S* ur, double t,

@@ -121,6 +121,39 @@ int add_user_functor(const UserFunctor& uf) {
     return SB_USER_FUNCTOR_BASE + (int)user_functors_unlocked().size() - 1;
 }
 
+// K1 on the device for m == 0 (get_quad_points_weights, src/utils.jl:683-718, and the interpolation / volume weights
+// of src/utils.jl:18-48, src/assembler.jl:36,68-69,98): every weight of slot s from the mesh points around it.  The
+// expressions are those of the host loop in sb_problem_create (divisions are IEEE on both sides, nothing contracts to
+// an FMA), so the arrays agree bit for bit with what the host computes for m >= 1 meshes -- without a 9*L staging
+// vector and a pass over it on the host (2^22 nodes: 300 MB).  Layout: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L]
+// | ivol[L] | xs[L]; xs is the input.
+__global__ void k_mesh_weights_m0(double* __restrict__ mesh, int Nx, int R, int T, size_t L) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= L) return;
+    const int Lt = R * T;
+    auto slot_of = [&](int i) { const int tile = i / Lt, il = i - tile * Lt; return (size_t)tile * Lt + (size_t)(il % R) * T + il / R; };
+    const int tile = (int)(s / Lt), sl = (int)(s - (size_t)tile * Lt);
+    const int i = tile * Lt + (sl % T) * R + sl / T;
+    const double* xs = mesh + 9 * L;
+    double xi = 0.0, aw = 0.0, bw = 0.0, gw = 0.0, wf = 0.0, fR = 0.0, fL = 0.0, ivol = 0.0;
+    if (i < Nx) {
+        const double xc = xs[s];
+        if (i < Nx - 1) {
+            const double xr = xs[slot_of(i + 1)], q = (xc + xr) / 2, h = xr - xc;
+            xi = q; aw = (xr - q) / h; bw = (q - xc) / h; gw = 1.0 / h; wf = 1.0;
+            fR = q - xc;
+        }
+        if (i >= 1) fL = xc - (xs[slot_of(i - 1)] + xc) / 2;
+        if (i >= 1 && i < Nx - 1) ivol = 1.0 / (fR + fL);
+    }
+    mesh[s] = xi;
+    mesh[L + 2 * s] = aw; mesh[L + 2 * s + 1] = bw;
+    mesh[3 * L + 2 * s] = gw; mesh[3 * L + 2 * s + 1] = wf;
+    mesh[5 * L + 2 * s] = fR; mesh[5 * L + 2 * s + 1] = fL;
+    mesh[7 * L + s] = gw;
+    mesh[8 * L + s] = ivol;
+}
+
 // reference layout [B][Nx][W] <-> device layout [B][tile][R][T][W]   (W doubles per node, tiles of Lt = R*T nodes,
 // L = ntiles*Lt padded nodes per instance).  identity != 0: padding nodes receive the W = P*P identity block (Jd)
 __global__ void k_to_device_layout(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int Nx, int R,
@@ -923,31 +956,36 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     // per-interval interpolation weights (src/utils.jl:18-48) and flux weights, per-node volume weights
     // (src/assembler.jl:36,68-69,74,84,98), written straight in the [r][t] device layout
     const size_t L = pd.L;
-    // device image: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L] | ivol[L] | xs[L]
-    std::vector<double> mesh(10 * L, 0.0);
-    double *h_xi = &mesh[0], *h_awbw = &mesh[L], *h_gwwf = &mesh[3 * L], *h_frac = &mesh[5 * L], *h_gw = &mesh[7 * L],
-           *h_ivol = &mesh[8 * L], *h_xs = &mesh[9 * L];
+    // device image: xi[L] | awbw[2L] | gwwf[2L] | frac[2L] | gw[L] | ivol[L] | xs[L].  m == 0: only xs is staged, the
+    // device computes the rest (k_mesh_weights_m0); m >= 1 (logarithms, cube roots: libm on the host, as the oracle)
+    // fills the whole image here
+    const bool device_weights = (m == 0);
+    std::vector<double> mesh((device_weights ? 1 : 10) * L, 0.0);
+    double* h_xs = &mesh[device_weights ? 0 : 9 * L];
     for (size_t i = 0; i < L; ++i) {   // the mesh points themselves (padding: the mesh continued with its last spacing)
         const size_t s = (i / (R * T)) * (R * T) + ((i % (R * T)) % R) * T + (i % (R * T)) / R;
         h_xs[s] = (i < (size_t)Nx) ? xmesh[i] : xmesh[Nx - 1] + (double)(i - (Nx - 1)) * (xmesh[Nx - 1] - xmesh[Nx - 2]);
     }
-    for (int i = 0; i < Nx; ++i) {
-        const size_t s = (size_t)(i / (R * T)) * (R * T) + (size_t)((i % (R * T)) % R) * T + (i % (R * T)) / R;
-        double fR = 0.0, fL = 0.0;
-        if (i < NI) {
-            const double xl = xmesh[i], xr = xmesh[i + 1], q = pb->xi[i];
-            double aw, bw, gw;
-            if (pd.singular) { const double h = xr * xr - xl * xl, th = (q * q - xl * xl) / h; aw = 1 - th; bw = th; gw = (2 * q) / h; }
-            else if (m == 0) { const double h = xr - xl; aw = (xr - q) / h; bw = (q - xl) / h; gw = 1.0 / h; }
-            else if (m == 1) { const double lg = std::log(xr / xl), th = std::log(q / xl) / lg; aw = 1 - th; bw = th; gw = 1.0 / (q * lg); }
-            else { const double h = xr - xl, th = (xr * (q - xl)) / (q * h); aw = 1 - th; bw = th; gw = (xr * xl) / (q * q * h); }
-            h_xi[s] = q; h_awbw[2 * s] = aw; h_awbw[2 * s + 1] = bw; h_gwwf[2 * s] = gw; h_gw[s] = gw;
-            h_gwwf[2 * s + 1] = pd.singular ? ipow(pb->zeta[i], mp) / q : ipow(q, m);
-            fR = (ipow(pb->zeta[i], mp) - ipow(xmesh[i], mp)) / mp;
+    if (!device_weights) {
+        double *h_xi = &mesh[0], *h_awbw = &mesh[L], *h_gwwf = &mesh[3 * L], *h_frac = &mesh[5 * L], *h_gw = &mesh[7 * L],
+               *h_ivol = &mesh[8 * L];
+        for (int i = 0; i < Nx; ++i) {
+            const size_t s = (size_t)(i / (R * T)) * (R * T) + (size_t)((i % (R * T)) % R) * T + (i % (R * T)) / R;
+            double fR = 0.0, fL = 0.0;
+            if (i < NI) {
+                const double xl = xmesh[i], xr = xmesh[i + 1], q = pb->xi[i];
+                double aw, bw, gw;
+                if (pd.singular) { const double h = xr * xr - xl * xl, th = (q * q - xl * xl) / h; aw = 1 - th; bw = th; gw = (2 * q) / h; }
+                else if (m == 1) { const double lg = std::log(xr / xl), th = std::log(q / xl) / lg; aw = 1 - th; bw = th; gw = 1.0 / (q * lg); }
+                else { const double h = xr - xl, th = (xr * (q - xl)) / (q * h); aw = 1 - th; bw = th; gw = (xr * xl) / (q * q * h); }
+                h_xi[s] = q; h_awbw[2 * s] = aw; h_awbw[2 * s + 1] = bw; h_gwwf[2 * s] = gw; h_gw[s] = gw;
+                h_gwwf[2 * s + 1] = pd.singular ? ipow(pb->zeta[i], mp) / q : ipow(q, m);
+                fR = (ipow(pb->zeta[i], mp) - ipow(xmesh[i], mp)) / mp;
+            }
+            if (i >= 1) fL = (ipow(xmesh[i], mp) - ipow(pb->zeta[i - 1], mp)) / mp;
+            h_frac[2 * s] = fR; h_frac[2 * s + 1] = fL;
+            if (i >= 1 && i < NI) h_ivol[s] = 1.0 / (fR + fL);
         }
-        if (i >= 1) fL = (ipow(xmesh[i], mp) - ipow(pb->zeta[i - 1], mp)) / mp;
-        h_frac[2 * s] = fR; h_frac[2 * s + 1] = fL;
-        if (i >= 1 && i < NI) h_ivol[s] = 1.0 / (fR + fL);
     }
     pd.x0 = xmesh[0]; pd.xN = xmesh[Nx - 1]; pd.x0m = ipow(xmesh[0], m); pd.xNm = ipow(xmesh[Nx - 1], m); pd.xi0 = pb->xi[0];
 
@@ -982,7 +1020,12 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     if (e != cudaSuccess) { sb_problem_destroy(pb); return fail(SB_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
     for (int i = 0; i < 3 * kSlots; ++i) pb->h_count[i] = 0;
     cudaStream_t st = ctx->stream;
-    e = cudaMemcpyAsync(pb->d_mesh, mesh.data(), 10 * L * sizeof(double), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(pb->d_mesh + (device_weights ? 9 * L : 0), mesh.data(), mesh.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && device_weights) {
+        k_mesh_weights_m0<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(pb->d_mesh, Nx, R, T, L);
+        ++g_launches;
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess && f_nparams > 0)
         e = cudaMemcpy2DAsync(pb->d_prm, pd.nprm_s * sizeof(double), params, f_nparams * sizeof(double),
                               f_nparams * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, st);

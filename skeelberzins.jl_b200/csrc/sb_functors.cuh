@@ -7,8 +7,9 @@
 // parameter vector of the sweep.  ql/qr are value-only (plain doubles): in every registry entry
 // they are constants, exactly as in the reference examples.
 // Ids and parameter order: include/skeelberzins_b200.h (enum sb_functor_id).
-// Traits: c_unit = the capacity c is identically 1, s_zero = the source s is identically 0; they let
-// the assembler drop dual arithmetic on structural zeros (the values are still what pde() returns).
+// Traits: c_unit = the capacity c is identically 1, s_zero = the source s is identically 0, s_const (optional) = s
+// does not depend on u or dudx; they let the assembler drop dual arithmetic on structural zeros (the values are
+// still what pde() returns).
 #pragma once
 #include "sb_dual.cuh"
 
@@ -54,7 +55,7 @@ struct FnLinDiffCyl {
 // examples/Example104_Poisson.jl:20-41 ; test/test_solveStationary.jl:6-23 (c0 = 0)
 struct FnPoisson {
     static constexpr int npde = 1, nparams = 3;
-    static constexpr bool c_unit = false, s_zero = false;
+    static constexpr bool c_unit = false, s_zero = false, s_const = true;
     template <class S> static SB_D void pde(double, double, const S*, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(p[0]); f[0] = ux[0]; s[0] = S(p[1]);
     }
@@ -66,7 +67,7 @@ struct FnPoisson {
 // examples/Example105_StationaryNonlinearDiffusion.jl:30-51
 struct FnStatNonlin {
     static constexpr int npde = 1, nparams = 3;
-    static constexpr bool c_unit = true, s_zero = false;
+    static constexpr bool c_unit = true, s_zero = false, s_const = true;
     template <class S> static SB_D void pde(double, double, const S* u, const S* ux, const double* p, S* c, S* f, S* s) {
         c[0] = S(1.0); f[0] = p[0] * u[0] * ux[0]; s[0] = S(p[1]);
     }

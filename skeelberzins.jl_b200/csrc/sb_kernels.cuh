@@ -596,6 +596,11 @@ SB_D double system_sum(double v, double* sm, int t) {
 // Functor traits: Fn::c_unit (c == 1 identically), Fn::s_zero (s == 0 identically) let the
 // compiler drop the corresponding dual arithmetic.
 // ---------------------------------------------------------------------------------------------
+// optional functor trait: `static constexpr bool s_const = true;` -- the source s does not depend on u or dudx (its partials
+// are structural zeros the compiler cannot fold: 0 * x is not 0 for a NaN x), so the Jacobian rows skip its terms
+template <class Fn, class = void> struct fn_s_const { static constexpr bool value = false; };
+template <class Fn> struct fn_s_const<Fn, decltype((void)Fn::s_const)> { static constexpr bool value = Fn::s_const; };
+
 template <int P, int ND>
 struct IntervalRes {  // (c,f,s) of one interval; partials w.r.t. (u_left[0..P), u_right[0..P))
     Dual<ND> c[P], f[P], s[P];
@@ -603,8 +608,8 @@ struct IntervalRes {  // (c,f,s) of one interval; partials w.r.t. (u_left[0..P),
 };
 
 // XW (m == 0 only): the interval's weights come from its two mesh points xl, xr instead of the weight arrays -- the
-// same expressions as the host set-up (sb_problem_create); the reciprocals are fast_rcp's (within an ulp of the host's
-// divisions; __drcp_rn would agree bit for bit at twice the instructions, measured 44 vs 35 us per cfg5 sweep).
+// same expressions as the set-up (k_mesh_weights_m0); the reciprocals are fast_rcp's (within an ulp of the set-up's
+// divisions; __drcp_rn would agree bit for bit at about twice the instructions and a branch per reciprocal).
 template <class Fn, int ND, bool SYM0, bool GLOB = true, bool XW = false>
 SB_D void eval_interval(const MeshDev& mesh, int slot, const double* ul, const double* ur, double tt, const double* prm,
                         IntervalRes<Fn::npde, ND>& out, double xl = 0.0, double xr = 0.0) {
@@ -865,7 +870,7 @@ SB_D void assemble_chunk(const ProbDev& pd, const MeshDev& mesh, const double* u
                     double nm = -(wL * Lr.f[j].d[q]);
                     double nc = wR * Rr.f[j].d[q] - wL * Lr.f[j].d[PO + q];
                     double np = wR * Rr.f[j].d[PO + q];
-                    if constexpr (!Fn::s_zero) {
+                    if constexpr (!Fn::s_zero && !fn_s_const<Fn>::value) {
                         nm += frL * Lr.s[j].d[q];
                         nc += frR * Rr.s[j].d[q] + frL * Lr.s[j].d[PO + q];
                         np += frR * Rr.s[j].d[PO + q];

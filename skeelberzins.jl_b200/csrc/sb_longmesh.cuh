@@ -25,7 +25,15 @@ namespace sb {
 #define SB_LONG_T0 128
 #endif
 constexpr int kLongR = 8, kLongT0 = SB_LONG_T0;   // level 0: rows per thread / threads per tile (tile = 1024 mesh nodes = one row of the level above; measured: 256 threads 87 us, 128 threads 80 us per cfg5 iteration)
-constexpr int kLongCtasPerSM = 512 / kLongT0;     // level-0 kernels are compiled for 16 warps per SM (128 registers)
+// resident warps per SM the two level-0 kernels are compiled for (register caps 96 / 128): measured on cfg5 at 16 / 20 / 24
+// warps -- forward sweep 35.2 / 33.9 / 35.2 us, backward sweep 32.2 / 33.6 / 39.2 us
+#ifndef SB_LONG_WARPS_FWD
+#define SB_LONG_WARPS_FWD 20
+#endif
+#ifndef SB_LONG_WARPS_BWD
+#define SB_LONG_WARPS_BWD 16
+#endif
+constexpr int kLongCtasFwd = 32 * SB_LONG_WARPS_FWD / kLongT0, kLongCtasBwd = 32 * SB_LONG_WARPS_BWD / kLongT0;
 constexpr int kLongTT = 256;              // stored levels and the top level: threads per tile
 constexpr int kLongRS = 16;               // stored levels (1 .. top-1): rows per thread = reduction factor per level
 
@@ -277,8 +285,8 @@ SB_D void chunk_numbers(const ChunkThomas<1, R>& th, double& y0, double& v0, dou
 // Reduction of the TT chunks of a tile inside its CTA.  Every thread leaves its chunk's 7 numbers in shared memory; warp 0
 // alone turns them into reduced rows (as form_rows does for a stored level), TT/32 per lane, eliminates those with the
 // same partition (lvl2) and finishes with the open reduction across its 32 lanes.  The other warps wait at the barrier
-// -- their issue slots go to the other CTAs of the SM; an all-warps variant (open_reduce in every warp, then across the
-// warps) was measured at 44 / 50 us per cfg5 sweep.
+// -- their issue slots go to the other CTAs of the SM (an all-warps variant, open_reduce in every warp and then across
+// the warps, was measured slower: more instructions, the same waiting).
 template <int TT>
 struct TileScratch {
     static constexpr int Q = TT / 32;
@@ -347,7 +355,7 @@ SB_D void tile_coefficients(ChunkThomas<1, TT / 32>& lvl2, const OpenRows& rows,
 // level 0, forward: assemble + eliminate the chunk (thread), reduce the 32 chunks of a warp and the TT/32 warps of the
 // CTA to ONE summary per tile of R*TT mesh nodes: the level above has Nx / (R*TT) rows
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_chunk_asm(ProbDev pd, double tt, double inv_tau, LevelDev lv) {
+__global__ void __launch_bounds__(TT, kLongCtasFwd) k6_chunk_asm(ProbDev pd, double tt, double inv_tau, LevelDev lv) {
     static_assert(Fn::npde == 1, "long-mesh path: scalar PDEs only");
     using LS = LongStage<Fn, R, TT, SYM0>;
     using TS = TileScratch<TT>;
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(TT) k6_back_sys(LevelDev lv, LevelDev up, cons
 // the forward sweep left and the tile's two outer separators from the level above, back-substitute, u -= h in place,
 // per-tile sum of h^2.  No reduction and no barrier between the assembly and the update.
 template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__(TT, kLongCtasPerSM) k6_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
+__global__ void __launch_bounds__(TT, kLongCtasBwd) k6_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
     using LS = LongStage<Fn, R, TT, SYM0>;
     constexpr int W = TT / 32;
     __shared__ double red[W];
@@ -590,9 +598,10 @@ __global__ void __launch_bounds__(TT) k6_assemble(ProbDev pd, double tt, double 
     if (JAC) { pt.Jl = pd.Jl + toff; pt.Jd = pd.Jd + toff; pt.Ju = pd.Ju + toff; }
     StoreSink<1, TT> sink{pt, k, t};
     const MeshDev mesh = mesh_of_tile(pd.mesh, toff);
-    assemble_chunk<Fn, R, TT, SYM0, JAC, true>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
-                                               pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink, (int)toff, ui,
-                                               ui + tiled_pos(pd.Nx - 1, R, TT));
+    // m == 0: weights from the mesh points, as in the Newton sweeps (the same arithmetic in both entry points)
+    assemble_chunk<Fn, R, TT, SYM0, JAC, true, SYM0>(pd, mesh, ub, bb, pd.mass + (size_t)k * 4, t, tt, inv_tau,
+                                                     pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink, (int)toff, ui,
+                                                     ui + tiled_pos(pd.Nx - 1, R, TT));
 }
 
 // ||h||_2 per instance (fixed summation order: thread, lane tree, warps), stop test, counters; one CTA per instance,

@@ -294,6 +294,27 @@ def test_longmesh_transient_vs_oracle(ctx, oracle, monkeypatch, cfg, Nx, nsteps)
     assert np.array_equal(its, r["iters"])
 
 
+def test_longmesh_graded_mesh_vs_oracle(ctx, oracle):
+    """The m = 0 long-mesh kernels compute gw, ivol and frac from the mesh points: a strongly graded mesh (spacing from
+    6e-6 at the centre to 6e-4 at the ends, ratio 100) through transient nonlinear diffusion, three instances with up to
+    75 Newton iterations per step, against the oracle."""
+    c = ex.baseline_case("2", B=3, Nx=5000)
+    s_ = np.linspace(-1.0, 1.0, 5000)
+    x = np.sign(s_) * np.abs(s_) ** 1.5
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:4]
+    fn = sb.Functor(c.functor, c.params)
+    u0 = np.broadcast_to(np.asarray(c.icfun(x), dtype=np.float64).reshape(1, -1, 1), (3, x.size, 1))
+    sol, hist, dev = sb.pdepe(c.m, fn, u0, fn, x, (tg[0], tg[-1]), ctx=ctx, tstep=tg, hist=True, squeeze=False, save="last",
+                              return_device=True)
+    assert dev.longmesh()
+    r = oracle.pdepe_transient(c.functor, c.m, x, c.params, u0, tg, None)
+    err = np.abs(sol.u[-1] - r["u"][:, :, 0]).max(axis=1) / np.abs(r["u"][:, :, 0]).max(axis=1)
+    assert err.max() < RTOL
+    its = np.array([[len(h[k]) for h in hist] for k in range(3)])
+    assert np.array_equal(its, r["iters"])
+
+
 def test_longmesh_assemble_entrywise(ctx, oracle):
     """assemble! and the Jacobian rows of a long mesh (tiles with neighbours in other tiles) against the oracle."""
     rng = np.random.default_rng(7)
