@@ -339,6 +339,7 @@ struct sb_problem {
     bool longmesh = false;
     std::vector<LevelDev> lv;
     int top_R = 1;
+    bool top_configured = false;
     double *d_lm = nullptr, *d_partial = nullptr;
     int* d_auto = nullptr;              // device-side stepping: {time step, iteration} (sb_solve_steps)
     double* d_tgrid = nullptr;          // its time grid
@@ -550,8 +551,11 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
              uf.name.c_str(), R, TT, sym);
     src += buf;
     if (longmesh) {
-        snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_long_smem = sb::LongStage<%s, %d, %d, %s>::bytes;\n",
-                 uf.name.c_str(), R, TT, sym);
+        if (uf.npde == 1)
+            snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_long_smem = sb::LongStage<%s, %d, %d, %s>::bytes;\n",
+                     uf.name.c_str(), R, TT, sym);
+        else
+            snprintf(buf, sizeof buf, "__device__ unsigned long long sb_user_long_smem = sb::long_sys_smem_bytes(%d);\n", uf.npde);
         src += buf;
     }
     snprintf(buf, sizeof buf, "static_assert(%s::npde == %d && %s::nparams == %d, \"npde/nparams differ from the registration\");\n",
@@ -566,11 +570,16 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     name("sb::k_newton_fused_p<%s, %d, %d, %s>");
     name("sb::k_solve_resident<%s, %d, %d, %s>");
     snprintf(buf, sizeof buf, "sb::k_solve<%d, %d, %d>", uf.npde, R, TT); names.push_back(buf);
-    if (longmesh) {
+    if (longmesh && uf.npde == 1) {
         name("sb::k6_chunk_asm<%s, %d, %d, %s>");
         name("sb::k6_back_asm<%s, %d, %d, %s>");
         name("sb::k6_assemble<%s, %d, %d, %s, true>");
         name("sb::k6_assemble<%s, %d, %d, %s, false>");
+    } else if (longmesh) {
+        name("sb::k6s_chunk_asm<%s, %d, %d, %s>");
+        name("sb::k6s_back_asm<%s, %d, %d, %s>");
+        name("sb::k6s_assemble<%s, %d, %d, %s, true>");
+        name("sb::k6s_assemble<%s, %d, %d, %s, false>");
     }
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, src.c_str(), "sb_user_functor.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
@@ -660,15 +669,15 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
 }
 
 // ---- long-mesh path (K6, sb_longmesh.cuh) -------------------------------------------------------
-constexpr int kLongTopRows = 16 * kLongTT;  // the top level is solved by one CTA of kLongTT threads, <= 16 rows each
-
 int longmesh_setup(sb_problem* pb) {
     const int64_t B = pb->pd.B;
+    const int P = pb->P;
     std::vector<LevelDev> lv;
     int n = pb->pd.Nx;
-    int top_rows = kLongTopRows;
+    const int max_top_rows = long_rows_top(P) * kLongTT;   // the top level is solved by one CTA of kLongTT threads
+    int top_rows = max_top_rows;
     if (const char* e = getenv("SB_LONG_TOP_ROWS")) {   // testing: stored levels on meshes of moderate length
-        top_rows = std::max(kLongTT, std::min(kLongTopRows, atoi(e)));
+        top_rows = std::max(kLongTT, std::min(max_top_rows, atoi(e)));
     }
     for (int l = 0;; ++l) {
         LevelDev L;
@@ -676,48 +685,88 @@ int longmesh_setup(sb_problem* pb) {
         L.n = n;
         const bool top = (l > 0 && n <= top_rows);
         if (top) { L.R = 1; while (L.R * kLongTT < n) L.R *= 2; }
-        else L.R = (l == 0) ? kLongR : kLongRS;
+        else L.R = (l == 0) ? pb->pd.R : long_rows_stored(P);
         const int tt = (l == 0) ? kLongT0 : kLongTT;
         L.ntiles = (n + L.R * tt - 1) / (L.R * tt);
         L.stride = (size_t)L.ntiles * L.R * tt;
-        // rows of the next level: level 0 reduces every tile to one row inside its CTA; a stored level keeps one row
-        // per thread chunk (padding chunks included)
-        L.nchunks = (l == 0) ? L.ntiles : L.ntiles * tt;
+        // rows of the next level: scalar PDEs reduce every level-0 tile to one row inside its CTA; a stored level, and
+        // level 0 of a system, keeps one row per thread chunk (padding chunks included)
+        L.nchunks = (l == 0 && P == 1) ? L.ntiles : L.ntiles * tt;
         lv.push_back(L);
         if (top) break;
         n = L.nchunks;
-        if (l > 12) return fail(SB_ERR_UNSUPPORTED, "long-mesh recursion too deep");
+        if (l > 24) return fail(SB_ERR_UNSUPPORTED, "long-mesh recursion too deep");
     }
     if (lv[0].ntiles != pb->pd.ntiles) return fail(SB_ERR_INVALID, "long-mesh tiling mismatch");
-    size_t total = 0;  // doubles
+    // doubles per stored row (a, c, d), per solution entry, per summary record
+    const size_t rowd = (size_t)(2 * P * P + P + 1) / 2 * 2, sumd = (size_t)(5 * P * P + 2 * P + 7) / 8 * 8;
+    size_t total = 0;
     for (size_t l = 0; l < lv.size(); ++l) {
-        if (l > 0) total += (l + 1 < lv.size() ? 5 : 1) * lv[l].stride * B;   // (a, c, d, -) records + x (top: x only)
-        if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += 8 * lv[l].up_stride * B; }
+        if (l > 0) total += ((l + 1 < lv.size() ? rowd : 0) + P) * lv[l].stride * B;   // stored rows (not at the top) + x
+        if (l + 1 < lv.size()) { lv[l].up_stride = lv[l + 1].stride; lv[l].up_R = lv[l + 1].R; total += sumd * lv[l].up_stride * B; }
     }
     CU(guarded_malloc((void**)&pb->d_lm, total * sizeof(double)));
     CU(cudaMemset(pb->d_lm, 0, total * sizeof(double)));
     double* p = pb->d_lm;
     for (size_t l = 0; l < lv.size(); ++l) {
         if (l > 0) {
-            if (l + 1 < lv.size()) { lv[l].acd = reinterpret_cast<double2*>(p); p += 4 * lv[l].stride * B; }
-            lv[l].x = p; p += lv[l].stride * B;
+            if (l + 1 < lv.size()) { lv[l].acd = reinterpret_cast<double2*>(p); p += rowd * lv[l].stride * B; }
+            lv[l].x = p; p += (size_t)P * lv[l].stride * B;
         }
-        if (l + 1 < lv.size()) { lv[l].sum = reinterpret_cast<double2*>(p); p += 8 * lv[l].up_stride * B; }
+        if (l + 1 < lv.size()) { lv[l].sum = reinterpret_cast<double2*>(p); p += sumd * lv[l].up_stride * B; }
     }
-    // per-tile sums | edge copies | the chunks' separator coefficients
-    CU(guarded_malloc((void**)&pb->d_partial, (size_t)B * ((3 + 3 * kLongT0) * (size_t)pb->pd.ntiles + 2) * sizeof(double)));
-    lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * pb->pd.ntiles;
-    lv[0].coef = lv[1].coef = pb->d_partial + (size_t)B * (3 * (size_t)pb->pd.ntiles + 2);
+    // per-tile sums | edge copies [2*ntiles + 2][P] | (scalar PDEs) the chunks' separator coefficients
+    const size_t nt = (size_t)pb->pd.ntiles;
+    const size_t edge_d = (2 * nt + 2) * P, coef_d = (P == 1) ? 3 * (size_t)kLongT0 * nt : 0;
+    CU(guarded_malloc((void**)&pb->d_partial, (size_t)B * (nt + edge_d + coef_d) * sizeof(double)));
+    lv[0].edge = lv[1].edge = pb->d_partial + (size_t)B * nt;
+    lv[0].coef = lv[1].coef = pb->d_partial + (size_t)B * (nt + edge_d);
     pb->lv = lv;
     pb->top_R = lv.back().R;
     return SB_OK;
 }
 
-template <int RT>
-void launch_top(sb_problem* pb, const LevelDev& top, const LevelDev& below) {
-    const size_t smem = (size_t)ChunkThomas<1, RT>::template smem_doubles<kLongTT>() * sizeof(double);
-    launch_pdl((const void*)k6_top<RT, kLongTT>, dim3((unsigned)pb->pd.B), dim3(kLongTT), smem, pb->ctx->stream, top, below,
-               (const int*)pb->d_active);
+template <int P, int RT>
+cudaError_t launch_top(sb_problem* pb, const LevelDev& top, const LevelDev& below) {
+    const size_t smem = (size_t)ChunkThomas<P, RT>::template smem_doubles<kLongTT>() * sizeof(double);
+    const void* kern = nullptr;
+    if constexpr (P == 1) kern = (const void*)k6_top<RT, kLongTT>;
+    else kern = (const void*)k6s_top<P, RT, kLongTT>;
+    if (smem > 48 * 1024 && !pb->top_configured) {     // (a problem has one top kernel: its P and its top_R)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pb->top_configured = true;
+    }
+    return launch_pdl(kern, dim3((unsigned)pb->pd.B), dim3(kLongTT), smem, pb->ctx->stream, top, below, (const int*)pb->d_active);
+}
+
+// the levels between the two level-0 sweeps: stored levels up, the top, stored levels down
+template <int P>
+int longmesh_middle(sb_problem* pb) {
+    cudaStream_t st = pb->ctx->stream;
+    const unsigned B = (unsigned)pb->pd.B;
+    std::vector<LevelDev>& lv = pb->lv;
+    const int top = (int)lv.size() - 1;
+    constexpr int RS = long_rows_stored(P);
+    for (int l = 1; l < top; ++l) {
+        if constexpr (P == 1)
+            CU(launch_pdl((const void*)k6_chunk_sys<RS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l - 1], (const int*)pb->d_active));
+        else
+            CU(launch_pdl((const void*)k6s_chunk_sys<P, RS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l - 1], (const int*)pb->d_active));
+    }
+    const int RT = pb->top_R;
+    if (RT <= 1) CU((launch_top<P, 1>(pb, lv[top], lv[top - 1])));
+    else if (RT == 2) CU((launch_top<P, 2>(pb, lv[top], lv[top - 1])));
+    else if (RT == 4) { if constexpr (long_rows_top(P) >= 4) CU((launch_top<P, 4>(pb, lv[top], lv[top - 1]))); }
+    else if (RT == 8) { if constexpr (long_rows_top(P) >= 8) CU((launch_top<P, 8>(pb, lv[top], lv[top - 1]))); }
+    else { if constexpr (long_rows_top(P) >= 16) CU((launch_top<P, 16>(pb, lv[top], lv[top - 1]))); }
+    for (int l = top - 1; l >= 1; --l) {
+        if constexpr (P == 1)
+            CU(launch_pdl((const void*)k6_back_sys<RS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l + 1], (const int*)pb->d_active));
+        else
+            CU(launch_pdl((const void*)k6s_back_sys<P, RS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l + 1], (const int*)pb->d_active));
+    }
+    return SB_OK;
 }
 
 // one Newton iteration of the long-mesh path; publishes the active count like the batched kernels
@@ -725,7 +774,6 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
     cudaStream_t st = pb->ctx->stream;
     const unsigned B = (unsigned)pb->pd.B;
     std::vector<LevelDev>& lv = pb->lv;
-    const int top = (int)lv.size() - 1;
     const size_t smem = pb->ks.long_smem;
     if (!pb->ks.long_configured) {  // one-time opt-in to the staged tiles' shared memory (static + dynamic may exceed 48 KB)
         CU(cudaFuncSetAttribute(pb->ks.long_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64)));
@@ -733,21 +781,16 @@ int longmesh_iteration(sb_problem* pb, double tol, int slot) {
         pb->ks.long_configured = true;
     }
     // every kernel of the sequence is launched with programmatic stream serialization: launch latency and the
-    // dependence-free prologues (barrier set-up, mesh weights of the level-0 tiles) overlap the predecessor's tail
-    CU(launch_pdl(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
-    for (int l = 1; l < top; ++l)
-        CU(launch_pdl((const void*)k6_chunk_sys<kLongRS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l - 1],
-                      (const int*)pb->d_active));
-    switch (pb->top_R) {
-        case 1: launch_top<1>(pb, lv[top], lv[top - 1]); break;
-        case 2: launch_top<2>(pb, lv[top], lv[top - 1]); break;
-        case 4: launch_top<4>(pb, lv[top], lv[top - 1]); break;
-        case 8: launch_top<8>(pb, lv[top], lv[top - 1]); break;
-        default: launch_top<16>(pb, lv[top], lv[top - 1]); break;
+    // dependence-free prologues (barrier set-up, mesh points of the level-0 tiles) overlap the predecessor's tail
+    CU(launch_pdl(pb->ks.long_chunk, dim3(lv[0].ntiles, B), dim3(kLongT0), pb->P == 1 ? smem : 0, st, pb->pd, pb->t_next, pb->inv_tau, lv[0]));
+    int rc = SB_OK;
+    switch (pb->P) {
+        case 1: rc = longmesh_middle<1>(pb); break;
+        case 2: rc = longmesh_middle<2>(pb); break;
+        case 3: rc = longmesh_middle<3>(pb); break;
+        default: rc = longmesh_middle<4>(pb); break;
     }
-    for (int l = top - 1; l >= 1; --l)
-        CU(launch_pdl((const void*)k6_back_sys<kLongRS, kLongTT>, dim3(lv[l].ntiles, B), dim3(kLongTT), 0, st, lv[l], lv[l + 1],
-                      (const int*)pb->d_active));
+    if (rc) return rc;
     CU(launch_pdl(pb->ks.long_back, dim3(lv[0].ntiles, B), dim3(kLongT0), smem, st, pb->pd, pb->t_next, pb->inv_tau, lv[1], pb->d_partial));
     CU(launch_pdl((const void*)k6_finalize<0>, dim3(B), dim3(256), 0, st, pb->pd, (const double*)pb->d_partial, tol, slot));
     CU(cudaGetLastError());
@@ -842,10 +885,8 @@ int sb_user_functor_compile_check(int functor_id, int Nx, int m, size_t* cubin_b
     int dec = pick_decomposition(Nx, uf.npde);
     bool longmesh = false;
     int R, TT;
-    if (dec < 0) {
-        if (uf.npde != 1) return fail(SB_ERR_UNSUPPORTED, "Nx = %d: long meshes need npde = 1", Nx);
-        longmesh = true; R = kLongR; TT = kLongT0;
-    } else { R = kDecomp[dec].R; TT = kDecomp[dec].TT; }
+    if (dec < 0) { longmesh = true; R = long_rows_level0(uf.npde); TT = kLongT0; }
+    else { R = kDecomp[dec].R; TT = kDecomp[dec].TT; }
     std::vector<char> cubin;
     std::vector<std::string> lowered;
     int rc = nvrtc_user_kernels(uf, R, TT, m == 0, longmesh, cubin, lowered);
@@ -912,17 +953,11 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
     ctx->refs++;
     pb->ctx = ctx; pb->fe = fe; pb->P = f_npde; pb->nparams = f_nparams; pb->design = pb->design_pending = SB_DESIGN_RESIDENT;
     pb->dec = pick_decomposition(Nx, pb->P);
-    if (getenv("SB_FORCE_LONGMESH") && pb->P == 1) pb->dec = -1;   // testing: long-mesh path on short meshes
+    if (getenv("SB_FORCE_LONGMESH")) pb->dec = -1;   // testing: long-mesh path on short meshes
     int R, T, ntiles = 1;
     if (pb->dec < 0) {
-        if (pb->P != 1) {
-            ctx->refs--;
-            delete pb;
-            return fail(SB_ERR_UNSUPPORTED, "Nx = %d exceeds the single-CTA range (%d nodes) for npde = %d; the long-mesh "
-                        "path handles scalar PDEs only", Nx, kMaxBlockT * std::min(8, max_rows_per_thread(f_npde)), f_npde);
-        }
         pb->longmesh = true;
-        R = kLongR; T = kLongT0;
+        R = long_rows_level0(pb->P); T = kLongT0;
         ntiles = (Nx + R * T - 1) / (R * T);
         for (int d = 0; d < kNumDecomp; ++d) if (kDecomp[d].R == R && kDecomp[d].TT == T) pb->dec = d;
     } else {

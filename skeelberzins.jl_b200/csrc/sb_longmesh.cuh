@@ -631,4 +631,278 @@ __global__ void __launch_bounds__(256) k6_finalize(ProbDev pd, const double* par
     if (t == 0) group_done(pd, slot, gridDim.x);
 }
 
+
+// =====================================================================================================================
+// Systems (npde >= 2) on long meshes.  The same recursive partition with P x P blocks, in round 1's structure: every
+// THREAD chunk of level 0 becomes a row of the level above (no reduction inside the CTA, no weights from x), stored
+// levels reduce kLongRSys<P>:1 until one CTA can solve the top.  Generic in P; tuned for nothing but correctness and
+// coalesced traffic -- the batched path covers systems up to 2048 / 1024 / 512 nodes (npde = 2 / 3 / 4), this covers
+// the rest of the reference's range.  Records (doubles): summary = y0[P] v0[PP] w0[PP] ar[PP] bp[PP] Cs[PP] dp[P], padded
+// to a multiple of 8; stored row = a[PP] c[PP] d[P], padded to an even number.
+// =====================================================================================================================
+template <int P> struct LongSys {
+    static constexpr int PP = P * P;
+    static constexpr int sum_doubles = (5 * PP + 2 * P + 7) / 8 * 8;
+    static constexpr int row_doubles = (2 * PP + P + 1) / 2 * 2;
+    static constexpr int oY0 = 0, oV0 = P, oW0 = P + PP, oAr = P + 2 * PP, oBp = P + 3 * PP, oCs = P + 4 * PP, oDp = P + 5 * PP;
+};
+__host__ __device__ constexpr int long_rows_level0(int P) { return P == 1 ? kLongR : (P == 2 ? 8 : (P == 3 ? 4 : 2)); }   // as the batched path
+__host__ __device__ constexpr int long_rows_stored(int P) { return P == 1 ? kLongRS : (P == 2 ? 8 : (P == 3 ? 4 : 2)); }
+__host__ __device__ constexpr int long_rows_top(int P) { return P == 1 ? 16 : (P == 2 ? 8 : (P == 3 ? 4 : 2)); }        // x kLongTT rows at most
+// dynamic shared memory of k6s_back_asm: the tile's u with one node of halo on either side
+__host__ __device__ constexpr size_t long_sys_smem_bytes(int P) { return (size_t)(long_rows_level0(P) * kLongT0 + 2) * P * sizeof(double); }
+
+template <int P> SB_D void ld_block(const double* p, Mat<P>& m) {
+#pragma unroll
+    for (int i = 0; i < P * P; ++i) m.a[i] = __ldcg(p + i);
+}
+template <int P> SB_D void ld_vec(const double* p, Vec<P>& v) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) v.a[i] = __ldcg(p + i);
+}
+template <int P> SB_D void st_block(double* p, const Mat<P>& m) {
+#pragma unroll
+    for (int i = 0; i < P * P; ++i) p[i] = m.a[i];
+}
+template <int P> SB_D void st_vec(double* p, const Vec<P>& v) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = v.a[i];
+}
+
+template <int P, int R>
+SB_D void store_summary_sys(const ChunkThomas<P, R>& th, const LevelDev& lv, int64_t k, int c) {
+    using LS = LongSys<P>;
+    Vec<P> y0, yL; Mat<P> v0, w0, vL, wL;
+    th.summary(y0, v0, w0, yL, vL, wL);
+    double* S = reinterpret_cast<double*>(lv.sum) + ((size_t)k * lv.up_stride + tiled_pos(c, lv.up_R, kLongTT)) * LS::sum_doubles;
+    st_vec<P>(S + LS::oY0, y0); st_block<P>(S + LS::oV0, v0); st_block<P>(S + LS::oW0, w0);
+    st_block<P>(S + LS::oAr, neg(mul(th.As, vL)));
+    st_block<P>(S + LS::oBp, sub_mul(th.Bs, th.As, wL));
+    st_block<P>(S + LS::oCs, th.Cs);
+    st_vec<P>(S + LS::oDp, sub_mul(th.ds, th.As, yL));
+}
+
+// rows of the level above `below` from the summaries of chunks j and j+1 (see form_rows)
+template <int P, int R, int TT>
+SB_D void form_rows_sys(const LevelDev& below, int64_t k, int tile, int t, Mat<P> (&ra)[R], Mat<P> (&rc)[R], Vec<P> (&rd)[R]) {
+    using LS = LongSys<P>;
+    const int n = below.nchunks;
+    const double* S = reinterpret_cast<const double*>(below.sum) + (size_t)k * below.up_stride * LS::sum_doubles;
+    const int j0 = (tile * TT + t) * R;
+    const size_t p0 = (size_t)tile * R * TT + t;
+    const size_t pl = (t + 1 < TT) ? (size_t)tile * R * TT + (t + 1) : (size_t)(tile + 1) * R * TT;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool in = j0 + r < n, in_next = j0 + r + 1 < n;
+        const double* rec = S + (p0 + (size_t)r * TT) * LS::sum_doubles;
+        const double* nxt = S + ((r + 1 < R) ? p0 + (size_t)(r + 1) * TT : (in_next ? pl : p0)) * LS::sum_doubles;
+        Mat<P> ar, bp, Cs, v0n, w0n; Vec<P> dp, y0n;
+        ld_block<P>(rec + LS::oAr, ar); ld_block<P>(rec + LS::oBp, bp); ld_block<P>(rec + LS::oCs, Cs); ld_vec<P>(rec + LS::oDp, dp);
+        ld_vec<P>(nxt + LS::oY0, y0n); ld_block<P>(nxt + LS::oV0, v0n); ld_block<P>(nxt + LS::oW0, w0n);
+        if (!in_next) { y0n = vec_zero<P>(); v0n = mat_zero<P>(); w0n = mat_zero<P>(); }
+        if (!in) { ar = mat_zero<P>(); bp = mat_identity<P>(); Cs = mat_zero<P>(); dp = vec_zero<P>(); }   // identity row
+        const Mat<P> binv = inverse_fast(sub_mul(bp, Cs, v0n));
+        ra[r] = mul(binv, ar);
+        rc[r] = neg(mul(binv, mul(Cs, w0n)));
+        rd[r] = mul(binv, sub_mul(dp, Cs, y0n));
+    }
+}
+
+template <int P>
+SB_D void separators_sys(const LevelDev& up, int64_t k, int c, Vec<P>& xp, Vec<P>& xs) {
+    const double* xu = up.x + (size_t)k * up.stride * P;
+    ld_vec<P>(xu + tiled_pos(c, up.R, kLongTT) * P, xs);
+    if (c > 0) ld_vec<P>(xu + tiled_pos(c - 1, up.R, kLongTT) * P, xp);
+    else xp = vec_zero<P>();
+}
+
+// level 0, forward
+template <class Fn, int R, int TT, bool SYM0>
+__global__ void __launch_bounds__(TT) k6s_chunk_asm(ProbDev pd, double tt, double inv_tau, LevelDev lv) {
+    constexpr int P = Fn::npde;
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int64_t k = blockIdx.y;
+    const size_t toff = (size_t)tile * R * TT;
+    pdl_release();
+    pdl_wait();
+    if (!pd.active[k]) return;
+    const double* ui = pd.u + (size_t)k * pd.L * P;
+    const double* ub = ui + toff * P;
+    const double* bb = pd.b + ((size_t)k * pd.L + toff) * P;
+    double uc[R][P], bc[R][P];
+    load_chunk<P, R, TT>(ub, t, uc);
+    load_chunk<P, R, TT>(bb, t, bc);
+    {   // the iterate at the tile edges and the mesh ends, for the in-place backward sweep
+        double* e = lv.edge + (size_t)k * (2 * pd.ntiles + 2) * P;
+        const int i0 = (int)toff + t * R;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if (t == 0) e[(2 * tile) * P + p] = uc[0][p];
+            if (t == TT - 1) e[(2 * tile + 1) * P + p] = uc[R - 1][p];
+            if (tile == 0 && t == 0) e[(2 * pd.ntiles) * P + p] = uc[0][p];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (i0 + r == pd.Nx - 1) e[(2 * pd.ntiles + 1) * P + p] = uc[r][p];
+        }
+    }
+    ChunkThomas<P, R> th;
+    assemble_chunk<Fn, R, TT, SYM0, true, true>(pd, mesh_of_tile(pd.mesh, toff), ub, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
+                                                pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, ui, ui + tiled_pos(pd.Nx - 1, R, TT) * P);
+    store_summary_sys<P, R>(th, lv, k, tile * TT + t);
+}
+
+// level l >= 1, forward: form the rows, keep them, eliminate, store the chunk summary
+template <int P, int R, int TT>
+__global__ void __launch_bounds__(TT) k6s_chunk_sys(LevelDev lv, LevelDev below, const int* active) {
+    using LS = LongSys<P>;
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int64_t k = blockIdx.y;
+    pdl_release();
+    pdl_wait();
+    if (!active[k]) return;
+    Mat<P> ra[R], rc[R]; Vec<P> rd[R];
+    form_rows_sys<P, R, TT>(below, k, tile, t, ra, rc, rd);
+    ChunkThomas<P, R> th;
+    double* rows = reinterpret_cast<double*>(lv.acd) + ((size_t)k * lv.stride + (size_t)tile * R * TT + t) * LS::row_doubles;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double* row = rows + (size_t)r * TT * LS::row_doubles;
+        st_block<P>(row, ra[r]); st_block<P>(row + LS::PP, rc[r]); st_vec<P>(row + 2 * LS::PP, rd[r]);
+        th.row(r, ra[r], mat_identity<P>(), rc[r], rd[r]);
+    }
+    store_summary_sys<P, R>(th, lv, k, tile * TT + t);
+}
+
+// top level: one CTA per instance
+template <int P, int RT, int TT>
+__global__ void __launch_bounds__(TT) k6s_top(LevelDev lv, LevelDev below, const int* active) {
+    extern __shared__ double sm[];
+    const int t = threadIdx.x;
+    const int64_t k = blockIdx.x;
+    pdl_release();
+    pdl_wait();
+    if (!active[k]) return;
+    Mat<P> ra[RT], rc[RT]; Vec<P> rd[RT];
+    form_rows_sys<P, RT, TT>(below, k, 0, t, ra, rc, rd);
+    ChunkThomas<P, RT> th;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) th.row(r, ra[r], mat_identity<P>(), rc[r], rd[r]);
+    Vec<P> x[RT];
+    th.template finish<TT>(x, sm, t);
+    double* xo = lv.x + (size_t)k * lv.stride * P;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) st_vec<P>(xo + ((size_t)r * TT + t) * P, x[r]);
+}
+
+// level l >= 1, backward
+template <int P, int R, int TT>
+__global__ void __launch_bounds__(TT) k6s_back_sys(LevelDev lv, LevelDev up, const int* active) {
+    using LS = LongSys<P>;
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int64_t k = blockIdx.y;
+    pdl_release();
+    pdl_wait();
+    if (!active[k]) return;
+    ChunkThomas<P, R> th;
+    const size_t base = (size_t)k * lv.stride + (size_t)tile * R * TT;
+    const double* rows = reinterpret_cast<const double*>(lv.acd) + (base + t) * LS::row_doubles;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double* row = rows + (size_t)r * TT * LS::row_doubles;
+        Mat<P> A, C; Vec<P> d;
+        ld_block<P>(row, A); ld_block<P>(row + LS::PP, C); ld_vec<P>(row + 2 * LS::PP, d);
+        th.row(r, A, mat_identity<P>(), C, d);
+    }
+    Vec<P> xp, xs, x[R];
+    separators_sys<P>(up, k, tile * TT + t, xp, xs);
+    th.back(x, xp, xs);
+#pragma unroll
+    for (int r = 0; r < R; ++r) st_vec<P>(lv.x + (base + (size_t)r * TT + t) * P, x[r]);
+}
+
+// level 0, backward: recompute, back-substitute, update u in place, per-tile sum of h^2
+template <class Fn, int R, int TT, bool SYM0>
+__global__ void __launch_bounds__(TT) k6s_back_asm(ProbDev pd, double tt, double inv_tau, LevelDev up, double* partial) {
+    constexpr int P = Fn::npde;
+    __shared__ double red[TT / 32];
+    extern __shared__ __align__(16) double k6sm[];      // [(R*TT + 2) * P]: the tile's u with one node of halo on either side
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int64_t k = blockIdx.y;
+    const size_t toff = (size_t)tile * R * TT;
+    pdl_release();
+    pdl_wait();
+    if (!pd.active[k]) return;
+    double* ug = pd.u + ((size_t)k * pd.L + toff) * P;
+    const double* bb = pd.b + ((size_t)k * pd.L + toff) * P;
+    const double* e = up.edge + (size_t)k * (2 * pd.ntiles + 2) * P;
+    double* um = k6sm + P;
+    double uc[R][P], bc[R][P];
+    load_chunk<P, R, TT>(ug, t, uc);
+    load_chunk<P, R, TT>(bb, t, bc);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < P; ++p) um[(r * TT + t) * P + p] = uc[r][p];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (t == 0 && tile > 0) um[-P + p] = e[(2 * (tile - 1) + 1) * P + p];
+        if (t == TT - 1 && tile + 1 < pd.ntiles) um[R * TT * P + p] = e[(2 * (tile + 1)) * P + p];
+    }
+    __syncthreads();
+    ChunkThomas<P, R> th;
+    assemble_chunk<Fn, R, TT, SYM0, true, true>(pd, mesh_of_tile(pd.mesh, toff), um, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
+                                                pd.prm + (size_t)k * pd.nprm_s, uc, bc, th, (int)toff, e + (2 * pd.ntiles) * P,
+                                                e + (2 * pd.ntiles + 1) * P);
+    Vec<P> xp, xs, h[R];
+    separators_sys<P>(up, k, tile * TT + t, xp, xs);
+    th.back(h, xp, xs);
+    double ss = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool in = (int)toff + t * R + r < pd.Nx;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            ug[(size_t)(r * TT + t) * P + p] = in ? uc[r][p] - h[r].a[p] : 0.0;
+            if (in) ss += h[r].a[p] * h[r].a[p];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
+    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int w = 1; w < TT / 32; ++w) ss += red[w];
+        partial[(size_t)k * pd.ntiles + tile] = ss;
+    }
+}
+
+// residual-only / residual+Jacobian of a long mesh of a system into F (and Jl, Jd, Ju)
+template <class Fn, int R, int TT, bool SYM0, bool JAC>
+__global__ void __launch_bounds__(TT) k6s_assemble(ProbDev pd, double tt, double inv_tau, int all_instances) {
+    constexpr int P = Fn::npde;
+    const int tile = blockIdx.x, t = threadIdx.x;
+    const int64_t k = blockIdx.y;
+    if (!all_instances && !pd.active[k]) return;
+    const size_t toff = (size_t)tile * R * TT;
+    const double* ui = pd.u + (size_t)k * pd.L * P;
+    const double* ub = ui + toff * P;
+    const double* bb = pd.b + ((size_t)k * pd.L + toff) * P;
+    double uc[R][P], bc[R][P];
+    load_chunk<P, R, TT>(ub, t, uc);
+    if constexpr (JAC) load_chunk<P, R, TT>(bb, t, bc);
+    else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < P; ++p) bc[r][p] = 0.0;
+    }
+    ProbDev pt = pd;  // StoreSink addresses (k*L + r*TT + t): shift the output arrays to the tile
+    pt.F = pd.F + toff * P;
+    if (JAC) { pt.Jl = pd.Jl + toff * P * P; pt.Jd = pd.Jd + toff * P * P; pt.Ju = pd.Ju + toff * P * P; }
+    StoreSink<P, TT> sink{pt, k, t};
+    assemble_chunk<Fn, R, TT, SYM0, JAC, true>(pd, mesh_of_tile(pd.mesh, toff), ub, bb, pd.mass + (size_t)k * 4 * P, t, tt, inv_tau,
+                                               pd.prm + (size_t)k * pd.nprm_s, uc, bc, sink, (int)toff, ui, ui + tiled_pos(pd.Nx - 1, R, TT) * P);
+}
+
 }  // namespace sb

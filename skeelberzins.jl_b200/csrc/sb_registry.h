@@ -95,8 +95,15 @@ FunctorEntry make_entry(const char* name) {
         e.long_assemble_jac[1] = k6_assemble<Fn, kLongR, kLongT0, true, true>;
         e.long_assemble_val[0] = k6_assemble<Fn, kLongR, kLongT0, false, false>;
         e.long_assemble_val[1] = k6_assemble<Fn, kLongR, kLongT0, true, false>;
-    } else {
-        for (int s = 0; s < 2; ++s) { e.long_chunk[s] = nullptr; e.long_back[s] = nullptr; e.long_smem[s] = 0; e.long_assemble_jac[s] = nullptr; e.long_assemble_val[s] = nullptr; }
+    } else {   // systems: the generic-P kernels (sb_longmesh.cuh, "Systems on long meshes")
+        constexpr int R0 = long_rows_level0(Fn::npde);
+        e.long_chunk[0] = k6s_chunk_asm<Fn, R0, kLongT0, false>; e.long_chunk[1] = k6s_chunk_asm<Fn, R0, kLongT0, true>;
+        e.long_back[0] = k6s_back_asm<Fn, R0, kLongT0, false>; e.long_back[1] = k6s_back_asm<Fn, R0, kLongT0, true>;
+        e.long_smem[0] = e.long_smem[1] = long_sys_smem_bytes(Fn::npde);
+        e.long_assemble_jac[0] = k6s_assemble<Fn, R0, kLongT0, false, true>;
+        e.long_assemble_jac[1] = k6s_assemble<Fn, R0, kLongT0, true, true>;
+        e.long_assemble_val[0] = k6s_assemble<Fn, R0, kLongT0, false, false>;
+        e.long_assemble_val[1] = k6s_assemble<Fn, R0, kLongT0, true, false>;
     }
     return e;
 }

@@ -315,6 +315,47 @@ def test_longmesh_graded_mesh_vs_oracle(ctx, oracle):
     assert np.array_equal(its, r["iters"])
 
 
+@pytest.mark.parametrize("Nx,force,top_rows", [(2500, False, None), (1500, True, None), (5000, False, 256)])
+def test_longmesh_two_species_vs_oracle(ctx, oracle, monkeypatch, Nx, force, top_rows):
+    """npde = 2 (Example106, reaction-diffusion) beyond the batched range of 2048 nodes -- and forced onto the long path
+    below it -- through the block version of the long-mesh kernels; with the top level lowered to 256 rows the 640 chunk
+    rows of the 5000-node mesh pass through a stored level.  Final state, iteration counts, assemble! and the Jacobian
+    blocks against the oracle.  (On these meshes the second Newton correction of the linear problem sits at its
+    rounding floor, 3e-11 .. 5e-10: the stop tolerance is 1e-8 here and in the oracle, above the floor.)"""
+    if force:
+        monkeypatch.setenv("SB_FORCE_LONGMESH", "1")
+    if top_rows:
+        monkeypatch.setenv("SB_LONG_TOP_ROWS", str(top_rows))
+    c = ex.baseline_case("4", B=3, Nx=Nx)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:4]
+    fn = sb.Functor(c.functor, c.params)
+    sol, hist, dev = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, hist=True, squeeze=False,
+                              save="last", return_device=True, tol=1e-8)
+    assert dev.longmesh()
+    r = oracle.pdepe_transient(c.functor, c.m, c.xmesh, c.params, c.initial(), tg, None, tol=1e-8)
+    uo = np.transpose(r["u"], (0, 2, 1))                      # reference shape [B][npde][Nx]
+    assert np.abs(sol.u[-1] - uo).max() < RTOL * np.abs(uo).max()
+    its = np.array([[len(h[k]) for h in hist] for k in range(c.B)])
+    assert np.array_equal(its, r["iters"])
+    u = r["u"]
+    assert _relerr(dev.assemble(u, 0.3), oracle.assemble(c.functor, c.m, c.xmesh, c.params, u, 0.3)) < 1e-12
+    dev.set_design("split")
+    dev.upload(u)
+    dev.mass_flags(0.1)
+    M = oracle.mass(c.functor, c.m, c.xmesh, c.params, u, 0.1)
+    dev.begin_step(0.3, 100.0)
+    dev.residual_jacobian()
+    F, Jl, Jd, Ju = dev.debug_system()
+    b = M * u
+    Fo, Jlo, Jdo, Juo = oracle.residual_jacobian(c.functor, c.m, c.xmesh, c.params, b, b, 1e-2, M, 0.3)
+    scale = np.abs(Jdo).max()
+    assert np.abs(F - Fo).max() <= 1e-12 * max(np.abs(Fo).max(), 1.0)
+    for A, Ao in ((Jl, Jlo), (Jd, Jdo), (Ju, Juo)):
+        assert np.abs(A - Ao).max() <= 1e-12 * scale
+    dev.close()
+
+
 def test_longmesh_assemble_entrywise(ctx, oracle):
     """assemble! and the Jacobian rows of a long mesh (tiles with neighbours in other tiles) against the oracle."""
     rng = np.random.default_rng(7)

@@ -190,3 +190,40 @@ def test_three_and_four_species_systems(ctx, oracle, npde, Nx, design):
             assert np.abs(dev.download() - u).max() < 1e-13 * np.abs(u).max() and np.array_equal(it1, its)
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("npde,Nx,top_rows", [(3, 1500, None), (3, 3000, 256), (4, 700, None)])
+def test_wide_systems_on_long_meshes(ctx, oracle, monkeypatch, npde, Nx, top_rows):
+    """Meshes beyond the batched range of a wide system (npde = 3: 1024 nodes, npde = 4: 512) take the long-mesh path
+    with P x P blocks (k6s_* kernels compiled through the plugin): host-owned and C Newton loops against the oracle;
+    with the top level lowered to 256 rows the 750 chunk rows of the 3000-node mesh pass through a stored level."""
+    if top_rows:
+        monkeypatch.setenv("SB_LONG_TOP_ROWS", str(top_rows))
+    src, name, oracle_id, base = WIDE[npde]
+    fid = sb.register_user_functor(src, name, npde, len(base))
+    B = 2
+    prm = np.tile(np.array(base), (B, 1)) * (1.0 + 0.1 * np.arange(B))[:, None]
+    x = ex.linspace(0, 1, Nx)
+    u0 = np.zeros((B, Nx, npde))
+    u0[:, :, 0] = np.exp(-5 * x)
+    tg = np.linspace(0.0, 0.15, 4)
+    dev = sb.DeviceProblem(ctx, 0, x, sb.Functor(fid, prm), design="fused")
+    try:
+        assert dev.longmesh()
+        dev.upload(u0)
+        dev.mass_flags(tg[0])
+        assert np.array_equal(dev.mass(), oracle.mass(oracle_id, 0, x, prm, u0, tg[0]))
+        its = np.empty((B, tg.size - 1), dtype=np.int32)
+        for i in range(tg.size - 1):
+            dev.begin_step(tg[i + 1], 1.0 / (tg[i + 1] - tg[i]))
+            if i % 2:
+                dev.newton_solve(1e-10, 100)
+            else:
+                sb.api._newton_loop(dev, 1e-10, 100)
+            its[:, i] = dev.step_iters()
+        u = dev.download().copy()
+        r = oracle.pdepe_transient(oracle_id, 0, x, prm, u0, tg, None)
+        assert np.abs(u - r["u"]).max() < 1e-10 * np.abs(r["u"]).max()
+        assert np.array_equal(its, r["iters"])
+    finally:
+        dev.close()
