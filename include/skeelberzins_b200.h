@@ -248,6 +248,13 @@ int sb_solve_steps(sb_problem* pb, int nsteps, const double* tgrid, double tau, 
 int sb_solve_steps_opt(sb_problem* pb, int nsteps, const double* tgrid, const double* tgrid_per_instance, double tau,
                        double tol, int maxit, int32_t* step_iters, double* snapshots, int* steps_done);
 
+/* The same time loop when only u(t_end) is wanted (src/pdepe.jl:112-120 with the last state): final_state is host
+ * [B][Nx][npde] (pinned memory recommended) and receives the result round by round of instances, on a second stream,
+ * while later rounds still compute -- the download of sb_state_download hidden behind the solve.  The device state is
+ * u(t_end) as after sb_solve_steps.  Resident design and batched range only, otherwise SB_ERR_UNSUPPORTED.          */
+int sb_solve_steps_final(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, double* final_state,
+                         int* steps_done);
+
 /* diagnostics (host arrays of length B unless stated)                                            */
 int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iterations this step  */
 int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */

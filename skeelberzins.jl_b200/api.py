@@ -397,6 +397,22 @@ class DeviceProblem:
         _lib.check(rc)
         return its
 
+    def solve_steps_final(self, tgrid, tau, tol, maxit, out=None):
+        """sb_solve_steps_final: the whole-solve kernel, u(t_end) delivered to host memory [B, Nx, npde] round by round
+        of instances while later rounds compute (the download hidden behind the solve).  Returns the array."""
+        tg = np.ascontiguousarray(tgrid, dtype=np.float64)
+        if out is None:
+            out = pinned_empty((self.B, self.Nx, self.npde))
+        elif out.dtype != np.float64 or out.size != self.B * self.Nx * self.npde or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array [B, Nx, npde]")
+        done = ctypes.c_int()
+        rc = self.lib.sb_solve_steps_final(self._h, tg.size - 1, _lib.ptr(tg), float(tau) if tau is not None else -1.0,
+                                           float(tol), int(maxit), _lib.ptr(out), ctypes.byref(done))
+        if rc == _lib.SB_ERR_CONVERGENCE:
+            raise ConvergenceFailed("convergence failed")
+        _lib.check(rc)
+        return out
+
     def _get(self, fn, dtype):
         out = np.empty(self.B, dtype=dtype)
         _lib.check(fn(self._h, _lib.ptr(out)))
@@ -832,7 +848,7 @@ def _pdepe_streams(m, pdefun, icfun, bdfun, x, tspan, params, ctx, design, squee
         _release(dev)
     if errors:
         raise errors[0]
-    u = out[:, :, 0] if npde == 1 else np.ascontiguousarray(np.transpose(out, (0, 2, 1)))
+    u = out[:, :, 0] if npde == 1 else np.transpose(out, (0, 2, 1))
     return DiffEqArray([u], timeSteps[-1:])
 
 
@@ -949,8 +965,9 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     if params.hist:
         dev.enable_history(params.maxit)
 
-    def shape(u):  # [B,Nx,npde] -> reference shapes
-        u = u[:, :, 0] if npde == 1 else np.ascontiguousarray(np.transpose(u, (0, 2, 1)))
+    def shape(u):  # [B,Nx,npde] -> reference shapes ([npde, Nx] per instance for systems: a transposed VIEW of the
+        # downloaded buffer -- copying 67 MB into the other order costs 15 ms on cfg4, 6 % of the whole call)
+        u = u[:, :, 0] if npde == 1 else np.transpose(u, (0, 2, 1))
         return u[0] if squeeze else u
 
     dev.upload(inival)
@@ -997,13 +1014,17 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     if whole:
         # the time loop of src/pdepe.jl:90-108 in one launch (sb_solve_steps_opt); with save="all" every state is
         # written by the kernel and streamed to pinned host memory round by round while later rounds compute
-        snaps = pinned_empty((nsteps + 1, B, Nx, npde)) if save == "all" else None
-        dev.solve_steps_opt(None if per_instance else timeSteps, tau, params.tol, params.maxit, snapshots=snaps,
-                            tgrid_per_instance=grids if per_instance else None)
-        if save == "all":
-            results = [shape(snaps[i]) for i in range(nsteps + 1)]
+        if save != "all" and not per_instance:
+            # only u(t_end): finished rounds of instances travel to the host while later rounds compute
+            results = [shape(dev.solve_steps_final(timeSteps, tau, params.tol, params.maxit))]
         else:
-            results = [shape(dev.download())]
+            snaps = pinned_empty((nsteps + 1, B, Nx, npde)) if save == "all" else None
+            dev.solve_steps_opt(None if per_instance else timeSteps, tau, params.tol, params.maxit, snapshots=snaps,
+                                tgrid_per_instance=grids if per_instance else None)
+            if save == "all":
+                results = [shape(snaps[i]) for i in range(nsteps + 1)]
+            else:
+                results = [shape(dev.download())]
     else:
         results = [shape(inival.reshape(B, Nx, npde))] if save == "all" else []
         if save != "all" and not params.hist and c_loop and timeSteps.size > 1:

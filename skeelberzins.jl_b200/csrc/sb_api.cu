@@ -341,6 +341,7 @@ struct sb_problem {
     int top_R = 1;
     bool top_configured = false;
     double *d_lm = nullptr, *d_partial = nullptr;
+    double* h_prm = nullptr;   // pinned staging of the parameter blocks (sb_problem_set_params)
     int* d_auto = nullptr;              // device-side stepping: {time step, iteration} (sb_solve_steps)
     double* d_tgrid = nullptr;          // its time grid
     int tgrid_cap = 0;
@@ -1132,6 +1133,7 @@ int sb_problem_destroy(sb_problem* pb) {
     guarded_free(pb->d_mass); guarded_free(pb->d_norm); guarded_free(pb->d_hist); guarded_free(pb->d_tmp); guarded_free(pb->d_active);
     guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid); guarded_free(pb->d_uin); guarded_free(pb->d_eval); guarded_free(pb->d_piv); guarded_free(pb->d_piv_lock); guarded_free(pb->d_itgrid); guarded_free(pb->d_step_iters); guarded_free(pb->d_snap); guarded_free(pb->d_rmisc);
     if (pb->h_rounds) cudaFreeHost(pb->h_rounds);
+    if (pb->h_prm) cudaFreeHost(pb->h_prm);
     if (pb->copy_stream) cudaStreamDestroy(pb->copy_stream);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
@@ -1186,8 +1188,16 @@ int sb_problem_set_params(sb_problem* pb, const double* params_host) {
     if (pb->nparams == 0) return SB_OK;
     if (!params_host) return fail(SB_ERR_INVALID, "params is NULL");
     CU(cudaSetDevice(pb->ctx->device));
-    CU(cudaMemcpy2DAsync(pb->d_prm, pb->pd.nprm_s * sizeof(double), params_host, pb->nparams * sizeof(double),
-                         pb->nparams * sizeof(double), (size_t)pb->pd.B, cudaMemcpyHostToDevice, pb->ctx->stream));
+    // packed into the padded device stride in a pinned staging buffer, then ONE contiguous copy: a strided 2-D copy of
+    // B rows of a few doubles from pageable memory costs 0.2 us per row (cfg4: 2.7 ms of a 4 ms call)
+    const size_t n = (size_t)pb->pd.B * pb->pd.nprm_s;
+    if (!pb->h_prm) CU(cudaHostAlloc((void**)&pb->h_prm, n * sizeof(double), cudaHostAllocDefault));
+    const int np = pb->nparams, ns = pb->pd.nprm_s;
+    for (int64_t k = 0; k < pb->pd.B; ++k) {
+        for (int i = 0; i < np; ++i) pb->h_prm[(size_t)k * ns + i] = params_host[(size_t)k * np + i];
+        for (int i = np; i < ns; ++i) pb->h_prm[(size_t)k * ns + i] = 0.0;
+    }
+    CU(cudaMemcpyAsync(pb->d_prm, pb->h_prm, n * sizeof(double), cudaMemcpyHostToDevice, pb->ctx->stream));
     CU(cudaStreamSynchronize(pb->ctx->stream));
     return SB_OK;
 }
@@ -1603,9 +1613,11 @@ static int grow(T** p, size_t* cap, size_t need, cudaStream_t st) {
 
 // nsteps implicit-Euler steps (tgrid != NULL) or one Newton solve at (t_single, inv_tau_single) on the b that
 // sb_begin_step prepared (tgrid == NULL), every instance resident on its SM from the first to the last iteration.
+// snap_host: every state [nsteps+1][B][row], or -- final_only -- u(t_end) alone [B][row]; either way finished rounds of
+// instances leave for the host while later rounds compute
 static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const double* inst_tgrid, double tau, double t_single,
                           double inv_tau_single, double tol, int maxit, int32_t* step_iters_host, double* snap_host,
-                          int* steps_done, int* max_iters_out) {
+                          int* steps_done, int* max_iters_out, bool final_only = false) {
     cudaStream_t st = pb->ctx->stream;
     const ProbDev& pd = pb->pd;
     const int64_t B = pd.B;
@@ -1655,9 +1667,10 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
     const size_t row = (size_t)pd.Nx * pb->P;              // doubles per instance and snapshot
     const bool stream_snaps = snap_host != nullptr && rounds <= kMaxRounds;
     if (snap_host) {
-        int rc = grow(&pb->d_snap, &pb->snap_cap, (size_t)(nsteps + 1) * B * row, st);
+        int rc = grow(&pb->d_snap, &pb->snap_cap, (size_t)(final_only ? 1 : nsteps + 1) * B * row, st);
         if (rc) return rc;
         ra.snap = pb->d_snap;
+        ra.snap_last = final_only ? 1 : 0;
         if (!pb->copy_stream) CU(cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking));
     }
     unsigned int init[4] = {0x7fffffffu, 0u, 0u, 0u};
@@ -1682,7 +1695,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
     pb->launched = 0; pb->confirmed = 0;
 
     if (snap_host) {
-        const int s0 = b_given ? 1 : 0;
+        const int s0 = (b_given && !final_only) ? 1 : 0, s1 = final_only ? 0 : nsteps;
         if (stream_snaps) {
             // finished rounds leave for the host while later rounds compute (src/pdepe.jl:99-107 stores every step)
             for (int r = 0; r < rounds; ++r) {
@@ -1696,7 +1709,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
                     }
                 }
                 const int64_t k0 = (int64_t)r * stride, nk = std::min<int64_t>(stride, B - k0);
-                for (int s = s0; s <= nsteps; ++s) {
+                for (int s = s0; s <= s1; ++s) {
                     const size_t off = ((size_t)s * B + k0) * row;
                     CU(cudaMemcpyAsync(snap_host + off, pb->d_snap + off, (size_t)nk * row * sizeof(double), cudaMemcpyDeviceToHost, pb->copy_stream));
                 }
@@ -1705,7 +1718,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         } else {
             CU(cudaStreamSynchronize(st));
             const size_t off = (size_t)s0 * B * row;
-            CU(cudaMemcpy(snap_host + off, pb->d_snap + off, ((size_t)(nsteps + 1 - s0) * B * row) * sizeof(double), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(snap_host + off, pb->d_snap + off, ((size_t)(s1 + 1 - s0) * B * row) * sizeof(double), cudaMemcpyDeviceToHost));
         }
     }
     unsigned int res[4];
@@ -1861,6 +1874,19 @@ int sb_solve_steps_opt(sb_problem* pb, int nsteps, const double* tgrid, const do
     pb->design = pb->design_pending;
     return solve_resident(pb, nsteps, tgrid_per_instance ? nullptr : tgrid, tgrid_per_instance, tgrid_per_instance ? -1.0 : tau, 0.0, 0.0,
                           tol, maxit, step_iters, snapshots, steps_done, nullptr);
+}
+
+int sb_solve_steps_final(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, double* final_state,
+                         int* steps_done) {
+    if (!pb || !tgrid || !final_state || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
+    if (steps_done) *steps_done = 0;
+    if (maxit < 1) return fail(SB_ERR_INVALID, "maxit must be >= 1");
+    if (pb->longmesh) return fail(SB_ERR_UNSUPPORTED, "sb_solve_steps_final: the long-mesh path has no whole-solve kernel; use sb_solve_steps and sb_state_download");
+    if (!resident_enabled(pb)) return fail(SB_ERR_UNSUPPORTED, "sb_solve_steps_final needs the resident design (whole-solve kernel)");
+    if (pb->pd.hist && nsteps > 1) return fail(SB_ERR_UNSUPPORTED, "norm histories are kept per step: drive the steps one by one with hist enabled");
+    CU(cudaSetDevice(pb->ctx->device));
+    pb->design = pb->design_pending;
+    return solve_resident(pb, nsteps, tgrid, nullptr, tau, 0.0, 0.0, tol, maxit, nullptr, final_state, steps_done, nullptr, true);
 }
 
 #define SB_GET(NAME, TYPE, DEVPTR)                                                                       \

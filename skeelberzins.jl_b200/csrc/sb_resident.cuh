@@ -30,6 +30,7 @@ struct ResidentArgs {
     double t_single, inv_tau_single;  // nsteps == 1 without a grid: one Newton solve at (t, 1/tau)  (sb_newton_solve)
     int* step_iters;                // [B][nsteps] Newton iterations of every instance in every step, or null
     double* snap;                   // [nsteps + 1][B][Nx*P] every state, reference layout, or null
+    int snap_last;                  // snap holds ONE state per instance, [B][Nx*P]: u(t_end) only (streamed out like the snapshots)
     unsigned int* round_done;       // [rounds] instances finished per round of the grid (snapshot streaming), or null
     volatile unsigned int* host_rounds;   // [rounds] mapped host flags: round complete
     int* fail_step;                 // [1] smallest step index in which an instance failed to converge (init INT_MAX)
@@ -129,7 +130,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
             }
         };
         group_sync<TT>(bar);               // parameters and mass flags visible
-        if (ra.snap && !ra.b_given) snapshot(0);
+        if (ra.snap && !ra.snap_last && !ra.b_given) snapshot(0);
 
         long long total = 0;
         int status = 0, it_last = 0, failed_at = -1;
@@ -222,7 +223,7 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
                 if (ra.max_iters) atomicMax(ra.max_iters, it);
             }
             if (!conv) { failed_at = s; if (status == 0 || status == 3) status = 1; break; }
-            if (ra.snap) snapshot(s + 1);
+            if (ra.snap && (!ra.snap_last || s + 1 == nsteps)) snapshot(ra.snap_last ? 0 : s + 1);
         }
         // ---- the instance goes back to HBM -------------------------------------------------------------------------
         double* ug = pd.u + (size_t)k * L * P;

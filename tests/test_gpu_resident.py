@@ -249,3 +249,31 @@ def test_devices_argument_shards_the_batch(ctx, oracle):
         assert np.array_equal(a, b)
     last = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), tstep=tg, c_loop=True, devices=devices, save="last")
     assert np.array_equal(last.u[-1], one.u[-1])
+
+
+@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 3000, 64, 4), ("4", 900, 100, 5), ("3a", 40, 512, 6)])
+def test_final_state_streamed_out_during_the_solve(ctx, cfg, B, Nx, nsteps):
+    """sb_solve_steps_final: u(t_end) arrives in host memory round by round of instances while later rounds compute
+    (3000 instances of 64 nodes are several rounds of the persistent grid); bit-identical to a solve followed by a
+    download, which is also what the device state holds afterwards, and what pdepe(save="last", c_loop=True) returns."""
+    c = ex.baseline_case(cfg, B=B, Nx=Nx)
+    tg, tau = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:nsteps + 1]
+    fn = sb.Functor(c.functor, c.params)
+    dev = sb.DeviceProblem(ctx, c.m, c.xmesh, fn)
+    try:
+        dev.upload(c.initial())
+        dev.mass_flags(tg[0])
+        dev.solve_steps_opt(tg, None, 1e-10, 100)             # (vector-tstep semantics, as the pdepe call below)
+        ref = dev.download().copy()
+        dev.upload(c.initial())
+        dev.mass_flags(tg[0])
+        out = dev.solve_steps_final(tg, None, 1e-10, 100)
+        assert np.array_equal(out, ref)
+        assert np.array_equal(dev.download(), ref)
+    finally:
+        dev.close()
+    sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, squeeze=False, save="last", c_loop=True)
+    got = np.asarray(sol.u[-1])
+    want = ref[:, :, 0] if c.npde == 1 else np.transpose(ref, (0, 2, 1))
+    assert np.array_equal(got, want)

@@ -1,7 +1,8 @@
-"""Where the end-to-end time of a stationary long-mesh solve goes: the public pdepe() call taken apart, host wall clock
-around synchronised phases (cfg5 by default).  Steers tuning; bench.py produces the reported numbers.
+"""Where the end-to-end time of a solve goes: the public pdepe() call taken apart, host wall clock around
+synchronised phases (cfg5 by default; transient configs: the whole-solve kernel).  Steers tuning; bench.py produces
+the reported numbers.
 
-    python tools/e2e_breakdown.py [--config 5]
+    python tools/e2e_breakdown.py [--config 5 | 2 | 3a | 3b | 4]
 """
 import argparse
 import os
@@ -24,12 +25,19 @@ def main():
     fn = sb.Functor(c.functor, c.params)
     u0 = api.pinned_empty((c.params.shape[0], c.xmesh.size, c.npde))
     u0[:] = c.initial()
+    stationary = c.tspan is None
+
+    def call():
+        if stationary:
+            return sb.pdepe(c.m, fn, u0, fn, c.xmesh, ctx=ctx, c_loop=True, squeeze=False)
+        return sb.pdepe(c.m, fn, u0, fn, c.xmesh, c.tspan, ctx=ctx, tstep=c.tstep, save="last", c_loop=True, squeeze=False)
+
     t0 = time.perf_counter()
-    sb.pdepe(c.m, fn, u0, fn, c.xmesh, ctx=ctx, c_loop=True, squeeze=False)
+    call()
     ctx.synchronize()
     cold = (time.perf_counter() - t0) * 1e3          # first call: problem set-up (mesh weights, allocations) included
     for _ in range(3):
-        sb.pdepe(c.m, fn, u0, fn, c.xmesh, ctx=ctx, c_loop=True, squeeze=False)
+        call()
     T = {}
 
     def lap(name, t0):
@@ -40,15 +48,23 @@ def main():
     n = 5
     for _ in range(n):
         t = time.perf_counter()
-        Nx, npde, inival, pb = api.problem_init(c.m, c.xmesh, (0, 1), fn, u0, fn, api.Params(), ctx, "resident")
+        Nx, npde, inival, pb = api.problem_init(c.m, c.xmesh, (0, 1) if stationary else c.tspan, fn, u0, fn, api.Params(), ctx, "resident")
         t = lap("problem_init (pool lookup, mesh compare)", t)
         dev = pb.device
         dev.upload(inival)
         t = lap("upload (H2D + layout)", t)
-        dev.mass_flags(1.0, stationary=True)
-        t = lap("mass_flags", t)
-        api.newton_stat(pb, np.inf, 1.0, 1e-10, 100, False, True)
-        t = lap("newton_stat (C loop)", t)
+        if stationary:
+            dev.mass_flags(1.0, stationary=True)
+            t = lap("mass_flags", t)
+            api.newton_stat(pb, np.inf, 1.0, 1e-10, 100, False, True)
+            t = lap("newton_stat (C loop)", t)
+        else:
+            tg, tau = sb.time_grid(c.tspan, c.tstep)
+            t = lap("time_grid", t)
+            dev.mass_flags(tg[0])
+            t = lap("mass_flags", t)
+            dev.solve_steps_opt(tg, tau, 1e-10, 100)
+            t = lap("solve_steps_opt (one launch)", t)
         u = dev.download()
         t = lap("download (layout + D2H)", t)
         pb.device = None
@@ -57,7 +73,7 @@ def main():
         t = lap("release", t)
     t0 = time.perf_counter()
     for _ in range(n):
-        sb.pdepe(c.m, fn, u0, fn, c.xmesh, ctx=ctx, c_loop=True, squeeze=False)
+        call()
     ctx.synchronize()
     whole = (time.perf_counter() - t0) * 1e3 / n
     for k, v in T.items():
