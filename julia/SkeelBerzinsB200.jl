@@ -241,8 +241,9 @@ _merge(params, kwargs) = Params(; (f => get(kwargs, f, getfield(params, f)) for 
 
 """Transient pdepe (src/pdepe.jl:42-128) for the batch.  Returns a `DiffEqArray` (`sol.u[k]` = `[npde*Nx, B]` states at
 `sol.t[k]`, `sol(t)`, `sol(x_eval, t, pb)`) and, as in the reference, `pb` / `storage` when `data` / `hist` are set.
-`c_loop = true` hands the time loop and the Newton loop to C (one kernel launch for the whole solve)."""
-function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params(), ctx = Context(0), c_loop = false, kwargs...)
+`c_loop = true` hands the time loop and the Newton loop to C (one kernel launch for the whole solve); with
+`save = :last` only u(t_end) is kept (`sb_solve_steps_final`: the download travels while later instances compute)."""
+function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params(), ctx = Context(0), c_loop = false, save = :all, kwargs...)
     params = _merge(params, kwargs)
     @assert m == 0 || m == 1 || m == 2 "Parameter m invalid"
     @assert m == 0 || m > 0 && xmesh[1] ≥ 0 "Non-conforming mesh"
@@ -259,8 +260,19 @@ function pdepe(m, pdefun::Functor, icfun, bdfun, xmesh, tspan; params = Params()
         # the time loop and the Newton loop in C: with the resident design the whole solve is one kernel launch
         # (sb_solve_steps_opt) that also writes every state, streamed out while later instances compute
         nsteps = length(timeSteps) - 1
-        snaps = Array{Float64, 3}(undef, npde * Nx, batch(pdefun), nsteps + 1)      # C layout [nsteps+1][B][Nx][npde]
         done = Ref{Cint}(0)
+        if save == :last
+            final = Array{Float64, 2}(undef, npde * Nx, batch(pdefun))                   # C layout [B][Nx][npde]
+            rc = ccall((:sb_solve_steps_final, libsb), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Float64}, Cdouble, Cdouble, Cint, Ptr{Float64}, Ref{Cint}),
+                       pb.handle, nsteps, collect(Float64, timeSteps), flag_tstep ? Float64(tstep) : -1.0, params.tol,
+                       params.maxit, final, done)
+            rc == -4 && throw("convergence failed")                                   # src/utils.jl:336
+            check(rc)
+            sol = DiffEqArray([final], [Float64(timeSteps[end])])
+            return params.data ? (sol, pb) : sol
+        end
+        snaps = Array{Float64, 3}(undef, npde * Nx, batch(pdefun), nsteps + 1)      # C layout [nsteps+1][B][Nx][npde]
         rc = ccall((:sb_solve_steps_opt, libsb), Cint,
                    (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Ptr{Int32}, Ptr{Float64}, Ref{Cint}),
                    pb.handle, nsteps, collect(Float64, timeSteps), C_NULL, flag_tstep ? Float64(tstep) : -1.0, params.tol,
