@@ -255,6 +255,15 @@ int sb_solve_steps_opt(sb_problem* pb, int nsteps, const double* tgrid, const do
 int sb_solve_steps_final(sb_problem* pb, int nsteps, const double* tgrid, double tau, double tol, int maxit, double* final_state,
                          int* steps_done);
 
+/* The whole data path of a transient pdepe call (src/pdepe.jl:66-110) as one pipelined operation: initial states from
+ * host memory u0_host [B][Nx][npde], mass flags at t0, the time loop, u(t_end) to host memory final_state [B][Nx][npde]
+ * (both pinned for real overlap).  Equivalent to sb_state_upload + sb_mass_flags(t0, 0) + sb_solve_steps_final, except
+ * that the states are uploaded in chunks of instances WHILE the whole-solve kernel already iterates on the chunks that
+ * have arrived (it waits per instance on an arrival word written by the copy engine), as finished rounds are downloaded
+ * while later ones iterate: neither transfer is exposed.  Resident design, batched range.                         */
+int sb_solve_from_host(sb_problem* pb, const double* u0_host, double t0, int nsteps, const double* tgrid, double tau, double tol,
+                       int maxit, double* final_state, int* steps_done);
+
 /* diagnostics (host arrays of length B unless stated)                                            */
 int sb_get_step_iters(sb_problem* pb, int32_t* iters_host);       /* Newton iterations this step  */
 int sb_get_total_iters(sb_problem* pb, int64_t* total_host);      /* since sb_state_upload        */

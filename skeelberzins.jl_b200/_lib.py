@@ -62,6 +62,7 @@ SIGNATURES = {
     "sb_solve_steps": (_c.c_int, [_vp, _c.c_int, _vp, _c.c_double, _c.c_double, _c.c_int, _c.POINTER(_c.c_int)]),
     "sb_solve_steps_opt": (_c.c_int, [_vp, _c.c_int, _vp, _vp, _c.c_double, _c.c_double, _c.c_int, _vp, _vp, _c.POINTER(_c.c_int)]),
     "sb_solve_steps_final": (_c.c_int, [_vp, _c.c_int, _vp, _c.c_double, _c.c_double, _c.c_int, _vp, _c.POINTER(_c.c_int)]),
+    "sb_solve_from_host": (_c.c_int, [_vp, _vp, _c.c_double, _c.c_int, _vp, _c.c_double, _c.c_double, _c.c_int, _vp, _c.POINTER(_c.c_int)]),
     "sb_get_step_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_total_iters": (_c.c_int, [_vp, _vp]),
     "sb_get_last_norm": (_c.c_int, [_vp, _vp]),

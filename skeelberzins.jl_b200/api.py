@@ -413,6 +413,26 @@ class DeviceProblem:
         _lib.check(rc)
         return out
 
+    def solve_from_host(self, u0, t0, tgrid, tau, tol, maxit, out=None):
+        """sb_solve_from_host: upload, mass flags at t0, the whole-solve kernel and the download of u(t_end) as one
+        pipelined operation -- chunks of instances are uploaded while the kernel already iterates on those that have
+        arrived, finished rounds are downloaded while later ones iterate.  u0 [B, Nx, npde] (pinned for real overlap:
+        ``pinned_empty``); returns u(t_end) [B, Nx, npde]."""
+        u0 = self._nodes(u0)
+        tg = np.ascontiguousarray(tgrid, dtype=np.float64)
+        if out is None:
+            out = pinned_empty((self.B, self.Nx, self.npde))
+        elif out.dtype != np.float64 or out.size != self.B * self.Nx * self.npde or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array [B, Nx, npde]")
+        done = ctypes.c_int()
+        rc = self.lib.sb_solve_from_host(self._h, _lib.ptr(u0), float(t0), tg.size - 1, _lib.ptr(tg),
+                                         float(tau) if tau is not None else -1.0, float(tol), int(maxit), _lib.ptr(out),
+                                         ctypes.byref(done))
+        if rc == _lib.SB_ERR_CONVERGENCE:
+            raise ConvergenceFailed("convergence failed")
+        _lib.check(rc)
+        return out
+
     def _get(self, fn, dtype):
         out = np.empty(self.B, dtype=dtype)
         _lib.check(fn(self._h, _lib.ptr(out)))
@@ -970,8 +990,8 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
         u = u[:, :, 0] if npde == 1 else np.transpose(u, (0, 2, 1))
         return u[0] if squeeze else u
 
-    dev.upload(inival)
     if stationary:
+        dev.upload(inival)
         dev.mass_flags(1.0, stationary=True)
         hist = newton_stat(pb, np.inf, 1.0, params.tol, params.maxit, params.hist, c_loop)   # src/pdepe.jl:180
         u = dev.download()
@@ -1005,18 +1025,22 @@ def pdepe(m, pdefun, icfun, bdfun, xmesh, tspan=None, *, params=None, ctx=None, 
     else:
         timeSteps, tau = time_grid(tspan, params.tstep)        # src/pdepe.jl:82-85
         t0 = timeSteps[0]
-    dev.mass_flags(t0)                                         # src/pdepe.jl:78-79
     nsteps = timeSteps.shape[-1] - 1
     storage = []
     whole = (per_instance or (c_loop and not params.hist)) and nsteps >= 1 and dev.design == "resident" and not dev.longmesh()
     if per_instance and not whole:
         raise ValueError("per-instance time grids need the resident design and a mesh in the batched range")
+    pipelined = whole and save != "all" and not per_instance
+    if not pipelined:
+        dev.upload(inival)
+        dev.mass_flags(t0)                                     # src/pdepe.jl:78-79
     if whole:
         # the time loop of src/pdepe.jl:90-108 in one launch (sb_solve_steps_opt); with save="all" every state is
         # written by the kernel and streamed to pinned host memory round by round while later rounds compute
-        if save != "all" and not per_instance:
-            # only u(t_end): finished rounds of instances travel to the host while later rounds compute
-            results = [shape(dev.solve_steps_final(timeSteps, tau, params.tol, params.maxit))]
+        if pipelined:
+            # only u(t_end) is wanted: upload, mass flags, solve and download as one pipelined operation -- instances
+            # are uploaded while earlier ones iterate, finished rounds travel back while later ones iterate
+            results = [shape(dev.solve_from_host(inival, t0, timeSteps, tau, params.tol, params.maxit))]
         else:
             snaps = pinned_empty((nsteps + 1, B, Nx, npde)) if save == "all" else None
             dev.solve_steps_opt(None if per_instance else timeSteps, tau, params.tol, params.maxit, snapshots=snaps,

@@ -342,6 +342,11 @@ struct sb_problem {
     bool top_configured = false;
     double *d_lm = nullptr, *d_partial = nullptr;
     double* h_prm = nullptr;   // pinned staging of the parameter blocks (sb_problem_set_params)
+    // pipelined upload (sb_solve_from_host): boundary nodes of every instance (pinned / device), chunk-arrival word and the
+    // pinned values that are copied into it, epoch of the words (they only ever grow, so a stale word never satisfies a wait)
+    double *h_bnd = nullptr, *d_bnd = nullptr;
+    unsigned int *d_ready = nullptr, *h_ready_vals = nullptr;
+    unsigned int ready_epoch = 0;
     int* d_auto = nullptr;              // device-side stepping: {time step, iteration} (sb_solve_steps)
     double* d_tgrid = nullptr;          // its time grid
     int tgrid_cap = 0;
@@ -1134,6 +1139,9 @@ int sb_problem_destroy(sb_problem* pb) {
     guarded_free(pb->d_iters); guarded_free(pb->d_status); guarded_free(pb->d_total); guarded_free(pb->d_count); guarded_free(pb->d_ckpt); guarded_free(pb->d_list); guarded_free(pb->d_lm); guarded_free(pb->d_partial); guarded_free(pb->d_auto); guarded_free(pb->d_tgrid); guarded_free(pb->d_uin); guarded_free(pb->d_eval); guarded_free(pb->d_piv); guarded_free(pb->d_piv_lock); guarded_free(pb->d_itgrid); guarded_free(pb->d_step_iters); guarded_free(pb->d_snap); guarded_free(pb->d_rmisc);
     if (pb->h_rounds) cudaFreeHost(pb->h_rounds);
     if (pb->h_prm) cudaFreeHost(pb->h_prm);
+    if (pb->h_bnd) cudaFreeHost(pb->h_bnd);
+    if (pb->h_ready_vals) cudaFreeHost(pb->h_ready_vals);
+    guarded_free(pb->d_bnd); guarded_free(pb->d_ready);
     if (pb->copy_stream) cudaStreamDestroy(pb->copy_stream);
     if (pb->prof_ev_ok) for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(pb->evA[i]); cudaEventDestroy(pb->evM[i]); cudaEventDestroy(pb->evB[i]); }
     if (pb->h_count) cudaFreeHost(pb->h_count);
@@ -1227,7 +1235,7 @@ int sb_mass_flags(sb_problem* pb, double t0, int stationary) {
     pb->b_ready = false;
     { int rc = materialize_begin(pb); if (rc) return rc; }
     const int bs = 128;
-    CU(launch_any(pb->ks.mass, dim3((unsigned)((pb->pd.B + bs - 1) / bs)), dim3(bs), 0, pb->ctx->stream, pb->pd, t0, pb->d_mass, stationary));
+    CU(launch_any(pb->ks.mass, dim3((unsigned)((pb->pd.B + bs - 1) / bs)), dim3(bs), 0, pb->ctx->stream, pb->pd, t0, pb->d_mass, stationary, (const double*)nullptr));
     CU(cudaGetLastError());
     pb->mass_ready = true;
     return SB_OK;
@@ -1617,7 +1625,7 @@ static int grow(T** p, size_t* cap, size_t need, cudaStream_t st) {
 // instances leave for the host while later rounds compute
 static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const double* inst_tgrid, double tau, double t_single,
                           double inv_tau_single, double tol, int maxit, int32_t* step_iters_host, double* snap_host,
-                          int* steps_done, int* max_iters_out, bool final_only = false) {
+                          int* steps_done, int* max_iters_out, bool final_only = false, const double* u0_host = nullptr) {
     cudaStream_t st = pb->ctx->stream;
     const ProbDev& pd = pb->pd;
     const int64_t B = pd.B;
@@ -1686,6 +1694,33 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         ra.round_done = pb->d_rmisc + 4;
         ra.host_rounds = d_h;
     }
+    constexpr int kMaxChunks = 4096;
+    if (u0_host) {
+        // The initial states travel chunk by chunk on the copy stream, each chunk followed by its arrival word, and ALL of
+        // it is enqueued BEFORE the launch: once the kernel runs (it may hold every SM while it waits for a chunk) nothing
+        // it waits for depends on this or any other host thread making progress -- copy engines need neither an SM nor a
+        // driver lock that a synchronising call of another thread (cudaFree, cudaMalloc ...) could be holding.
+        int64_t chunk = std::max<int64_t>(1, (int64_t)((1u << 20) / (row * sizeof(double))));          // about 1 MB per chunk
+        if ((B + chunk - 1) / chunk > kMaxChunks) chunk = (B + kMaxChunks - 1) / kMaxChunks;
+        const int nchunks = (int)((B + chunk - 1) / chunk);
+        if (!pb->d_ready) {
+            CU(guarded_malloc((void**)&pb->d_ready, 4 * sizeof(unsigned int)));
+            CU(cudaHostAlloc((void**)&pb->h_ready_vals, kMaxChunks * sizeof(unsigned int), cudaHostAllocDefault));
+            CU(cudaMemsetAsync(pb->d_ready, 0, 4 * sizeof(unsigned int), st));
+            CU(cudaStreamSynchronize(st));
+        }
+        if (!pb->copy_stream) CU(cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking));
+        int rc = ensure_tmp(pb, (size_t)B * row);
+        if (rc) return rc;
+        ra.u_ref = pb->d_tmp; ra.ready = pb->d_ready; ra.ready_base = pb->ready_epoch; ra.chunk = (int)chunk;
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t k0 = (int64_t)c * chunk, nk = std::min<int64_t>(chunk, B - k0);
+            pb->h_ready_vals[c] = pb->ready_epoch + (unsigned int)c + 1u;
+            CU(cudaMemcpyAsync(pb->d_tmp + (size_t)k0 * row, u0_host + (size_t)k0 * row, (size_t)nk * row * sizeof(double), cudaMemcpyHostToDevice, pb->copy_stream));
+            CU(cudaMemcpyAsync(pb->d_ready, pb->h_ready_vals + c, sizeof(unsigned int), cudaMemcpyHostToDevice, pb->copy_stream));
+        }
+        pb->ready_epoch += (unsigned int)nchunks + 1u;
+    }
     if (pb->prof) CU(cudaEventRecord(pb->evA[0], st));
     CU(launch_any(pb->ks.resident, dim3((unsigned)pb->r_grid), dim3(threads), pb->ks.resident_smem, st, pb->pd, ra));
     CU(cudaGetLastError());
@@ -1721,6 +1756,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
             CU(cudaMemcpy(snap_host + off, pb->d_snap + off, ((size_t)(s1 + 1 - s0) * B * row) * sizeof(double), cudaMemcpyDeviceToHost));
         }
     }
+    if (u0_host) CU(cudaStreamSynchronize(pb->copy_stream));   // (the pinned words and the caller's buffer are free again)
     unsigned int res[4];
     CU(cudaMemcpyAsync(res, pb->d_rmisc, sizeof res, cudaMemcpyDeviceToHost, st));
     if (step_iters_host)
@@ -1887,6 +1923,44 @@ int sb_solve_steps_final(sb_problem* pb, int nsteps, const double* tgrid, double
     CU(cudaSetDevice(pb->ctx->device));
     pb->design = pb->design_pending;
     return solve_resident(pb, nsteps, tgrid, nullptr, tau, 0.0, 0.0, tol, maxit, nullptr, final_state, steps_done, nullptr, true);
+}
+
+int sb_solve_from_host(sb_problem* pb, const double* u0_host, double t0, int nsteps, const double* tgrid, double tau, double tol,
+                       int maxit, double* final_state, int* steps_done) {
+    if (!pb || !u0_host || !tgrid || !final_state || nsteps < 1) return fail(SB_ERR_INVALID, "NULL argument or nsteps < 1");
+    if (steps_done) *steps_done = 0;
+    if (maxit < 1) return fail(SB_ERR_INVALID, "maxit must be >= 1");
+    if (pb->longmesh) return fail(SB_ERR_UNSUPPORTED, "sb_solve_from_host: the long-mesh path has no whole-solve kernel");
+    if (!resident_enabled(pb)) return fail(SB_ERR_UNSUPPORTED, "sb_solve_from_host needs the resident design (whole-solve kernel)");
+    if (pb->pd.hist && nsteps > 1) return fail(SB_ERR_UNSUPPORTED, "norm histories are kept per step: drive the steps one by one with hist enabled");
+    CU(cudaSetDevice(pb->ctx->device));
+    pb->design = pb->design_pending;
+    cudaStream_t st = pb->ctx->stream;
+    const int P = pb->P, Nx = pb->pd.Nx;
+    const int64_t B = pb->pd.B;
+    // what sb_state_upload resets
+    pb->b_ready = false; pb->lazy_pending = false; pb->pd.lazy_b = 0;
+    CU(cudaMemsetAsync(pb->d_total, 0, B * sizeof(long long), st));
+    CU(cudaMemsetAsync(pb->d_status, 0, B * sizeof(int), st));
+    // mass flags (src/pdepe.jl:78-79) need nodes 0, 1 and Nx-1 of every instance only: those go ahead of the states
+    const size_t nb = (size_t)B * 3 * P;
+    if (!pb->h_bnd) {
+        CU(cudaHostAlloc((void**)&pb->h_bnd, nb * sizeof(double), cudaHostAllocDefault));
+        CU(guarded_malloc((void**)&pb->d_bnd, nb * sizeof(double)));
+    }
+    const size_t row = (size_t)Nx * P;
+    for (int64_t k = 0; k < B; ++k)
+        for (int p = 0; p < P; ++p) {
+            pb->h_bnd[((size_t)k * 3 + 0) * P + p] = u0_host[(size_t)k * row + p];
+            pb->h_bnd[((size_t)k * 3 + 1) * P + p] = u0_host[(size_t)k * row + P + p];
+            pb->h_bnd[((size_t)k * 3 + 2) * P + p] = u0_host[(size_t)k * row + (size_t)(Nx - 1) * P + p];
+        }
+    CU(cudaMemcpyAsync(pb->d_bnd, pb->h_bnd, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int bs = 128;
+    CU(launch_any(pb->ks.mass, dim3((unsigned)((B + bs - 1) / bs)), dim3(bs), 0, st, pb->pd, t0, pb->d_mass, 0, (const double*)pb->d_bnd));
+    CU(cudaGetLastError());
+    pb->mass_ready = true;
+    return solve_resident(pb, nsteps, tgrid, nullptr, tau, 0.0, 0.0, tol, maxit, nullptr, final_state, steps_done, nullptr, true, u0_host);
 }
 
 #define SB_GET(NAME, TYPE, DEVPTR)                                                                       \

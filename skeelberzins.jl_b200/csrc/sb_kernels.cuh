@@ -1560,7 +1560,7 @@ k_newton_fused_p(ProbDev pd, double tt, double inv_tau, double tol, int slot,
 // K2: mass flags (mass_matrix, src/assembler.jl:138-174), one thread per instance
 // ---------------------------------------------------------------------------------------------
 template <class Fn>
-__global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary) {
+__global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary, const double* bnd) {
     constexpr int P = Fn::npde;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= pd.B) return;
@@ -1576,9 +1576,13 @@ __global__ void k_mass_flags(ProbDev pd, double t0, double* mass, int stationary
     auto slot_of = [&](int i) { const int tile = i / Lt, il = i - tile * Lt; return tile * Lt + (il % R) * T + il / R; };
     double u0[P], u1[P], uN[P];
     for (int p = 0; p < P; ++p) {
-        u0[p] = ub[(size_t)slot_of(0) * P + p];
-        u1[p] = ub[(size_t)slot_of(1) * P + p];
-        uN[p] = ub[(size_t)slot_of(Nx - 1) * P + p];
+        if (bnd) {   // [B][3][P]: nodes 0, 1 and Nx-1 of every instance, gathered by the host (the state itself is still on its way)
+            u0[p] = bnd[((size_t)k * 3 + 0) * P + p]; u1[p] = bnd[((size_t)k * 3 + 1) * P + p]; uN[p] = bnd[((size_t)k * 3 + 2) * P + p];
+        } else {
+            u0[p] = ub[(size_t)slot_of(0) * P + p];
+            u1[p] = ub[(size_t)slot_of(1) * P + p];
+            uN[p] = ub[(size_t)slot_of(Nx - 1) * P + p];
+        }
     }
     Dual<0> ul_[P], ur_[P], pl[P], pr[P];
     double ql[P], qr[P];

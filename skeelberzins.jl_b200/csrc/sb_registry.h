@@ -30,7 +30,7 @@ typedef void (*FusedKernel)(ProbDev, double, double, double, int);
 typedef void (*FusedPKernel)(ProbDev, double, double, double, int, int, int);
 typedef void (*SolveKernel)(ProbDev, double, int, int);
 typedef void (*ResidentKernel)(ProbDev, ResidentArgs);
-typedef void (*MassKernel)(ProbDev, double, double*, int);
+typedef void (*MassKernel)(ProbDev, double, double*, int, const double*);
 typedef void (*LongChunkKernel)(ProbDev, double, double, LevelDev);
 typedef void (*LongBackKernel)(ProbDev, double, double, LevelDev, double*);
 

@@ -33,6 +33,12 @@ struct ResidentArgs {
     int snap_last;                  // snap holds ONE state per instance, [B][Nx*P]: u(t_end) only (streamed out like the snapshots)
     unsigned int* round_done;       // [rounds] instances finished per round of the grid (snapshot streaming), or null
     volatile unsigned int* host_rounds;   // [rounds] mapped host flags: round complete
+    // pipelined upload (sb_solve_from_host): the initial states arrive in u_ref, reference layout [B][Nx*P], chunk by chunk of
+    // `chunk` instances while the kernel already runs; *ready >= ready_base + c + 1 once chunk c has landed
+    const double* u_ref;
+    const volatile unsigned int* ready;
+    unsigned int ready_base;
+    int chunk;
     int* fail_step;                 // [1] smallest step index in which an instance failed to converge (init INT_MAX)
     int* max_iters;                 // [1] largest iteration count of a step (sb_newton_solve reports it)
     unsigned long long* sum_iters;  // [1] Newton iterations summed over instances and steps (the work counter)
@@ -116,7 +122,23 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
         if (t < NPS) pbuf[t] = pd.prm[(size_t)k * NPS + t];
         if (t < 4 * P) mbuf[t] = pd.mass[(size_t)k * 4 * P + t];
         double uc[R][P];
-        load_chunk<P, R, TT>((ra.b_given ? pd.b : pd.u) + (size_t)k * L * P, t, uc);
+        if (ra.u_ref) {
+            if (t == 0) {
+                const unsigned int need = ra.ready_base + (unsigned int)(k / ra.chunk) + 1u;
+                while ((int)(*ra.ready - need) < 0) __nanosleep(200);     // copy engines need no SM: this always ends
+                __threadfence();
+            }
+            group_sync<TT>(bar);
+            const double* src = ra.u_ref + (size_t)k * Nx * P;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = t * R + r;
+#pragma unroll
+                for (int p = 0; p < P; ++p) uc[r][p] = (i < Nx) ? __ldcg(src + (size_t)i * P + p) : 0.0;
+            }
+        } else {
+            load_chunk<P, R, TT>((ra.b_given ? pd.b : pd.u) + (size_t)k * L * P, t, uc);
+        }
         const double* tg = ra.inst_tgrid ? ra.inst_tgrid + (size_t)k * (nsteps + 1) : ra.tgrid;
         auto snapshot = [&](int s) {   // reference layout: node-major, components fastest; a thread's rows are contiguous
             double* dst = ra.snap + ((size_t)s * pd.B + k) * Nx * P;

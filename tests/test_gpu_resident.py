@@ -251,11 +251,12 @@ def test_devices_argument_shards_the_batch(ctx, oracle):
     assert np.array_equal(last.u[-1], one.u[-1])
 
 
-@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 3000, 64, 4), ("4", 900, 100, 5), ("3a", 40, 512, 6)])
+@pytest.mark.parametrize("cfg,B,Nx,nsteps", [("2", 3000, 64, 4), ("4", 900, 100, 5), ("3a", 40, 512, 6), ("2", 700, 1024, 3)])
 def test_final_state_streamed_out_during_the_solve(ctx, cfg, B, Nx, nsteps):
     """sb_solve_steps_final: u(t_end) arrives in host memory round by round of instances while later rounds compute
     (3000 instances of 64 nodes are several rounds of the persistent grid); bit-identical to a solve followed by a
-    download, which is also what the device state holds afterwards, and what pdepe(save="last", c_loop=True) returns."""
+    download, which is also what the device state holds afterwards, and what pdepe(save="last", c_loop=True) returns.
+    sb_solve_from_host pipelines the upload as well (chunks of about 1 MB: 2, 2, 1 and 6 chunks here): same bits."""
     c = ex.baseline_case(cfg, B=B, Nx=Nx)
     tg, tau = sb.time_grid(c.tspan, c.tstep)
     tg = tg[:nsteps + 1]
@@ -271,6 +272,13 @@ def test_final_state_streamed_out_during_the_solve(ctx, cfg, B, Nx, nsteps):
         out = dev.solve_steps_final(tg, None, 1e-10, 100)
         assert np.array_equal(out, ref)
         assert np.array_equal(dev.download(), ref)
+        for _ in range(2):                                    # (twice: the arrival words of the first call must not satisfy the second)
+            u0p = sb.api.pinned_empty((B, Nx, c.npde))
+            u0p[:] = c.initial()
+            out2 = dev.solve_from_host(u0p, tg[0], tg, None, 1e-10, 100)
+            assert np.array_equal(out2, ref)
+            assert np.array_equal(dev.download(), ref)
+        assert np.array_equal(dev.solve_from_host(np.array(c.initial()), tg[0], tg, None, 1e-10, 100), ref)   # pageable source
     finally:
         dev.close()
     sol = sb.pdepe(c.m, fn, c.icfun, fn, c.xmesh, (tg[0], tg[-1]), ctx=ctx, tstep=tg, squeeze=False, save="last", c_loop=True)
