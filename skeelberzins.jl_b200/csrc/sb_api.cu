@@ -62,6 +62,8 @@ std::atomic<long long> g_launches{0};  // kernels launched by this library (all 
 // cudaLaunchKernel.
 struct KernelSet {
     const void *mass = nullptr, *assemble_jac = nullptr, *assemble_val = nullptr, *fused = nullptr, *fused_p = nullptr, *resident = nullptr, *solve = nullptr;
+    const void* resident_pipe = nullptr;   // k_solve_resident<..., PIPE = true> (sb_solve_from_host)
+    bool pipe_configured = false;
     const void *long_chunk = nullptr, *long_back = nullptr, *long_assemble_jac = nullptr, *long_assemble_val = nullptr;
     size_t fused_p_smem = 0, long_smem = 0, resident_smem = 0;
     bool long_configured = false, small_configured = false;
@@ -576,6 +578,7 @@ int nvrtc_user_kernels(const UserFunctor& uf, int R, int TT, bool sym0, bool lon
     name("sb::k_newton_fused_p<%s, %d, %d, %s>");
     name("sb::k_solve_resident<%s, %d, %d, %s>");
     snprintf(buf, sizeof buf, "sb::k_solve<%d, %d, %d>", uf.npde, R, TT); names.push_back(buf);
+    name("sb::k_solve_resident_pipe<%s, %d, %d, %s>");
     if (longmesh && uf.npde == 1) {
         name("sb::k6_chunk_asm<%s, %d, %d, %s>");
         name("sb::k6_back_asm<%s, %d, %d, %s>");
@@ -647,7 +650,7 @@ int compile_user_kernels(sb_problem* pb, const UserFunctor& uf) {
     KernelSet& ks = pb->ks;
     cudaError_t e = cudaLibraryLoadData(&ks.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) return fail(SB_ERR_PLUGIN, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
-    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p, &ks.resident, &ks.solve,
+    const void** slots[] = {&ks.mass, &ks.assemble_jac, &ks.assemble_val, &ks.fused, &ks.fused_p, &ks.resident, &ks.solve, &ks.resident_pipe,
                             &ks.long_chunk, &ks.long_back, &ks.long_assemble_jac, &ks.long_assemble_val};
     for (size_t i = 0; i < lowered.size(); ++i) {
         cudaKernel_t kern;
@@ -1111,6 +1114,7 @@ int sb_problem_create(sb_ctx* ctx, int m, int Nx, int64_t B, const double* xmesh
         ks.fused_p = (const void*)fe->fused_p[pb->dec][pb->sym0];
         ks.fused_p_smem = fe->fused_p_smem[pb->dec][pb->sym0];
         ks.resident = (const void*)fe->resident[pb->dec][pb->sym0];
+        ks.resident_pipe = (const void*)fe->resident_pipe[pb->dec][pb->sym0];
         ks.solve = (const void*)solve_kernel(pb->P, pb->dec);
         ks.resident_smem = fe->resident_smem[pb->dec][pb->sym0];
         ks.long_chunk = (const void*)fe->long_chunk[pb->sym0];
@@ -1695,6 +1699,8 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         ra.host_rounds = d_h;
     }
     constexpr int kMaxChunks = 4096;
+    ResidentPipe rp;
+    memset(&rp, 0, sizeof rp);
     if (u0_host) {
         // The initial states travel chunk by chunk on the copy stream, each chunk followed by its arrival word, and ALL of
         // it is enqueued BEFORE the launch: once the kernel runs (it may hold every SM while it waits for a chunk) nothing
@@ -1712,7 +1718,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         if (!pb->copy_stream) CU(cudaStreamCreateWithFlags(&pb->copy_stream, cudaStreamNonBlocking));
         int rc = ensure_tmp(pb, (size_t)B * row);
         if (rc) return rc;
-        ra.u_ref = pb->d_tmp; ra.ready = pb->d_ready; ra.ready_base = pb->ready_epoch; ra.chunk = (int)chunk;
+        rp.u_ref = pb->d_tmp; rp.ready = pb->d_ready; rp.ready_base = pb->ready_epoch; rp.chunk = (int)chunk;
         for (int c = 0; c < nchunks; ++c) {
             const int64_t k0 = (int64_t)c * chunk, nk = std::min<int64_t>(chunk, B - k0);
             pb->h_ready_vals[c] = pb->ready_epoch + (unsigned int)c + 1u;
@@ -1722,11 +1728,24 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         pb->ready_epoch += (unsigned int)nchunks + 1u;
     }
     if (pb->prof) CU(cudaEventRecord(pb->evA[0], st));
-    CU(launch_any(pb->ks.resident, dim3((unsigned)pb->r_grid), dim3(threads), pb->ks.resident_smem, st, pb->pd, ra));
+    const void* kern = pb->ks.resident;
+    if (u0_host) {
+        kern = pb->ks.resident_pipe;
+        if (!pb->ks.pipe_configured) {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->ks.resident_smem));
+            pb->ks.pipe_configured = true;
+        }
+    }
+    if (u0_host) CU(launch_any(kern, dim3((unsigned)pb->r_grid), dim3(threads), pb->ks.resident_smem, st, pb->pd, ra, rp));
+    else CU(launch_any(kern, dim3((unsigned)pb->r_grid), dim3(threads), pb->ks.resident_smem, st, pb->pd, ra));
     CU(cudaGetLastError());
     if (pb->prof) CU(cudaEventRecord(pb->evB[0], st));
     // from here on the state is what the kernel leaves: u = u(t_end), b unspecified
     pb->b_ready = false; pb->lazy_pending = false; pb->pd.lazy_b = 0; pb->step_all_tma = false;
+    // the per-iteration launches of an earlier step keep their ring slots (a slot is cleaned only kSlots/2 launches
+    // later): the ring position moves past them before the counter of the step is cleared, exactly as sb_begin_step does
+    // -- a pooled problem that went host loop -> whole-solve kernel -> host loop reused uncleaned slots otherwise
+    pb->slot_base = pb->slot_of(pb->launched);
     pb->launched = 0; pb->confirmed = 0;
 
     if (snap_host) {

@@ -30,6 +30,7 @@ typedef void (*FusedKernel)(ProbDev, double, double, double, int);
 typedef void (*FusedPKernel)(ProbDev, double, double, double, int, int, int);
 typedef void (*SolveKernel)(ProbDev, double, int, int);
 typedef void (*ResidentKernel)(ProbDev, ResidentArgs);
+typedef void (*ResidentPipeKernel)(ProbDev, ResidentArgs, ResidentPipe);
 typedef void (*MassKernel)(ProbDev, double, double*, int, const double*);
 typedef void (*LongChunkKernel)(ProbDev, double, double, LevelDev);
 typedef void (*LongBackKernel)(ProbDev, double, double, LevelDev, double*);
@@ -43,6 +44,7 @@ struct FunctorEntry {
     FusedPKernel fused_p[kNumDecomp][2];      // persistent TMA-prefetch variant
     size_t fused_p_smem[kNumDecomp][2];       // its dynamic shared memory (bytes)
     ResidentKernel resident[kNumDecomp][2];   // whole solve in one launch (sb_resident.cuh)
+    ResidentPipeKernel resident_pipe[kNumDecomp][2];   // ... whose instances wait for the pipelined upload (sb_solve_from_host)
     size_t resident_smem[kNumDecomp][2];
     MassKernel mass;
     // long-mesh path (scalar PDEs): [SYM0]
@@ -68,12 +70,14 @@ void fill_one(FunctorEntry& e) {
         e.fused_p_smem[D][1] = FusedPLayout<Fn, R, TT, true>::bytes;
         e.resident[D][0] = k_solve_resident<Fn, R, TT, false>;
         e.resident[D][1] = k_solve_resident<Fn, R, TT, true>;
+        e.resident_pipe[D][0] = k_solve_resident_pipe<Fn, R, TT, false>;
+        e.resident_pipe[D][1] = k_solve_resident_pipe<Fn, R, TT, true>;
         e.resident_smem[D][0] = ResidentLayout<Fn, R, TT, false>::bytes;
         e.resident_smem[D][1] = ResidentLayout<Fn, R, TT, true>::bytes;
     } else {
         for (int s = 0; s < 2; ++s) {
             e.assemble_jac[D][s] = nullptr; e.assemble_val[D][s] = nullptr; e.fused[D][s] = nullptr;
-            e.fused_p[D][s] = nullptr; e.fused_p_smem[D][s] = 0; e.resident[D][s] = nullptr; e.resident_smem[D][s] = 0;
+            e.fused_p[D][s] = nullptr; e.fused_p_smem[D][s] = 0; e.resident[D][s] = nullptr; e.resident_pipe[D][s] = nullptr; e.resident_smem[D][s] = 0;
         }
     }
 }

@@ -33,12 +33,6 @@ struct ResidentArgs {
     int snap_last;                  // snap holds ONE state per instance, [B][Nx*P]: u(t_end) only (streamed out like the snapshots)
     unsigned int* round_done;       // [rounds] instances finished per round of the grid (snapshot streaming), or null
     volatile unsigned int* host_rounds;   // [rounds] mapped host flags: round complete
-    // pipelined upload (sb_solve_from_host): the initial states arrive in u_ref, reference layout [B][Nx*P], chunk by chunk of
-    // `chunk` instances while the kernel already runs; *ready >= ready_base + c + 1 once chunk c has landed
-    const double* u_ref;
-    const volatile unsigned int* ready;
-    unsigned int ready_base;
-    int chunk;
     int* fail_step;                 // [1] smallest step index in which an instance failed to converge (init INT_MAX)
     int* max_iters;                 // [1] largest iteration count of a step (sb_newton_solve reports it)
     unsigned long long* sum_iters;  // [1] Newton iterations summed over instances and steps (the work counter)
@@ -53,6 +47,18 @@ __host__ __device__ constexpr int resident_min_blocks(int TT, int P) {
     const int threads = resident_groups(TT) * TT;
     return (32 * warps) / threads > 0 ? (32 * warps) / threads : 1;
 }
+
+// pipelined upload (sb_solve_from_host): the initial states arrive in u_ref, reference layout [B][Nx*P], chunk by chunk of
+// `chunk` instances while the kernel already runs; *ready >= ready_base + c + 1 once chunk c has landed.  A kernel
+// argument of its own (and a kernel of its own, k_solve_resident_pipe): adding these fields and the branch that uses them
+// to the headline kernel cost it 1.7 % (12.40 -> 12.61 ms per cfg2 solve) although the code runs once per instance --
+// the register allocation of everything after it changed.
+struct ResidentPipe {
+    const double* u_ref;
+    const volatile unsigned int* ready;
+    unsigned int ready_base;
+    int chunk;
+};
 
 template <class Fn, int R, int TT, bool SYM0>
 struct ResidentLayout {  // shared-memory carve-up (offsets in doubles)
@@ -70,9 +76,8 @@ struct ResidentLayout {  // shared-memory carve-up (offsets in doubles)
     static constexpr size_t bytes = sizeof(double) * (size_t)(mesh_doubles + G * group_doubles);
 };
 
-template <class Fn, int R, int TT, bool SYM0>
-__global__ void __launch_bounds__(resident_groups(TT) * TT, resident_min_blocks(TT, Fn::npde))
-k_solve_resident(ProbDev pd, ResidentArgs ra) {
+template <class Fn, int R, int TT, bool SYM0, bool PIPE>
+SB_D void resident_body(const ProbDev& pd, const ResidentArgs& ra, const ResidentPipe& rp) {
     using LY = ResidentLayout<Fn, R, TT, SYM0>;
     constexpr int P = LY::P, L = LY::L, G = LY::G, NPS = LY::NPS;
     extern __shared__ __align__(16) double smr[];
@@ -121,24 +126,26 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
         // ---- the instance comes on chip --------------------------------------------------------------------------
         if (t < NPS) pbuf[t] = pd.prm[(size_t)k * NPS + t];
         if (t < 4 * P) mbuf[t] = pd.mass[(size_t)k * 4 * P + t];
-        double uc[R][P];
-        if (ra.u_ref) {
+        if constexpr (PIPE) {
+            // pipelined upload: wait for the instance's chunk, then bring its rows from the reference layout into the
+            // device layout (every thread moves the rows it owns, so the load below reads what this thread wrote).  Kept
+            // apart from the load so that the code after it is the same with and without the pipeline.
             if (t == 0) {
-                const unsigned int need = ra.ready_base + (unsigned int)(k / ra.chunk) + 1u;
-                while ((int)(*ra.ready - need) < 0) __nanosleep(200);     // copy engines need no SM: this always ends
+                const unsigned int need = rp.ready_base + (unsigned int)(k / rp.chunk) + 1u;
+                while ((int)(*rp.ready - need) < 0) __nanosleep(200);     // copy engines need no SM: this always ends
                 __threadfence();
             }
             group_sync<TT>(bar);
-            const double* src = ra.u_ref + (size_t)k * Nx * P;
-#pragma unroll
+            const double* src = rp.u_ref + (size_t)k * Nx * P;
+            double* dst = pd.u + (size_t)k * L * P;
+#pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 const int i = t * R + r;
-#pragma unroll
-                for (int p = 0; p < P; ++p) uc[r][p] = (i < Nx) ? __ldcg(src + (size_t)i * P + p) : 0.0;
+                for (int p = 0; p < P; ++p) dst[(size_t)(r * TT + t) * P + p] = (i < Nx) ? __ldcg(src + (size_t)i * P + p) : 0.0;
             }
-        } else {
-            load_chunk<P, R, TT>((ra.b_given ? pd.b : pd.u) + (size_t)k * L * P, t, uc);
         }
+        double uc[R][P];
+        load_chunk<P, R, TT>((ra.b_given ? pd.b : pd.u) + (size_t)k * L * P, t, uc);
         const double* tg = ra.inst_tgrid ? ra.inst_tgrid + (size_t)k * (nsteps + 1) : ra.tgrid;
         auto snapshot = [&](int s) {   // reference layout: node-major, components fastest; a thread's rows are contiguous
             double* dst = ra.snap + ((size_t)s * pd.B + k) * Nx * P;
@@ -273,6 +280,21 @@ k_solve_resident(ProbDev pd, ResidentArgs ra) {
         }
         group_sync<TT>(bar);               // the tiles, parameters and flags are rewritten by the next instance
     }
+}
+
+template <class Fn, int R, int TT, bool SYM0>
+__global__ void __launch_bounds__(resident_groups(TT) * TT, resident_min_blocks(TT, Fn::npde))
+k_solve_resident(ProbDev pd, ResidentArgs ra) {
+    ResidentPipe none;
+    none.u_ref = nullptr; none.ready = nullptr; none.ready_base = 0u; none.chunk = 1;
+    resident_body<Fn, R, TT, SYM0, false>(pd, ra, none);
+}
+
+// the variant launched by sb_solve_from_host: every instance waits for its chunk of the pipelined upload
+template <class Fn, int R, int TT, bool SYM0>
+__global__ void __launch_bounds__(resident_groups(TT) * TT, resident_min_blocks(TT, Fn::npde))
+k_solve_resident_pipe(ProbDev pd, ResidentArgs ra, ResidentPipe rp) {
+    resident_body<Fn, R, TT, SYM0, true>(pd, ra, rp);
 }
 
 }  // namespace sb

@@ -285,3 +285,33 @@ def test_final_state_streamed_out_during_the_solve(ctx, cfg, B, Nx, nsteps):
     got = np.asarray(sol.u[-1])
     want = ref[:, :, 0] if c.npde == 1 else np.transpose(ref, (0, 2, 1))
     assert np.array_equal(got, want)
+
+
+def test_host_loops_after_a_whole_solve_on_the_same_problem(ctx):
+    """A problem (as the pool hands it out again) that goes host-owned loops -> whole-solve kernel -> host-owned loops: the
+    ring of completion counters of the per-iteration launches must move past the launches of the first phase when the
+    whole-solve kernel clears the step's launch counter (it did not: uncleaned slots never reported)."""
+    c = ex.baseline_case("2", B=40, Nx=512)
+    tg, _ = sb.time_grid(c.tspan, c.tstep)
+    tg = tg[:5]
+    dev = sb.DeviceProblem(ctx, c.m, c.xmesh, sb.Functor(c.functor, c.params))
+
+    def host_loops():
+        dev.upload(c.initial())
+        dev.mass_flags(tg[0])
+        for i in range(tg.size - 1):
+            dev.begin_step(tg[i + 1], 1.0 / (tg[i + 1] - tg[i]))
+            sb.api._newton_loop(dev, 1e-10, 100)
+        return dev.download().copy()
+
+    try:
+        a = host_loops()
+        dev.upload(c.initial())
+        dev.mass_flags(tg[0])
+        dev.solve_steps_opt(tg, None, 1e-10, 100)
+        assert np.array_equal(dev.download(), a)
+        for _ in range(3):
+            assert np.array_equal(host_loops(), a)
+            assert np.array_equal(dev.solve_from_host(c.initial(), tg[0], tg, None, 1e-10, 100), a)
+    finally:
+        dev.close()
