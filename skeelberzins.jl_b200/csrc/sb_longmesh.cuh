@@ -2,19 +2,24 @@
 //
 // The mesh is stored as tiles of R*TT nodes, each tile in the chunk-transposed layout of the batched path,
 // so an instance looks like a batch of coupled tiles.  One Newton iteration is a recursive partition
-// ("SPIKE") solve over levels:
+// ("SPIKE") solve over levels.  Scalar PDEs (the tuned path, four launches per iteration for up to 4096 tiles):
 //
-//   level 0   k6_chunk_asm   every thread assembles its R rows on the fly (residual + Jacobian by duals, nothing
-//                            but u, b and the mesh weights is read) and eliminates them -> 7 numbers per chunk
-//   level l   k6_chunk_sys   forms its rows (one per chunk of level l-1) from those numbers, keeps them for the way
-//                            back, eliminates them                                        -> level l+1 ...
+//   level 0   k6_chunk_asm   every thread assembles its R rows on the fly (residual + Jacobian by duals; m = 0: nothing
+//                            but u, b and the mesh points x is read, every weight is computed from x) and eliminates
+//                            them; the TT chunks of the tile are reduced inside the CTA (warp 0: TT/32 reduced rows per
+//                            lane, then an open cyclic reduction across its lanes) -> ONE row of the level above per
+//                            tile, and per chunk the three numbers that give its separator once the tile's two outer
+//                            separators are known
 //   top       k6_top         a single CTA forms and solves the last level (<= 4096 rows) with the batched-path solver
-//   level l   k6_back_sys    recompute the elimination, back-substitute with the separator values from level l+1
-//   level 0   k6_back_asm    recompute assembly + elimination, back-substitute, u -= h in place, per-tile sum of h^2
+//   level 0   k6_back_asm    recompute assembly + elimination, separators from those three numbers, back-substitute,
+//                            u -= h in place, per-tile sum of h^2 (no reduction, no barrier before the update)
 //             k6_finalize    ||h||_2 per instance in a fixed summation order, stop test, counters, host notice
 //
-// Recomputing instead of storing the block rows keeps the traffic at level 0 to two reads of (u, b, weights) and
-// one write of u per Newton iteration.  Scalar PDEs (npde = 1) only.
+// More tiles than the top level takes go through stored levels in between (k6_chunk_sys forms its rows, one per chunk of
+// the level below, keeps them for the way back and eliminates them; k6_back_sys recomputes the elimination and
+// back-substitutes).  Recomputing instead of storing the block rows keeps the traffic at level 0 to two reads of (u, b, x)
+// and one write of u per Newton iteration.  Systems (npde = 2, 3, 4): the block version at the end of this file (k6s_*),
+// one row of the level above per THREAD chunk, weights from the arrays.
 #pragma once
 #include "sb_kernels.cuh"
 #include "sb_resident.cuh"
