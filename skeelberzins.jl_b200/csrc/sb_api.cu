@@ -1706,7 +1706,7 @@ static int solve_resident(sb_problem* pb, int nsteps, const double* tgrid, const
         // it is enqueued BEFORE the launch: once the kernel runs (it may hold every SM while it waits for a chunk) nothing
         // it waits for depends on this or any other host thread making progress -- copy engines need neither an SM nor a
         // driver lock that a synchronising call of another thread (cudaFree, cudaMalloc ...) could be holding.
-        int64_t chunk = std::max<int64_t>(1, (int64_t)((1u << 20) / (row * sizeof(double))));          // about 1 MB per chunk
+        int64_t chunk = std::max<int64_t>(1, (int64_t)((2u << 20) / (row * sizeof(double))));          // about 2 MB per chunk: every chunk is two enqueue calls before the launch
         if ((B + chunk - 1) / chunk > kMaxChunks) chunk = (B + kMaxChunks - 1) / kMaxChunks;
         const int nchunks = (int)((B + chunk - 1) / chunk);
         if (!pb->d_ready) {

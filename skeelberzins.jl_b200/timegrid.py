@@ -8,6 +8,7 @@ element is the correctly rounded value of ``(start_n + i*step_n)/den`` -- e.g. e
 This module restates that construction so the Python host produces the same grid bit for bit.
 """
 from fractions import Fraction
+import functools
 import math
 
 import numpy as np
@@ -37,8 +38,13 @@ def _rat(x):
 
 
 def julia_range(start, step, stop):
-    """``collect(start:step:stop)`` for Float64 arguments."""
-    start, step, stop = float(start), float(step), float(stop)
+    """``collect(start:step:stop)`` for Float64 arguments (a fresh array; the exact-rational construction is cached per
+    argument triple: 65 us for 90 steps, 0.5 ms for 1000, on every pdepe() call of a parameter study otherwise)."""
+    return _julia_range(float(start), float(step), float(stop)).copy()
+
+
+@functools.lru_cache(maxsize=64)
+def _julia_range(start, step, stop):
     if step == 0:
         raise ValueError("range step cannot be zero")
     sn, sd = _rat(step)
