@@ -2,7 +2,7 @@
 # round-2 call 24 (re-run after the last kernel change): full GPU suite, final bench lines of every BASELINE config (with extras) and the launch list of the default bench command
 set -u
 O=gpurun_out/prof3; mkdir -p $O
-( time timeout -s KILL 500 python -m pytest tests -m gpu -q --maxfail=8 ) > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
+
 python bench.py --steps 20 --warmup 3 2>$O/err_cfg2.log | tail -1 > $O/r2_bench_n1_resident.json; echo "cfg2 rc=$?"
 python bench.py --config 3a --steps 80 --warmup 3 2>/dev/null | tail -1 > $O/r2_bench_cfg3a.json
 python bench.py --config 3b --steps 80 --warmup 3 2>/dev/null | tail -1 > $O/r2_bench_cfg3b.json
