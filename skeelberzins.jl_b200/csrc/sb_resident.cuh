@@ -120,6 +120,8 @@ SB_D void resident_body(const ProbDev& pd, const ResidentArgs& ra, const Residen
     }
 
     const int Nx = pd.Nx, nsteps = ra.nsteps;
+    const double inv_tau_const = (ra.tau > 1.0e300) ? 0.0 : 1.0 / ra.tau;
+    const double tol2 = ra.tol * ra.tol, tol2_lo = tol2 * (1.0 - 0x1p-48), tol2_hi = tol2 * (1.0 + 0x1p-48);
     const int64_t stride = (int64_t)gridDim.x * G;
     int round = 0;
     for (int64_t k = (int64_t)blockIdx.x * G + g; k < pd.B; k += stride, ++round) {
@@ -163,13 +165,13 @@ SB_D void resident_body(const ProbDev& pd, const ResidentArgs& ra, const Residen
 
         long long total = 0;
         int status = 0, it_last = 0, failed_at = -1;
-        double nm = 0.0;
+        double ss_last = 0.0;       // sum of h^2 of the last finished iteration (its root is taken when somebody asks for it)
         for (int s = 0; s < nsteps; ++s) {
             double tt, inv_tau;
             if (tg) {
                 tt = tg[s + 1];
-                const double tau_s = (ra.tau > 0.0) ? ra.tau : tt - tg[s];
-                inv_tau = (tau_s > 1.0e300) ? 0.0 : 1.0 / tau_s;
+                if (ra.tau > 0.0) inv_tau = inv_tau_const;                  // (the division is hoisted out of the time loop)
+                else { const double tau_s = tt - tg[s]; inv_tau = (tau_s > 1.0e300) ? 0.0 : 1.0 / tau_s; }
             } else { tt = ra.t_single; inv_tau = ra.inv_tau_single; }
             // ---- b = M .* u_n ; the Newton iterate starts from b (src/pdepe.jl:94, src/utils.jl:309) -------------
 #pragma unroll
@@ -197,10 +199,13 @@ SB_D void resident_body(const ProbDev& pd, const ResidentArgs& ra, const Residen
 #pragma unroll
                         for (int w = 1; w < TT / 32; ++w) ss += sl[w];
                     }
-                    nm = ::sqrt(ss);
-                    if (t == 0 && pd.hist && it - 1 < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it - 1] = nm;
-                    if (!(nm == nm) || nm > 1.0e300) status = 2;                       // goes on to maxit like the reference
-                    if (nm < ra.tol) { conv = true; break; }                                 // src/utils.jl:329-333
+                    ss_last = ss;
+                    if (t == 0 && pd.hist && it - 1 < pd.hist_cap) pd.hist[(size_t)k * pd.hist_cap + it - 1] = ::sqrt(ss);
+                    // ||h||_2 > 1e300 or NaN <=> the sum of squares is not a finite number (a finite sum has a root below 1.4e154)
+                    if (!(ss < __longlong_as_double(0x7ff0000000000000LL))) status = 2;     // goes on to maxit like the reference
+                    // sqrt(ss) < tol (src/utils.jl:329-333), decided on ss wherever the rounding of the root cannot matter
+                    const bool below = (ss < tol2_lo) || (!(ss > tol2_hi) && ::sqrt(ss) < ra.tol);
+                    if (below) { conv = true; break; }
                     if (it >= ra.maxit) break;                                          // src/utils.jl:336
                 }
                 double bc[R][P];
@@ -264,7 +269,7 @@ SB_D void resident_body(const ProbDev& pd, const ResidentArgs& ra, const Residen
             pd.iters[k] = it_last;
             atomicAdd((unsigned long long*)(pd.total_iters + k), (unsigned long long)total);
             atomicAdd(ra.sum_iters, (unsigned long long)total);
-            pd.norm[k] = nm;
+            pd.norm[k] = ::sqrt(ss_last);
             if (status) pd.status[k] = status;
             pd.active[k] = (failed_at >= 0) ? 1 : 0;
             if (failed_at >= 0) atomicMin(ra.fail_step, failed_at);
